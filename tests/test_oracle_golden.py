@@ -1,0 +1,57 @@
+"""Pins the CPU oracle (oracle/rbr_oracle.py) to outputs of the unmodified reference modules
+(tests/golden/*.npz, written by tests/golden/make_golden.py in the build container)."""
+import torch
+
+from conftest import Golden, grad_floor, rel_err
+from oracle import rbr_oracle as orc
+
+TOL = 1e-5   # fp32 tolerance stated by BASELINE.json north_star
+
+
+def test_oracle_matches_reference(golden: Golden):
+    pred, loss, grads = orc.loss_and_grads(golden.model, golden.params, golden.batch, golden.ratings)
+    assert rel_err(pred, golden.out["pred"]) < TOL
+    assert rel_err(loss, golden.out["loss"]) < TOL
+    assert set(grads) == set(golden.grads)
+    for k, g in golden.grads.items():
+        assert grads[k].shape == g.shape, k
+        assert rel_err(grads[k], g, grad_floor(k)) < 2e-5, k
+
+
+def test_oracle_aux_outputs():
+    g = Golden("deepconn_edge")
+    pred, aux = orc.deepconn_forward(g.params, *g.batch, return_aux=True)
+    assert rel_err(aux["u_rev_feats"], g.out["u_rev_feats"]) < TOL
+    assert rel_err(aux["i_rev_feats"], g.out["i_rev_feats"]) < TOL
+    # all-pad doc pools to relu(bias)  
+    bias = g.params["ngram.feature_layer.0.list_of_conv1d.0.bias"]
+    assert torch.allclose(aux["u_rev_feats"][0], torch.relu(bias), atol=1e-7)
+    n = Golden("narre_small")
+    p, us, is_ = orc.narre_forward(n.params, *n.batch)
+    assert rel_err(us, n.out["u_att_scores"]) < TOL and rel_err(is_, n.out["i_att_scores"]) < TOL
+    assert torch.allclose(us.sum(dim=1), torch.ones(us.shape[0], 1), atol=1e-6)
+
+
+def test_padding_row_gets_zero_grad(golden: Golden):
+    _, _, grads = orc.loss_and_grads(golden.model, golden.params, golden.batch, golden.ratings)
+    assert float(grads["word_embeddings.embedding.weight"][0].abs().max()) == 0.0
+
+
+def test_gather_is_bit_exact():
+    g = Golden("deepconn_small")
+    table = g.params["word_embeddings.embedding.weight"]
+    ids = g.batch[0]
+    out = orc.embedding_gather(table, ids)
+    assert torch.equal(out, torch.nn.functional.embedding(ids, table))
+    gr = torch.randn(*ids.shape, table.shape[1])
+    dense = orc.embedding_dense_grad(ids, gr, table.shape[0])
+    ref = torch.zeros_like(table).index_add_(0, ids.reshape(-1), gr.reshape(-1, table.shape[1]))
+    ref[0] = 0
+    assert rel_err(dense, ref) < 1e-6
+    assert torch.equal(orc.get_mask(ids), ids != 0)
+
+
+def test_first_argmax_tie_rule():
+    y = torch.tensor([[[1.0], [3.0], [3.0], [2.0]]])
+    vals, idx = orc.first_argmax_pool(y)
+    assert vals.item() == 3.0 and idx.item() == 1
