@@ -1,0 +1,153 @@
+/* rbr_b200.h — C-ABI of the B200-native (sm_100a) review-encoder hot path.
+ *
+ * The reference (H263/review-based-recommender) has no FFI of its own: its hot path is the
+ * PyTorch nn.Module code cited beside each entry point below (paths relative to the reference
+ * root).  Each function replaces the library calls those lines make on the GPU.  The host side
+ * (review-based-recommender_b200/*.py) binds this library with ctypes; INTEGRATION.md shows the
+ * stub a reference maintainer would add.
+ *
+ * Conventions:
+ *   - plain pointers and int64 sizes only; every data pointer is a DEVICE pointer unless named host_*;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*; NULL = legacy default
+ *     stream) and never synchronises the device, allocates or frees caller-visible memory;
+ *   - scratch memory is passed in (`ws`, `ws_bytes`) and sized by the matching *_workspace_bytes();
+ *   - return value: 0 = ok, negative = error (RBR_E*); rbr_last_error() gives a thread-local message;
+ *   - `*_grad` outputs are ACCUMULATED INTO (+=): the caller zero-fills them once per step
+ *     (this is what lets several launches and both document sides share one gradient buffer);
+ *   - token / id tensors are int64 row-major exactly as torch.LongTensor lays them out; masks are
+ *     1 byte per element (torch.bool); floats are fp32 row-major contiguous.
+ *   - there is no CPU implementation behind any of these symbols.
+ */
+#ifndef RBR_B200_H_
+#define RBR_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RBR_OK 0
+#define RBR_EINVAL (-1)      /* bad argument (null pointer, unsupported shape)            */
+#define RBR_ECUDA (-2)       /* a CUDA runtime call or kernel launch failed               */
+#define RBR_EWORKSPACE (-3)  /* workspace too small                                       */
+#define RBR_EUNSUPPORTED (-4)/* shape outside what the selected kernel variant supports   */
+
+/* precision of the conv contraction */
+#define RBR_PREC_FP32 0 /* fp32 CUDA-core implicit GEMM, matches the reference within 1e-5          */
+#define RBR_PREC_BF16 1 /* bf16 operands on tcgen05 tensor cores, fp32 accumulate in TMEM (1e-2)    */
+
+/* activation fused after the conv, before max-over-time */
+#define RBR_ACT_RELU 0 /* NgramFeat: nn.ReLU  (models/deepconn/layers.py:108)                       */
+#define RBR_ACT_TANH 1 /* D-ATT:     nn.Tanh  (models/dual_att/layers.py:39,69,73,77)               */
+
+int rbr_version(void);
+const char* rbr_last_error(void);
+/* Number of out-of-range token/id values seen by any kernel since the last call (they are treated as
+ * padding rows); synchronises `stream`.  The reference raises IndexError / a device assert instead. */
+int rbr_consume_oob_count(void* stream);
+
+/* ---- K1: embedding row gather -------------------------------------------------------------------
+ * Replaces nn.Embedding forward: WordEmbedding.forward, models/deepconn/layers.py:22-24
+ * (same code at models/narre/narre.py:22-24, models/dual_att/layers.py:21-23).
+ * out[t, :] = table[ids[t], :], bit-exact.                                                          */
+int rbr_gather_fwd(const float* table, int64_t vocab, int64_t emb, const int64_t* ids, int64_t n_tokens,
+                   float* out, void* stream);
+
+/* ---- K1b: dense embedding gradient (warp-segmented scatter-add) ----------------------------------
+ * Replaces aten::embedding_dense_backward, i.e. the autograd backward of layers.py:23.
+ * table_grad[ids[t], :] += grad_rows[t, :] for ids[t] != padding_idx (padding_idx < 0: no padding row). */
+int64_t rbr_embgrad_workspace_bytes(int64_t n_tokens, int64_t vocab);
+int rbr_embgrad_scatter_add(const int64_t* ids, const float* grad_rows, int64_t n_tokens, int64_t emb,
+                            int64_t vocab, int64_t padding_idx, float* table_grad, void* ws, int64_t ws_bytes,
+                            void* stream);
+
+/* ---- K0: bf16 shadow of the embedding table and packed conv weights (operand staging for K2) -----
+ * shadow[v, 0:emb_pad] = bf16(table[v, 0:emb]) zero-padded; emb_pad = rbr_emb_pad(emb).             */
+int64_t rbr_emb_pad(int64_t emb);
+int rbr_table_to_bf16(const float* table, int64_t vocab, int64_t emb, void* shadow_bf16, void* stream);
+/* Packed conv weights: one opaque buffer holding (a) fp32 [k][E][Hpad] for the fp32 conv, (b) fp32
+ * [H][k][E] for the backward, (c) bf16 K-major UMMA operand tiles for the tensor-core conv.
+ * weight is nn.Conv1d's [H, E, k] (models/deepconn/layers.py:44).                                    */
+int64_t rbr_conv_pack_bytes(int64_t emb, int64_t filters, int64_t ksize);
+int rbr_conv_pack(const float* weight, int64_t emb, int64_t filters, int64_t ksize, void* packed, void* stream);
+
+/* ---- K2: fused  mask → Conv1d(same padding) → activation → max-over-time --------------------------
+ * Replaces NgramFeat.forward, models/deepconn/layers.py:123-136 (masked_tensor utils.py:58-60,
+ * transpose, MyConv1d :54-58, nn.ReLU, nn.MaxPool1d(seq_len) :107-109) together with the embedding
+ * gather that feeds it (deepconn.py:43-47): the [N,L,E] activations are never materialised.
+ *   ids   [n_docs, doc_len] int64 token ids;  mask [n_docs, doc_len] bytes or NULL (NULL = all true)
+ *   table fp32 [vocab, emb] (RBR_PREC_FP32) — shadow_bf16 from rbr_table_to_bf16 (RBR_PREC_BF16)
+ *   pad   symmetric zero padding of the conv ((k-1)/2 for NgramFeat, 0 for D-ATT's global convs);
+ *         the pooled window is all doc_len + 2*pad - k + 1 output positions, padded tokens included
+ *   gate  optional fp32 multiplier applied to every (unmasked) token row before the conv:
+ *         gate_mode 0 = none, 1 = per token [n_docs, doc_len], 2 = per doc [n_docs]  (D-ATT gates)
+ *   feat  [n_docs, feat_ld] fp32, columns [0, filters) written;  argmax [n_docs, feat_ld] int32 with
+ *         the FIRST position attaining the max (nn.MaxPool1d tie rule).                               */
+int rbr_conv_act_maxpool_fwd(int precision, int activation, const void* table, const void* shadow_bf16,
+                             int64_t vocab, int64_t emb, const int64_t* ids, const uint8_t* mask,
+                             const float* gate, int gate_mode, int64_t n_docs, int64_t doc_len,
+                             const void* packed, const float* bias, int64_t filters, int64_t ksize,
+                             int64_t pad, float* feat, int32_t* argmax, int64_t feat_ld, void* stream);
+
+/* ---- K2b: arg-max-sparse backward of K2 ------------------------------------------------------------
+ * Replaces aten::convolution_backward + max_pool1d backward + relu backward + masked_fill backward +
+ * embedding_dense_backward (the autograd reverse of layers.py:123-136 and :23).  After max-over-time
+ * only ONE position per (doc, filter) carries gradient, so
+ *   weight_grad[h,:,j] += g[n,h] * x[n, t*+j-pad, :],  bias_grad[h] += g[n,h],
+ *   table_grad[ids[n, t*+j-pad], :] += g[n,h] * W[h,:,j]            (mask true, id != padding_idx)
+ * with g = feat_grad * act'(feat), t* = argmax[n,h].
+ * gate / gate_grad: as in the forward; gate_grad (same shape as gate) receives d loss / d gate.       */
+int64_t rbr_conv_bwd_workspace_bytes(int64_t n_docs, int64_t filters, int64_t ksize, int64_t emb, int64_t vocab);
+int rbr_conv_act_maxpool_bwd(int precision, int activation, const void* table, const void* shadow_bf16,
+                             int64_t vocab, int64_t emb, const int64_t* ids, const uint8_t* mask,
+                             const float* gate, int gate_mode, int64_t n_docs, int64_t doc_len,
+                             const void* packed, int64_t filters, int64_t ksize, int64_t pad,
+                             const float* feat, const int32_t* argmax, const float* feat_grad, int64_t feat_ld,
+                             int64_t padding_idx, float* weight_grad, float* bias_grad, float* table_grad,
+                             float* gate_grad, void* ws, int64_t ws_bytes, void* stream);
+
+/* ---- K3: fused NARRE review-level attention --------------------------------------------------------
+ * Replaces LinearAttention.forward, models/narre/narre.py:40-64 (dropout excluded: applied by the caller).
+ *   feat [B,R,H], other_id [B,R] int64, W_rv [H,A], W_id [A,A], h [A], b_1 [A], b_2 [1], ebd_vals [n_ids, A]
+ *   out [B,H], scores [B,R]                                                                           */
+int rbr_narre_attn_fwd(const float* feat, const int64_t* other_id, int64_t batch, int64_t reviews, int64_t hidden,
+                       int64_t att, const float* W_rv, const float* W_id, const float* h, const float* b_1,
+                       const float* b_2, const float* ebd_vals, int64_t n_ids, float* out, float* scores,
+                       void* stream);
+/* out_grad [B,H], scores_grad [B,R] or NULL → feat_grad [B,R,H] (written), parameter grads (+=).      */
+int rbr_narre_attn_bwd(const float* feat, const int64_t* other_id, int64_t batch, int64_t reviews, int64_t hidden,
+                       int64_t att, const float* W_rv, const float* W_id, const float* h, const float* b_1,
+                       const float* b_2, const float* ebd_vals, int64_t n_ids, int64_t padding_idx,
+                       const float* scores, const float* out_grad, const float* scores_grad, float* feat_grad,
+                       float* W_rv_grad, float* W_id_grad, float* h_grad, float* b_1_grad, float* b_2_grad,
+                       float* ebd_vals_grad, void* stream);
+
+/* ---- K4: fused LastFeat ×2 + FM head (+ MSE loss) --------------------------------------------------
+ * Replaces LastFeat.forward (models/deepconn/layers.py:156-165) for the user and the item side,
+ * FM.forward (layers.py:188-209) and nn.MSELoss (trainer/train_deepconn_pp.py:140,164).
+ *   u_text/i_text [B,H]; u_id/i_id [B] int64; W [H,K], b [K], ebd [users|items, K]; fm_h [K];
+ *   user_bias [users], item_bias [items]; g_bias [1].
+ *   drop_p in [0,1): FM dropout (0 = eval); the keep-mask is a counter hash of (drop_seed, sample, k) —
+ *   it cannot bit-match torch's Philox stream, parity tests run with drop_p = 0.
+ *   pred [B];  u_lat/i_lat [B,K] saved for the backward.
+ *   ratings may be NULL; otherwise loss_sum[0] += sum (pred-rating)^2 and
+ *   pred_grad[b] = 2*(pred-rating)*grad_scale  (grad_scale = 1/B for MSELoss 'mean').                 */
+int rbr_head_fwd(const float* u_text, const float* i_text, const int64_t* u_id, const int64_t* i_id, int64_t batch,
+                 int64_t hidden, int64_t latent, const float* Wu, const float* bu, const float* ebd_u,
+                 const float* Wi, const float* bi, const float* ebd_i, const float* fm_h, const float* user_bias,
+                 const float* item_bias, const float* g_bias, int64_t users, int64_t items, float drop_p,
+                 uint64_t drop_seed, float* pred, float* u_lat, float* i_lat, const float* ratings,
+                 float grad_scale, float* loss_sum, float* pred_grad, void* stream);
+/* pred_grad [B] → u_text_grad/i_text_grad [B,H] (written) and parameter grads (+=).                    */
+int rbr_head_bwd(const float* u_text, const float* i_text, const int64_t* u_id, const int64_t* i_id, int64_t batch,
+                 int64_t hidden, int64_t latent, const float* Wu, const float* Wi, const float* fm_h,
+                 const float* u_lat, const float* i_lat, float drop_p, uint64_t drop_seed, int64_t padding_idx,
+                 int64_t users, int64_t items, const float* pred_grad, float* u_text_grad, float* i_text_grad, float* Wu_grad, float* bu_grad,
+                 float* ebd_u_grad, float* Wi_grad, float* bi_grad, float* ebd_i_grad, float* fm_h_grad,
+                 float* user_bias_grad, float* item_bias_grad, float* g_bias_grad, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RBR_B200_H_ */

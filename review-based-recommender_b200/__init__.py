@@ -9,3 +9,19 @@ fallback: calling a compute op without the built library or without a CUDA devic
 __version__ = "0.1.0"
 
 from . import synth  # noqa: F401  (pure-torch, no native dependency)
+
+
+def __getattr__(name):          # lazy: model classes import torch.nn and the native binding on first use
+    if name == "DeepCoNNpp":
+        from .deepconn import DeepCoNNpp
+        return DeepCoNNpp
+    if name == "NARRE":
+        from .narre import NARRE
+        return NARRE
+    if name == "DualAtt":
+        from .dual_att import DualAtt
+        return DualAtt
+    if name in ("layers", "ops", "parallel", "deepconn", "narre", "dual_att", "_lib"):
+        import importlib
+        return importlib.import_module(f"{__name__}.{name}")
+    raise AttributeError(name)

@@ -1,0 +1,115 @@
+// rbr_common.cuh — shared helpers for the rbr_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+
+#include "../../include/rbr_b200.h"
+
+namespace rbr {
+
+// ---- error reporting -------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+
+#define RBR_REQUIRE(cond, code, ...)                    \
+    do {                                                \
+        if (!(cond)) {                                  \
+            rbr::set_error(__VA_ARGS__);                \
+            return (code);                              \
+        }                                               \
+    } while (0)
+
+#define RBR_CUDA(call)                                                   \
+    do {                                                                 \
+        cudaError_t e__ = (call);                                        \
+        if (e__ != cudaSuccess) return rbr::cuda_fail(e__, #call);       \
+    } while (0)
+
+#define RBR_LAUNCH_CHECK(name)                                           \
+    do {                                                                 \
+        cudaError_t e__ = cudaGetLastError();                            \
+        if (e__ != cudaSuccess) return rbr::cuda_fail(e__, name);        \
+    } while (0)
+
+// out-of-range id counter (ids outside [0, rows) are treated as padding rows and counted).
+// One counter per translation unit (no relocatable device code needed); each .cu that can count defines
+// an accessor with RBR_DEFINE_OOB_ACCESSOR and api.cu sums them in rbr_consume_oob_count().
+static __device__ unsigned int g_oob_count = 0;
+__device__ __forceinline__ void note_oob() { atomicAdd(&g_oob_count, 1u); }
+#define RBR_DEFINE_OOB_ACCESSOR(name)                                                                              \
+    namespace rbr {                                                                                                \
+    int oob_consume_##name(cudaStream_t s, unsigned int* host_out) {                                               \
+        unsigned int zero = 0;                                                                                     \
+        if (cudaMemcpyFromSymbolAsync(host_out, g_oob_count, sizeof(unsigned int), 0, cudaMemcpyDeviceToHost, s) != \
+            cudaSuccess)                                                                                           \
+            return RBR_ECUDA;                                                                                      \
+        if (cudaMemcpyToSymbolAsync(g_oob_count, &zero, sizeof(zero), 0, cudaMemcpyHostToDevice, s) != cudaSuccess) \
+            return RBR_ECUDA;                                                                                      \
+        return cudaStreamSynchronize(s) == cudaSuccess ? RBR_OK : RBR_ECUDA;                                       \
+    }                                                                                                              \
+    }
+
+// ---- packed conv weight buffer layout (rbr_conv_pack) -------------------------------------------
+// [0]            fp32  Wkeh  [k][E][Hpad4]      forward fp32 conv (filter index fastest)
+// [off_hke]      fp32  Whke  [H][k][Epad4]      backward (embedding index fastest)
+// [off_umma]     bf16  UMMA B operand, K-major no-swizzle core-matrix tiles:
+//                       [k][Epad16/8 chunks][Npad rows][8 bf16]
+struct PackLayout {
+    int64_t E, H, k;
+    int64_t Hpad4;      // H rounded up to 4
+    int64_t Epad4;      // E rounded up to 4
+    int64_t Epad16;     // E rounded up to 16 (UMMA K granularity for bf16)
+    int64_t Npad;       // H rounded up to 16 (UMMA N granularity at M=128)
+    int64_t off_keh, off_hke, off_umma, total;
+};
+__host__ __device__ inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+inline PackLayout pack_layout(int64_t E, int64_t H, int64_t k) {
+    PackLayout p;
+    p.E = E; p.H = H; p.k = k;
+    p.Hpad4 = round_up(H, 4);
+    p.Epad4 = round_up(E, 4);
+    p.Epad16 = round_up(E, 16);
+    p.Npad = round_up(H, 16);
+    p.off_keh = 0;
+    int64_t b = k * E * p.Hpad4 * 4;
+    p.off_hke = round_up(b, 256);
+    b = p.off_hke + H * k * p.Epad4 * 4;
+    p.off_umma = round_up(b, 256);
+    b = p.off_umma + k * p.Epad16 * p.Npad * 2;
+    p.total = round_up(b, 256);
+    return p;
+}
+
+// ---- small device helpers ----------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// counter-based keep mask for FM dropout: splitmix64 of (seed, index) → uniform in [0,1)
+__device__ __forceinline__ float hash_uniform(uint64_t seed, uint64_t idx) {
+    uint64_t z = seed + 0x9E3779B97F4A7C15ull * (idx + 1);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z = z ^ (z >> 31);
+    return (float)(z >> 40) * (1.0f / 16777216.0f);
+}
+
+__device__ __forceinline__ float act_apply(int act, float x) { return act == RBR_ACT_RELU ? fmaxf(x, 0.f) : tanhf(x); }
+// derivative expressed through the activation OUTPUT y (relu: y>0, tanh: 1-y^2)
+__device__ __forceinline__ float act_grad_from_out(int act, float y) {
+    return act == RBR_ACT_RELU ? (y > 0.f ? 1.f : 0.f) : (1.f - y * y);
+}
+
+inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+}  // namespace rbr

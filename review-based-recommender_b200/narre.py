@@ -1,0 +1,57 @@
+"""NARRE — drop-in for the reference's models/narre/narre.py:139-192 (same constructor, forward signature,
+parameter names and state_dict keys), running on the rbr_b200 CUDA kernels."""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .layers import FM, LastFeat, LinearAttention, NgramFeat, WordEmbedding, fused_head
+
+
+class NARRE(nn.Module):
+    def __init__(self, user_size, item_size, vocab_size, kernel_sizes, hidden_dim, embedding_dim, att_dim, latent_dim,
+                 max_doc_num, max_doc_len, dropout, word_padding_idx, user_padding_idx, item_padding_idx,
+                 pretrained_embeddings, arch, precision=None):
+        super().__init__()
+        self.embedding_dim = embedding_dim
+        self.hiddem_dim = hidden_dim          # (sic) the reference's attribute name, narre.py:147
+        self.doc_num = max_doc_num
+        self.doc_len = max_doc_len
+
+        self.word_embeddings = WordEmbedding(vocab_size, embedding_dim, pretrained_embeddings=pretrained_embeddings)
+        self.ngram = NgramFeat(kernel_sizes, embedding_dim, hidden_dim, max_doc_len, arch=arch, precision=precision)
+        # a user's reviews are attended with the ITEM-id embedding and vice versa (narre.py:156-157)
+        self.user_att = LinearAttention(item_size, hidden_dim, att_dim, dropout, padding_idx=item_padding_idx)
+        self.item_att = LinearAttention(user_size, hidden_dim, att_dim, dropout, padding_idx=user_padding_idx)
+        self.user_feat = LastFeat(user_size, hidden_dim, latent_dim, padding_idx=user_padding_idx)
+        self.item_feat = LastFeat(item_size, hidden_dim, latent_dim, padding_idx=item_padding_idx)
+        self.fm = FM(user_size, item_size, latent_dim, dropout, user_padding_idx=user_padding_idx,
+                     item_padding_idx=item_padding_idx)
+        self.last_arena = None
+
+    def _new_arena(self):
+        arena = ops.GradArena(list(self.named_parameters())) if torch.is_grad_enabled() else None
+        self.last_arena = arena
+        self.ngram._arena = arena
+        self.user_att._arena = arena
+        self.item_att._arena = arena
+        return arena
+
+    def forward(self, u_text, i_text, u_text_masks, i_text_masks, u_id, i_id, reuid, reiid):
+        """u_text/i_text [bz, R, T] int64, masks [bz, R, T] bool, ids [bz], reuid/reiid [bz, R] →
+        (pred [bz], u_att_scores [bz, R, 1], i_att_scores [bz, R, 1])."""
+        arena = self._new_arena()
+        bz = u_text.shape[0]
+        # every review is an independent doc of length T (narre.py:170-176)
+        u_docs = u_text.reshape(-1, self.doc_len)
+        i_docs = i_text.reshape(-1, self.doc_len)
+        u_m = u_text_masks.reshape(-1, self.doc_len)
+        i_m = i_text_masks.reshape(-1, self.doc_len)
+        u_feat, i_feat = self.ngram.encode(self.word_embeddings, [u_docs, i_docs], [u_m, i_m])
+        u_feat = u_feat.view(bz, self.doc_num, self.hiddem_dim)
+        i_feat = i_feat.view(bz, self.doc_num, self.hiddem_dim)
+        u_feat, u_att_scores = self.user_att(u_feat, reuid)            # narre.py:184
+        i_feat, i_att_scores = self.item_att(i_feat, reiid)            # narre.py:185
+        pred = fused_head(self.user_feat, self.item_feat, self.fm, u_feat, i_feat, u_id, i_id, self.training, arena)
+        return pred.view(-1), u_att_scores, i_att_scores

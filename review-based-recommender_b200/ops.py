@@ -1,0 +1,325 @@
+"""Host-side operators: torch.autograd.Functions whose forward/backward call the C-ABI kernels.
+
+PyTorch provides device memory, the current CUDA stream and autograd bookkeeping; every arithmetic step
+of the hot path runs in librbr_b200.so.  Tensors handed to the library must be CUDA, contiguous, fp32 /
+int64 / bool — anything else raises (there is no CPU path).
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from ._lib import lib
+
+PREC_FP32, PREC_BF16 = 0, 1
+ACT_RELU, ACT_TANH = 0, 1
+_PREC = {"fp32": PREC_FP32, "bf16": PREC_BF16}
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _req(t: torch.Tensor, dtype, name: str) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError(f"rbr_b200: `{name}` must be a CUDA tensor (the hot path has no CPU implementation)")
+    if t.dtype != dtype:
+        raise TypeError(f"rbr_b200: `{name}` must be {dtype}, got {t.dtype}")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _mask_u8(mask: Optional[torch.Tensor], name: str) -> Optional[torch.Tensor]:
+    if mask is None:
+        return None
+    if not mask.is_cuda:
+        raise RuntimeError(f"rbr_b200: `{name}` must be a CUDA tensor")
+    if mask.dtype == torch.bool:
+        return mask.contiguous().view(torch.uint8)
+    if mask.dtype == torch.uint8:
+        return mask.contiguous()
+    raise TypeError(f"rbr_b200: `{name}` must be bool, got {mask.dtype}")
+
+
+# ---------------------------------------------------------------------------------------------------
+# Step context: one flat fp32 gradient buffer per backward pass, with a view per parameter.
+# ---------------------------------------------------------------------------------------------------
+class GradArena:
+    """Allocates ONE zero-filled flat buffer holding the gradient of every trainable parameter of a model
+    (allocated at the first backward call of a step) and hands out per-parameter views.  The kernels
+    accumulate straight into these views, autograd installs them as `.grad`, and data-parallel training
+    all-reduces the flat buffer with a single NCCL call (parallel.py)."""
+
+    def __init__(self, named_params: Sequence[Tuple[str, torch.nn.Parameter]]):
+        self.slots: Dict[int, Tuple[int, torch.Size]] = {}
+        off = 0
+        for _, prm in named_params:
+            if prm.requires_grad and id(prm) not in self.slots:
+                self.slots[id(prm)] = (off, prm.shape)
+                off += (prm.numel() + 63) // 64 * 64            # 256-byte aligned slots (float4 atomics)
+        self.total = off
+        self.flat: Optional[torch.Tensor] = None
+        self.device = None
+
+    def _ensure(self, device):
+        if self.flat is None:
+            self.flat = torch.zeros(self.total, dtype=torch.float32, device=device)
+
+    def view(self, prm: torch.Tensor) -> Optional[torch.Tensor]:
+        slot = self.slots.get(id(prm))
+        if slot is None:
+            return None
+        self._ensure(prm.device)
+        off, shape = slot
+        return self.flat[off:off + shape.numel()].view(shape)
+
+
+def _grad_buf(arena: Optional[GradArena], prm: torch.Tensor, needs: bool) -> Optional[torch.Tensor]:
+    if not needs:
+        return None
+    if arena is not None:
+        v = arena.view(prm)
+        if v is not None:
+            return v
+    return torch.zeros_like(prm)
+
+
+# ---------------------------------------------------------------------------------------------------
+# K1 / K1b: embedding gather
+# ---------------------------------------------------------------------------------------------------
+def gather_rows(table: torch.Tensor, ids: torch.Tensor) -> torch.Tensor:
+    table = _req(table, torch.float32, "table")
+    ids = _req(ids, torch.int64, "ids")
+    out = torch.empty(*ids.shape, table.shape[1], dtype=torch.float32, device=table.device)
+    lib.check(lib.rbr_gather_fwd(_p(table), table.shape[0], table.shape[1], _p(ids), ids.numel(), _p(out), _stream()),
+              "rbr_gather_fwd")
+    return out
+
+
+def embedding_dense_grad(ids: torch.Tensor, grad_rows: torch.Tensor, vocab: int, padding_idx: Optional[int],
+                         out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    ids = _req(ids, torch.int64, "ids")
+    grad_rows = _req(grad_rows, torch.float32, "grad_rows")
+    emb = grad_rows.shape[-1]
+    if out is None:
+        out = torch.zeros(vocab, emb, dtype=torch.float32, device=grad_rows.device)
+    n = ids.numel()
+    ws_bytes = lib.rbr_embgrad_workspace_bytes(n, vocab)
+    ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=grad_rows.device)
+    lib.check(lib.rbr_embgrad_scatter_add(_p(ids), _p(grad_rows), n, emb, vocab, -1 if padding_idx is None else padding_idx,
+                                          _p(out), _p(ws), ws_bytes, _stream()), "rbr_embgrad_scatter_add")
+    return out
+
+
+class EmbeddingFn(torch.autograd.Function):
+    """nn.Embedding forward/backward (reference models/deepconn/layers.py:15,23)."""
+
+    @staticmethod
+    def forward(ctx, table, ids, padding_idx, arena):
+        ctx.save_for_backward(ids)
+        ctx.vocab, ctx.padding_idx, ctx.arena, ctx.table = table.shape[0], padding_idx, arena, table
+        return gather_rows(table, ids)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (ids,) = ctx.saved_tensors
+        buf = _grad_buf(ctx.arena, ctx.table, True)
+        embedding_dense_grad(ids, grad_out.contiguous(), ctx.vocab, ctx.padding_idx, out=buf)
+        return buf, None, None, None
+
+
+# ---------------------------------------------------------------------------------------------------
+# K0 staging: bf16 shadow table + packed conv weights
+# ---------------------------------------------------------------------------------------------------
+def table_to_bf16(table: torch.Tensor) -> torch.Tensor:
+    table = _req(table, torch.float32, "table")
+    emb_pad = lib.rbr_emb_pad(table.shape[1])
+    shadow = torch.empty(table.shape[0], emb_pad, dtype=torch.bfloat16, device=table.device)
+    lib.check(lib.rbr_table_to_bf16(_p(table), table.shape[0], table.shape[1], _p(shadow), _stream()), "rbr_table_to_bf16")
+    return shadow
+
+
+def conv_pack(weight: torch.Tensor) -> torch.Tensor:
+    weight = _req(weight, torch.float32, "conv weight")
+    h, e, k = weight.shape
+    nbytes = lib.rbr_conv_pack_bytes(e, h, k)
+    packed = torch.empty(nbytes, dtype=torch.uint8, device=weight.device)
+    lib.check(lib.rbr_conv_pack(_p(weight), e, h, k, _p(packed), _stream()), "rbr_conv_pack")
+    return packed
+
+
+# ---------------------------------------------------------------------------------------------------
+# K2 / K2b: fused gather → mask → conv → activation → max-over-time, for one or several token tensors
+# ("sides": DeepCoNN's user and item documents share the table and the conv, deepconn.py:43-47)
+# ---------------------------------------------------------------------------------------------------
+class EncodeDocsFn(torch.autograd.Function):
+    """feats[s] = max_t act(conv(mask(table[ids[s]])))  for every side s; all sides share table/weights.
+
+    Replaces WordEmbedding.forward + NgramFeat.forward (reference models/deepconn/layers.py:22-24, 123-136).
+    Inputs after the fixed ones: n_conv conv weights, n_conv conv biases, then per side (ids, mask-or-None).
+    """
+
+    @staticmethod
+    def forward(ctx, table, cfg, *rest):
+        n_conv = cfg["n_conv"]
+        weights, biases = rest[:n_conv], rest[n_conv:2 * n_conv]
+        sides = rest[2 * n_conv:]
+        ids_l = [_req(t, torch.int64, "token ids") for t in sides[0::2]]
+        mask_l = [_mask_u8(m, "token mask") for m in sides[1::2]]
+        table = _req(table, torch.float32, "embedding table")
+        prec = _PREC[cfg["precision"]]
+        act, pads = cfg["act"], cfg["pads"]
+        vocab, emb = table.shape
+        shadow = cfg["shadow_fn"]() if prec == PREC_BF16 else None
+        packed = [cfg["pack_fn"](i) for i in range(n_conv)]
+        h_total = sum(w.shape[0] for w in weights)
+        feats, argmaxes = [], []
+        for ids, mask in zip(ids_l, mask_l):
+            doc_len = ids.shape[-1]
+            n_docs = ids.numel() // doc_len
+            if mask is not None and mask.numel() != ids.numel():
+                raise ValueError("rbr_b200: mask shape does not match token ids")
+            feat = torch.empty(n_docs, h_total, dtype=torch.float32, device=table.device)
+            amax = torch.empty(n_docs, h_total, dtype=torch.int32, device=table.device)
+            col = 0
+            for w, b, pk, pad in zip(weights, biases, packed, pads):
+                h, _, k = w.shape
+                lib.check(lib.rbr_conv_act_maxpool_fwd(
+                    prec, act, _p(table), _p(shadow), vocab, emb, _p(ids), _p(mask), None, 0, n_docs, doc_len, _p(pk),
+                    _p(_req(b, torch.float32, "conv bias")), h, k, pad, feat.data_ptr() + 4 * col, amax.data_ptr() + 4 * col,
+                    h_total, _stream()), "rbr_conv_act_maxpool_fwd")
+                col += h
+            feats.append(feat)
+            argmaxes.append(amax)
+        ctx.cfg, ctx.n_conv, ctx.n_sides = cfg, n_conv, len(ids_l)
+        ctx.table, ctx.weights, ctx.biases = table, weights, biases
+        ctx.shadow, ctx.packed = shadow, packed
+        ctx.save_for_backward(*ids_l, *[m for m in mask_l if m is not None], *feats, *argmaxes)
+        ctx.mask_present = [m is not None for m in mask_l]
+        return tuple(feats)
+
+    @staticmethod
+    def backward(ctx, *feat_grads):
+        cfg, n_conv, ns = ctx.cfg, ctx.n_conv, ctx.n_sides
+        saved = list(ctx.saved_tensors)
+        ids_l = saved[:ns]
+        n_masks = sum(ctx.mask_present)
+        masks_present = saved[ns:ns + n_masks]
+        feats = saved[ns + n_masks:ns + n_masks + ns]
+        argmaxes = saved[ns + n_masks + ns:]
+        mask_l, mi = [], 0
+        for present in ctx.mask_present:
+            mask_l.append(masks_present[mi] if present else None)
+            mi += int(present)
+        table = ctx.table
+        arena: Optional[GradArena] = cfg.get("arena")
+        prec = _PREC[cfg["precision"]]
+        vocab, emb = table.shape
+        need_table = ctx.needs_input_grad[0]
+        g_table = _grad_buf(arena, cfg["table_param"], need_table)
+        g_w = [_grad_buf(arena, cfg["weight_params"][i], True) for i in range(n_conv)]
+        g_b = [_grad_buf(arena, cfg["bias_params"][i], True) for i in range(n_conv)]
+        h_total = feats[0].shape[1]
+        for s in range(ns):
+            if feat_grads[s] is None:
+                continue
+            fg = feat_grads[s].contiguous()
+            ids, mask = ids_l[s], mask_l[s]
+            doc_len = ids.shape[-1]
+            n_docs = ids.numel() // doc_len
+            col = 0
+            for i in range(n_conv):
+                h, _, k = ctx.weights[i].shape
+                ws_bytes = lib.rbr_conv_bwd_workspace_bytes(n_docs, h, k, emb, vocab)
+                ws = torch.empty(ws_bytes, dtype=torch.uint8, device=table.device)
+                lib.check(lib.rbr_conv_act_maxpool_bwd(
+                    prec, cfg["act"], _p(table), _p(ctx.shadow), vocab, emb, _p(ids), _p(mask), None, 0, n_docs, doc_len,
+                    _p(ctx.packed[i]), h, k, cfg["pads"][i], feats[s].data_ptr() + 4 * col, argmaxes[s].data_ptr() + 4 * col,
+                    fg.data_ptr() + 4 * col, h_total, cfg["padding_idx"], _p(g_w[i]), _p(g_b[i]), _p(g_table), None,
+                    _p(ws), ws_bytes, _stream()), "rbr_conv_act_maxpool_bwd")
+                col += h
+        return (g_table, None, *g_w, *g_b, *([None] * (2 * ns)))
+
+
+# ---------------------------------------------------------------------------------------------------
+# K3: NARRE attention
+# ---------------------------------------------------------------------------------------------------
+class NarreAttnFn(torch.autograd.Function):
+    """LinearAttention.forward without dropout (reference models/narre/narre.py:40-60)."""
+
+    @staticmethod
+    def forward(ctx, feat, other_id, W_rv, W_id, h, b_1, b_2, ebd, padding_idx, arena, params):
+        feat = _req(feat, torch.float32, "feat")
+        other_id = _req(other_id, torch.int64, "other_id")
+        B, R, H = feat.shape
+        A = W_rv.shape[1]
+        out = torch.empty(B, H, dtype=torch.float32, device=feat.device)
+        scores = torch.empty(B, R, dtype=torch.float32, device=feat.device)
+        args = [_req(t, torch.float32, n) for t, n in ((W_rv, "W_rv"), (W_id, "W_id"), (h, "h"), (b_1, "b_1"), (b_2, "b_2"),
+                                                        (ebd, "ebd_vals"))]
+        lib.check(lib.rbr_narre_attn_fwd(_p(feat), _p(other_id), B, R, H, A, *[_p(a) for a in args], ebd.shape[0], _p(out),
+                                         _p(scores), _stream()), "rbr_narre_attn_fwd")
+        ctx.save_for_backward(feat, other_id, scores, *args)
+        ctx.padding_idx, ctx.arena, ctx.params = padding_idx, arena, params
+        return out, scores.view(B, R, 1)
+
+    @staticmethod
+    def backward(ctx, g_out, g_scores):
+        feat, other_id, scores, W_rv, W_id, h, b_1, b_2, ebd = ctx.saved_tensors
+        B, R, H = feat.shape
+        A = W_rv.shape[1]
+        g_out = torch.zeros(B, H, device=feat.device) if g_out is None else g_out.contiguous()
+        g_scores = None if g_scores is None else g_scores.contiguous()
+        g_feat = torch.empty_like(feat)
+        grads = [_grad_buf(ctx.arena, p, True) for p in ctx.params]
+        lib.check(lib.rbr_narre_attn_bwd(_p(feat), _p(other_id), B, R, H, A, _p(W_rv), _p(W_id), _p(h), _p(b_1), _p(b_2), _p(ebd),
+                                         ebd.shape[0], -1 if ctx.padding_idx is None else ctx.padding_idx, _p(scores), _p(g_out),
+                                         _p(g_scores), _p(g_feat), *[_p(g) for g in grads], _stream()), "rbr_narre_attn_bwd")
+        return (g_feat, None, *grads, None, None, None)
+
+
+# ---------------------------------------------------------------------------------------------------
+# K4: LastFeat x2 + FM head
+# ---------------------------------------------------------------------------------------------------
+class HeadFn(torch.autograd.Function):
+    """pred = FM(LastFeat_u(u_text, u_id), LastFeat_i(i_text, i_id))  (reference layers.py:156-165, 188-209)."""
+
+    @staticmethod
+    def forward(ctx, u_text, i_text, u_id, i_id, Wu, bu, ebd_u, Wi, bi, ebd_i, fm_h, user_bias, item_bias, g_bias, drop_p,
+                drop_seed, padding_idx, arena, params):
+        u_text = _req(u_text, torch.float32, "u_text")
+        i_text = _req(i_text, torch.float32, "i_text")
+        u_id = _req(u_id, torch.int64, "u_id")
+        i_id = _req(i_id, torch.int64, "i_id")
+        B, H = u_text.shape
+        K = Wu.shape[1]
+        fl = [_req(t, torch.float32, "head parameter") for t in (Wu, bu, ebd_u, Wi, bi, ebd_i, fm_h, user_bias, item_bias, g_bias)]
+        pred = torch.empty(B, dtype=torch.float32, device=u_text.device)
+        u_lat = torch.empty(B, K, dtype=torch.float32, device=u_text.device)
+        i_lat = torch.empty(B, K, dtype=torch.float32, device=u_text.device)
+        lib.check(lib.rbr_head_fwd(_p(u_text), _p(i_text), _p(u_id), _p(i_id), B, H, K, *[_p(t) for t in fl], ebd_u.shape[0],
+                                   ebd_i.shape[0], float(drop_p), int(drop_seed), _p(pred), _p(u_lat), _p(i_lat), None, 0.0,
+                                   None, None, _stream()), "rbr_head_fwd")
+        ctx.save_for_backward(u_text, i_text, u_id, i_id, fl[0], fl[3], fl[6], u_lat, i_lat)
+        ctx.drop, ctx.padding_idx, ctx.arena, ctx.params = (float(drop_p), int(drop_seed)), padding_idx, arena, params
+        ctx.sizes = (ebd_u.shape[0], ebd_i.shape[0])
+        return pred
+
+    @staticmethod
+    def backward(ctx, g_pred):
+        u_text, i_text, u_id, i_id, Wu, Wi, fm_h, u_lat, i_lat = ctx.saved_tensors
+        B, H = u_text.shape
+        K = Wu.shape[1]
+        g_pred = g_pred.contiguous()
+        g_ut, g_it = torch.empty_like(u_text), torch.empty_like(i_text)
+        # params order: Wu, bu, ebd_u, Wi, bi, ebd_i, fm_h, user_bias, item_bias, g_bias
+        grads = [_grad_buf(ctx.arena, p, True) for p in ctx.params]
+        lib.check(lib.rbr_head_bwd(_p(u_text), _p(i_text), _p(u_id), _p(i_id), B, H, K, _p(Wu), _p(Wi), _p(fm_h), _p(u_lat),
+                                   _p(i_lat), ctx.drop[0], ctx.drop[1], -1 if ctx.padding_idx is None else ctx.padding_idx,
+                                   ctx.sizes[0], ctx.sizes[1], _p(g_pred), _p(g_ut), _p(g_it), *[_p(g) for g in grads],
+                                   _stream()), "rbr_head_bwd")
+        return (g_ut, g_it, None, None, *grads, None, None, None, None, None)

@@ -1,0 +1,136 @@
+"""CPU-side tests (no GPU): the C-ABI library loads and exports every declared symbol, the host logic
+(gradient arena, sharding, data-parallel all-reduce over gloo with world_size 2) and the synthetic data."""
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+import rbr_b200
+from rbr_b200 import synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_cabi_loads_and_exports_every_declared_symbol():
+    import __graft_entry__ as ge
+    if not os.path.exists(os.path.join(ge.CSRC, "librbr_b200.so")):
+        ge.build()
+    from rbr_b200._lib import lib
+    assert len(lib.protos) >= 17
+    for name in lib.protos:
+        assert getattr(lib, name) is not None, name
+    assert lib.rbr_version() >= 100
+    assert lib.rbr_emb_pad(300) == 304 and lib.rbr_emb_pad(100) == 112
+    assert lib.rbr_conv_pack_bytes(300, 100, 3) > 0
+    assert lib.rbr_conv_bwd_workspace_bytes(8, 100, 3, 300, 50000) > 0
+    assert lib.rbr_embgrad_workspace_bytes(1000, 50000) > 0
+
+
+def test_no_cpu_fallback():
+    m = rbr_b200.DeepCoNNpp(9, 7, 60, [3], 12, 8, 6, 20, None, 0.0)
+    ids = torch.zeros(2, 20, dtype=torch.long)
+    with pytest.raises(RuntimeError, match="no CPU implementation"):
+        m(ids, ids, ids != 0, ids != 0, torch.ones(2, dtype=torch.long), torch.ones(2, dtype=torch.long))
+
+
+def test_state_dict_keys_match_reference_goldens():
+    from conftest import Golden
+    g = Golden("deepconn_multik")
+    m = g.meta
+    model = rbr_b200.DeepCoNNpp(m["U"], m["I"], m["V"], "3,5", m["E"], m["H"], m["K"], m["L"], None, 0.0)
+    assert set(model.state_dict()) == set(g.params)
+    for k, v in model.state_dict().items():
+        assert v.shape == g.params[k].shape, k
+    n = Golden("narre_small")
+    m = n.meta
+    model = rbr_b200.NARRE(m["U"], m["I"], m["V"], [3], m["H"], m["E"], m["A"], m["K"], m["R"], m["T"], 0.5, 0, 0, 0, None, "CNN")
+    assert set(model.state_dict()) == set(n.params)
+    with pytest.raises(ValueError):
+        rbr_b200.layers.NgramFeat([3], 8, 8, 10, arch="nope")
+    with pytest.raises(AssertionError):
+        rbr_b200.layers.MyConv1d([2], 8, 8)              # even kernel sizes are rejected, layers.py:39
+
+
+def test_grad_arena_views_are_disjoint_and_aligned():
+    from rbr_b200.ops import GradArena
+    ps = [("a", torch.nn.Parameter(torch.zeros(3, 5))), ("b", torch.nn.Parameter(torch.zeros(7))),
+          ("c", torch.nn.Parameter(torch.zeros(2, 2), requires_grad=False))]
+    arena = GradArena(ps)
+    va, vb = arena.view(ps[0][1]), arena.view(ps[1][1])
+    assert arena.view(ps[2][1]) is None
+    assert va.shape == (3, 5) and vb.shape == (7,)
+    assert va.data_ptr() % 256 == arena.flat.data_ptr() % 256 and (vb.data_ptr() - va.data_ptr()) % 256 == 0
+    va.fill_(1.0)
+    assert float(vb.sum()) == 0.0 and float(arena.flat.sum()) == 15.0
+
+
+def test_synthetic_batches_follow_the_preprocessing_contract():
+    (u, i, um, im, uid, iid), r = synth.deepconn_batch(16, 50, 1000, 30, 20, seed=3)
+    assert u.dtype == torch.int64 and um.dtype == torch.bool and torch.equal(um, u != 0)
+    assert int(u.max()) < 1000 and int(u[um].min()) >= 3
+    assert ((u == 0).long().diff(dim=1) >= 0).all()                      # padding only at the tail
+    assert set(r.tolist()) <= {1.0, 2.0, 3.0, 4.0, 5.0} and int(uid.min()) >= 1
+    (ut, it, utm, itm, uid, iid, reu, rei), r = synth.narre_batch(8, 5, 12, 500, 30, 20, seed=3)
+    assert ut.shape == (8, 5, 12) and reu.shape == (8, 5)
+    pad_reviews = (reu == 0)
+    assert (ut[pad_reviews] == 0).all()                                   # padded reviews are all-zero with id 0
+    again = synth.narre_batch(8, 5, 12, 500, 30, 20, seed=3)[0][0]
+    assert torch.equal(ut, again)
+
+
+def test_shard_range_partitions_batch():
+    from rbr_b200.parallel import shard_range
+    for n, w in ((4096, 8), (10, 4), (7, 2), (3, 8)):
+        seen = []
+        for r in range(w):
+            seen += list(shard_range(n, r, w))
+        assert seen == list(range(n))
+
+
+_DP_WORKER = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["RBR_ROOT"])
+import rbr_b200
+from rbr_b200 import parallel
+from rbr_b200.ops import GradArena
+rank, local, world = parallel.init_from_env("gloo")
+torch.manual_seed(0)
+model = torch.nn.Linear(6, 3)
+parallel.broadcast_parameters(model)
+x = torch.arange(8 * 6, dtype=torch.float32).view(8, 6) / 10
+y = torch.ones(8, 3)
+sh = parallel.shard_range(8, rank, world)
+# gradients placed in a flat arena, as the CUDA backward does
+arena = GradArena(list(model.named_parameters()))
+loss = torch.nn.functional.mse_loss(model(x[sh.start:sh.stop]), y[sh.start:sh.stop])
+gw, gb = torch.autograd.grad(loss, [model.weight, model.bias])
+model.weight.grad = arena.view(model.weight); model.weight.grad.copy_(gw)
+model.bias.grad = arena.view(model.bias); model.bias.grad.copy_(gb)
+model.last_arena = arena
+n = parallel.allreduce_gradients(model)
+assert n == 1
+ref = torch.nn.Linear(6, 3); ref.load_state_dict(model.state_dict())
+torch.nn.functional.mse_loss(ref(x), y).backward()
+assert torch.allclose(model.weight.grad, ref.weight.grad, atol=1e-6), (model.weight.grad, ref.weight.grad)
+assert torch.allclose(model.bias.grad, ref.bias.grad, atol=1e-6)
+# slow path: grads not in the arena
+model.last_arena = None
+model.weight.grad = gw.clone(); model.bias.grad = gb.clone()
+parallel.allreduce_gradients(model)
+assert torch.allclose(model.weight.grad, ref.weight.grad, atol=1e-6)
+dist.barrier()
+print("rank", rank, "ok")
+'''
+
+
+def test_data_parallel_allreduce_world2_gloo(tmp_path):
+    script = tmp_path / "dp_worker.py"
+    script.write_text(_DP_WORKER)
+    env = dict(os.environ, RBR_ROOT=ROOT, OMP_NUM_THREADS="1")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29731", str(script)],
+                         env=env, capture_output=True, text=True, timeout=240)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.count("ok") == 2

@@ -1,0 +1,216 @@
+"""GPU parity tests: the CUDA path (through the C-ABI library) against the committed reference golden
+fixtures and against the CPU oracle on seeded inputs.  Tolerances are BASELINE.json's: bit-exact gathers,
+1e-5 relative in fp32, 1e-2 relative in bf16."""
+import os
+
+import pytest
+import torch
+
+import rbr_b200
+from conftest import Golden, grad_floor, rel_err
+from oracle import rbr_oracle as orc
+from rbr_b200 import ops, synth
+
+pytestmark = pytest.mark.gpu
+FP32_TOL = 1e-5
+FP32_GRAD_TOL = 3e-5      # sums over the batch in a different association order than the CPU oracle
+BF16_TOL = 1e-2
+
+DEEPCONN_CASES = ["deepconn_small", "deepconn_edge", "deepconn_multik", "deepconn_odd"]
+NARRE_CASES = ["narre_small", "narre_h150ish"]
+
+
+def dev(t):
+    return t.cuda() if isinstance(t, torch.Tensor) else t
+
+
+def build_model(g: Golden, precision="fp32"):
+    m = g.meta
+    if g.model == "deepconn":
+        model = rbr_b200.DeepCoNNpp(m["U"], m["I"], m["V"], m["ks"], m["E"], m["H"], m["K"], m["L"], None, 0.0,
+                                    precision=precision)
+    else:
+        model = rbr_b200.NARRE(m["U"], m["I"], m["V"], [3], m["H"], m["E"], m["A"], m["K"], m["R"], m["T"], 0.0, 0, 0, 0,
+                               None, "CNN", precision=precision)
+    assert set(model.state_dict()) == set(g.params)
+    model.load_state_dict(g.params)
+    return model.cuda()
+
+
+def run_step(model, batch, ratings):
+    model.train()
+    model.zero_grad()
+    out = model(*[dev(t) for t in batch])
+    pred = out[0] if isinstance(out, tuple) else out
+    loss = torch.nn.MSELoss()(pred, dev(ratings))
+    loss.backward()
+    grads = {k: p.grad.detach().cpu() for k, p in model.named_parameters()}
+    return out, loss.detach().cpu(), grads
+
+
+# ------------------------------------------------------------------------------------------------
+def test_gather_bit_exact_and_dense_grad():
+    g = Golden("deepconn_odd")
+    table = g.params["word_embeddings.embedding.weight"].cuda()
+    ids = g.batch[0].cuda()
+    out = ops.gather_rows(table, ids)
+    assert torch.equal(out.cpu(), orc.embedding_gather(table.cpu(), ids.cpu()))
+    gr = torch.randn(*ids.shape, table.shape[1], generator=torch.Generator().manual_seed(1))
+    dense = ops.embedding_dense_grad(ids, gr.cuda(), table.shape[0], 0).cpu()
+    ref = orc.embedding_dense_grad(ids.cpu(), gr, table.shape[0], 0)
+    assert rel_err(dense, ref) < 1e-6
+    assert float(dense[0].abs().max()) == 0.0
+
+
+def test_gather_large_bit_exact():
+    gen = torch.Generator().manual_seed(3)
+    table = torch.randn(5000, 300, generator=gen)
+    ids, _ = synth.doc_batch(64, 500, 5000, seed=11)
+    out = ops.gather_rows(table.cuda(), ids.cuda()).cpu()
+    assert torch.equal(out, table[ids])
+    # scalar path (emb % 4 != 0) and empty input
+    t2 = torch.randn(50, 7, generator=gen)
+    i2 = torch.randint(0, 50, (3, 5), generator=gen)
+    assert torch.equal(ops.gather_rows(t2.cuda(), i2.cuda()).cpu(), t2[i2])
+    assert ops.gather_rows(t2.cuda(), i2[:0].cuda()).shape == (0, 5, 7)
+
+
+def test_dense_grad_hot_rows_and_scalar_path():
+    gen = torch.Generator().manual_seed(5)
+    ids = synth.skewed_tokens(gen, (4096 * 4,), 300)          # heavy duplicates → long segments
+    ids[::7] = 0
+    gr = torch.randn(ids.numel(), 64, generator=gen)
+    dense = ops.embedding_dense_grad(ids.cuda(), gr.cuda(), 300, 0).cpu()
+    assert rel_err(dense, orc.embedding_dense_grad(ids, gr, 300, 0)) < 1e-5
+    gr7 = torch.randn(ids.numel(), 7, generator=gen)
+    dense7 = ops.embedding_dense_grad(ids.cuda(), gr7.cuda(), 300, 0).cpu()
+    assert rel_err(dense7, orc.embedding_dense_grad(ids, gr7, 300, 0)) < 1e-5
+
+
+@pytest.mark.parametrize("case", DEEPCONN_CASES + NARRE_CASES)
+def test_golden_fp32(case):
+    """Forward outputs, loss and EVERY parameter gradient against the reference's own numbers."""
+    g = Golden(case)
+    model = build_model(g, "fp32")
+    out, loss, grads = run_step(model, g.batch, g.ratings)
+    pred = out[0] if isinstance(out, tuple) else out
+    assert rel_err(pred.detach().cpu(), g.out["pred"]) < FP32_TOL
+    assert rel_err(loss, g.out["loss"]) < FP32_TOL
+    if isinstance(out, tuple):
+        assert out[1].shape == g.out["u_att_scores"].shape
+        assert rel_err(out[1].detach().cpu(), g.out["u_att_scores"]) < FP32_TOL
+        assert rel_err(out[2].detach().cpu(), g.out["i_att_scores"]) < FP32_TOL
+    assert set(grads) == set(g.grads)
+    for k, ref in g.grads.items():
+        assert grads[k].shape == ref.shape, k
+        assert rel_err(grads[k], ref, grad_floor(k)) < FP32_GRAD_TOL, k
+    assert float(grads["word_embeddings.embedding.weight"][0].abs().max()) == 0.0      # padding row
+
+
+def test_edge_semantics_fp32():
+    """all-pad doc pools to relu(bias); masks are honoured even where ids != 0; eval == train at dropout 0."""
+    g = Golden("deepconn_edge")
+    model = build_model(g, "fp32")
+    u_feat, i_feat = model.ngram.encode(model.word_embeddings, [g.batch[0].cuda(), g.batch[1].cuda()],
+                                        [g.batch[2].cuda(), g.batch[3].cuda()])
+    assert rel_err(u_feat.detach().cpu(), g.out["u_rev_feats"]) < FP32_TOL
+    assert rel_err(i_feat.detach().cpu(), g.out["i_rev_feats"]) < FP32_TOL
+    bias = g.params["ngram.feature_layer.0.list_of_conv1d.0.bias"]
+    assert torch.allclose(u_feat[0].detach().cpu(), torch.relu(bias), atol=1e-7)
+    model.eval()
+    with torch.no_grad():
+        p = model(*[t.cuda() for t in g.batch])
+    assert rel_err(p.cpu(), g.out["pred"]) < FP32_TOL
+
+
+def test_ngramfeat_standalone_matches_oracle():
+    """Reference-signature NgramFeat.forward(inputs [bz,L,E], masks) incl. gradient w.r.t. the dense inputs."""
+    gen = torch.Generator().manual_seed(9)
+    bz, L, E, H = 6, 33, 20, 12
+    x = torch.randn(bz, L, E, generator=gen)
+    mask = torch.rand(bz, L, generator=gen) > 0.2
+    layer = rbr_b200.layers.NgramFeat([3], E, H, L, precision="fp32").cuda()
+    w = layer.conv.list_of_conv1d[0].weight.detach().cpu()
+    b = layer.conv.list_of_conv1d[0].bias.detach().cpu()
+    xg = x.cuda().requires_grad_(True)
+    out = layer(xg, mask.cuda())
+    assert out.shape == (bz, H, 1)
+    xo = x.clone().requires_grad_(True)
+    ref = orc.ngram_feat(xo, mask, [w], [b])
+    assert rel_err(out.detach().cpu().view(bz, H), ref.detach()) < FP32_TOL
+    gout = torch.randn(bz, H, generator=gen)
+    out.view(bz, H).backward(gout.cuda())
+    ref.backward(gout)
+    assert rel_err(xg.grad.cpu(), xo.grad) < FP32_GRAD_TOL
+
+
+def test_linear_attention_standalone_and_padding_quirk():
+    """Padded reviews are NOT masked out of the softmax (narre.py:58): they keep non-zero weight."""
+    g = Golden("narre_small")
+    m = g.meta
+    att = rbr_b200.layers.LinearAttention(m["I"], m["H"], m["A"], 0.0).cuda()
+    sd = {k[len("user_att."):]: v for k, v in g.params.items() if k.startswith("user_att.")}
+    att.load_state_dict(sd)
+    gen = torch.Generator().manual_seed(2)
+    feat = torch.randn(m["B"], m["R"], m["H"], generator=gen)
+    out, sc = att(feat.cuda(), g.batch[6].cuda())
+    ro, rs = orc.linear_attention(feat, g.batch[6], sd["W_rv"], sd["W_id"], sd["h"], sd["b_1"], sd["b_2"], sd["ebd_vals.weight"])
+    assert rel_err(out.detach().cpu(), ro) < FP32_TOL and rel_err(sc.detach().cpu(), rs) < FP32_TOL
+    assert torch.allclose(sc.sum(dim=1).cpu(), torch.ones(m["B"], 1), atol=1e-6)
+    assert float(sc.min()) > 0.0
+
+
+@pytest.mark.parametrize("model_name", ["deepconn", "narre"])
+def test_seeded_midsize_vs_oracle_fp32(model_name):
+    """Realistic dims (E=300, k=3, H=100/150) at a batch the CPU oracle finishes in seconds."""
+    if model_name == "deepconn":
+        B, L, V, U, I, E, H, K = 24, 500, 3000, 50, 40, 300, 100, 32
+        params = synth.deepconn_params(U, I, V, E, H, K, (3,), seed=1)
+        batch, ratings = synth.deepconn_batch(B, L, V, U, I, seed=123)
+        model = rbr_b200.DeepCoNNpp(U, I, V, [3], E, H, K, L, None, 0.0, precision="fp32")
+    else:
+        B, R, T, V, U, I, E, H, A, K = 12, 10, 60, 3000, 50, 40, 300, 150, 32, 32
+        params = synth.narre_params(U, I, V, E, H, A, K, (3,), seed=1)
+        batch, ratings = synth.narre_batch(B, R, T, V, U, I, seed=123)
+        model = rbr_b200.NARRE(U, I, V, [3], H, E, A, K, R, T, 0.0, 0, 0, 0, None, "CNN", precision="fp32")
+    model.load_state_dict(params)
+    model.cuda()
+    out, loss, grads = run_step(model, batch, ratings)
+    pred = out[0] if isinstance(out, tuple) else out
+    rp, rl, rg = orc.loss_and_grads(model_name, params, batch, ratings)
+    assert rel_err(pred.detach().cpu(), rp) < FP32_TOL
+    assert rel_err(loss, rl) < FP32_TOL
+    for k in rg:
+        assert rel_err(grads[k], rg[k], grad_floor(k)) < FP32_GRAD_TOL, k
+
+
+def test_properties_full_size_fp32_forward():
+    """Size-independent properties at a larger batch: changing tokens under a false mask changes nothing;
+    permuting the batch permutes the predictions; eval forward is deterministic."""
+    B, L, V, U, I, E, H, K = 256, 500, 50000, 200, 120, 300, 100, 32
+    params = synth.deepconn_params(U, I, V, E, H, K, (3,), seed=2)
+    batch, _ = synth.deepconn_batch(B, L, V, U, I, seed=77)
+    model = rbr_b200.DeepCoNNpp(U, I, V, [3], E, H, K, L, None, 0.5, precision="fp32")
+    model.load_state_dict(params)
+    model.cuda().eval()
+    b = [t.cuda() for t in batch]
+    with torch.no_grad():
+        p0 = model(*b)
+        p1 = model(*b)
+        assert torch.equal(p0, p1)
+        scr = b[0].clone()
+        scr[~b[2]] = 17                                     # garbage under the mask
+        assert torch.equal(model(scr, b[1], b[2], b[3], b[4], b[5]), p0)
+        perm = torch.randperm(B, device="cuda")
+        pp = model(*[t[perm] for t in b])
+        assert torch.equal(pp, p0[perm])
+
+
+def test_oob_ids_are_counted_not_fatal():
+    from rbr_b200._lib import lib
+    lib.rbr_consume_oob_count(None)
+    table = torch.randn(10, 8).cuda()
+    ids = torch.tensor([[1, 2, 99, -4]]).cuda()
+    out = ops.gather_rows(table, ids)
+    assert float(out[0, 2].abs().max()) == 0.0 and float(out[0, 3].abs().max()) == 0.0
+    assert lib.rbr_consume_oob_count(None) == 2
