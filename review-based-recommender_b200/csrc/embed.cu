@@ -222,9 +222,9 @@ static int grid_for(int64_t work_items, int threads, int max_blocks = 148 * 16) 
 
 extern "C" int rbr_gather_fwd(const float* table, int64_t vocab, int64_t emb, const int64_t* ids, int64_t n_tokens,
                               float* out, void* stream) {
-    RBR_REQUIRE(table && ids && out, RBR_EINVAL, "rbr_gather_fwd: null pointer");
     RBR_REQUIRE(vocab > 0 && emb > 0 && n_tokens >= 0, RBR_EINVAL, "rbr_gather_fwd: bad sizes");
-    if (n_tokens == 0) return RBR_OK;
+    if (n_tokens == 0) return RBR_OK;                       // empty batch: pointers may legitimately be null
+    RBR_REQUIRE(table && ids && out, RBR_EINVAL, "rbr_gather_fwd: null pointer");
     cudaStream_t s = as_stream(stream);
     const bool vec = (emb % 4 == 0) && ((uintptr_t)table % 16 == 0) && ((uintptr_t)out % 16 == 0);
     if (vec) {
@@ -249,8 +249,9 @@ extern "C" int64_t rbr_embgrad_workspace_bytes(int64_t n_tokens, int64_t vocab) 
 extern "C" int rbr_embgrad_scatter_add(const int64_t* ids, const float* grad_rows, int64_t n_tokens, int64_t emb,
                                        int64_t vocab, int64_t padding_idx, float* table_grad, void* ws, int64_t ws_bytes,
                                        void* stream) {
-    RBR_REQUIRE(ids && grad_rows && table_grad, RBR_EINVAL, "rbr_embgrad_scatter_add: null pointer");
     RBR_REQUIRE(vocab > 0 && emb > 0 && n_tokens >= 0, RBR_EINVAL, "rbr_embgrad_scatter_add: bad sizes");
+    if (n_tokens == 0) return RBR_OK;
+    RBR_REQUIRE(ids && grad_rows && table_grad, RBR_EINVAL, "rbr_embgrad_scatter_add: null pointer");
     RBR_REQUIRE(n_tokens < (1ll << 31) && vocab < (1ll << 31), RBR_EUNSUPPORTED, "rbr_embgrad_scatter_add: > 2^31 entries");
     if (n_tokens == 0) return RBR_OK;
     cudaStream_t s = as_stream(stream);
