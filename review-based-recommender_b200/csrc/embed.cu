@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(256) table_to_bf16_kernel(const float* __restr
 }
 
 // K0: conv weight packing, weight [H][E][k] (nn.Conv1d) → the three layouts of PackLayout
-__global__ void conv_pack_kernel(const float* __restrict__ w, int E, int H, int k, int Hpad4, int Epad4, int Epad16, int Npad,
+__global__ void conv_pack_kernel(const float* __restrict__ w, int E, int H, int k, int Hpad4, int Epad4, int Epad16, int Npad, int Nb,
                                  float* __restrict__ keh, float* __restrict__ hke, __nv_bfloat16* __restrict__ umma) {
     const int64_t n_keh = (int64_t)k * E * Hpad4;
     const int64_t n_hke = (int64_t)H * k * Epad4;
@@ -196,14 +196,17 @@ __global__ void conv_pack_kernel(const float* __restrict__ w, int E, int H, int 
             const int h = (int)(r / ((int64_t)Epad4 * k));
             hke[r] = (e < E) ? w[((int64_t)h * E + e) * k + j] : 0.f;
         } else {
-            // [j][chunk c = e/8][row n][e%8]
+            // [pass][j][chunk c = e/8][row n][e%8],  filter h = pass*Nb + n
             const int64_t r = q - n_keh - n_hke;
+            const int C = Epad16 >> 3;
             const int e8 = (int)(r & 7);
-            const int n = (int)((r >> 3) % Npad);
-            const int c = (int)((r >> 3) / Npad % (Epad16 >> 3));
-            const int j = (int)((r >> 3) / ((int64_t)Npad * (Epad16 >> 3)));
+            int64_t u = r >> 3;
+            const int n = (int)(u % Nb); u /= Nb;
+            const int c = (int)(u % C); u /= C;
+            const int j = (int)(u % k); u /= k;
+            const int h = (int)u * Nb + n;
             const int e = c * 8 + e8;
-            const float v = (n < H && e < E) ? w[((int64_t)n * E + e) * k + j] : 0.f;
+            const float v = (h < H && e < E) ? w[((int64_t)h * E + e) * k + j] : 0.f;
             umma[r] = __float2bfloat16_rn(v);
         }
     }
@@ -313,7 +316,7 @@ extern "C" int rbr_conv_pack(const float* weight, int64_t emb, int64_t filters, 
     char* base = reinterpret_cast<char*>(packed);
     const int64_t total = ksize * emb * p.Hpad4 + filters * ksize * p.Epad4 + ksize * p.Epad16 * p.Npad;
     conv_pack_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(
-        weight, (int)emb, (int)filters, (int)ksize, (int)p.Hpad4, (int)p.Epad4, (int)p.Epad16, (int)p.Npad,
+        weight, (int)emb, (int)filters, (int)ksize, (int)p.Hpad4, (int)p.Epad4, (int)p.Epad16, (int)p.Npad, (int)(p.Nb > 0 ? p.Nb : 1),
         reinterpret_cast<float*>(base + p.off_keh), reinterpret_cast<float*>(base + p.off_hke),
         reinterpret_cast<__nv_bfloat16*>(base + p.off_umma));
     RBR_LAUNCH_CHECK("conv_pack");

@@ -56,13 +56,17 @@ __device__ __forceinline__ void note_oob() { atomicAdd(&g_oob_count, 1u); }
 // [0]            fp32  Wkeh  [k][E][Hpad4]      forward fp32 conv (filter index fastest)
 // [off_hke]      fp32  Whke  [H][k][Epad4]      backward (embedding index fastest)
 // [off_umma]     bf16  UMMA B operand, K-major no-swizzle core-matrix tiles:
-//                       [k][Epad16/8 chunks][Npad rows][8 bf16]
+//                       [P passes][k][Epad16/8 chunks][Nb rows][8 bf16]   (filter h = pass*Nb + row)
+// (P, Nb) come from tc_pass_split (conv_tc.cu): the largest filter block whose weights stay resident in
+// shared memory next to the activation ring; P == 0 means the tensor-core variant cannot take this shape.
+void tc_pass_split(int64_t E, int64_t H, int64_t K, int64_t* P, int64_t* Nb);
 struct PackLayout {
     int64_t E, H, k;
+    int64_t P, Nb;      // tensor-core filter passes and filters per pass
     int64_t Hpad4;      // H rounded up to 4
     int64_t Epad4;      // E rounded up to 4
     int64_t Epad16;     // E rounded up to 16 (UMMA K granularity for bf16)
-    int64_t Npad;       // H rounded up to 16 (UMMA N granularity at M=128)
+    int64_t Npad;       // P * Nb
     int64_t off_keh, off_hke, off_umma, total;
 };
 __host__ __device__ inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
@@ -72,7 +76,8 @@ inline PackLayout pack_layout(int64_t E, int64_t H, int64_t k) {
     p.Hpad4 = round_up(H, 4);
     p.Epad4 = round_up(E, 4);
     p.Epad16 = round_up(E, 16);
-    p.Npad = round_up(H, 16);
+    tc_pass_split(E, H, k, &p.P, &p.Nb);
+    p.Npad = p.P * p.Nb;
     p.off_keh = 0;
     int64_t b = k * E * p.Hpad4 * 4;
     p.off_hke = round_up(b, 256);

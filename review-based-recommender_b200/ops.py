@@ -323,3 +323,29 @@ class HeadFn(torch.autograd.Function):
                                    ctx.sizes[0], ctx.sizes[1], _p(g_pred), _p(g_ut), _p(g_it), *[_p(g) for g in grads],
                                    _stream()), "rbr_head_bwd")
         return (g_ut, g_it, None, None, *grads, None, None, None, None, None)
+
+
+# ---------------------------------------------------------------------------------------------------
+# Raw (no-autograd) entry used by the kernel-level tests and by bench.py's per-kernel roofline timing
+# ---------------------------------------------------------------------------------------------------
+def conv_act_maxpool(table: torch.Tensor, ids: torch.Tensor, mask: Optional[torch.Tensor], weight: torch.Tensor,
+                     bias: torch.Tensor, pad: int, act: int = ACT_RELU, precision: str = "bf16",
+                     shadow: Optional[torch.Tensor] = None, packed: Optional[torch.Tensor] = None):
+    """One K2 launch: returns (feat [n_docs, H] fp32, argmax [n_docs, H] int32)."""
+    table = _req(table, torch.float32, "table")
+    ids = _req(ids, torch.int64, "ids")
+    mask = _mask_u8(mask, "mask")
+    prec = _PREC[precision]
+    if prec == PREC_BF16 and shadow is None:
+        shadow = table_to_bf16(table)
+    if packed is None:
+        packed = conv_pack(weight)
+    h, emb, k = weight.shape
+    doc_len = ids.shape[-1]
+    n_docs = ids.numel() // doc_len
+    feat = torch.empty(n_docs, h, dtype=torch.float32, device=table.device)
+    amax = torch.empty(n_docs, h, dtype=torch.int32, device=table.device)
+    lib.check(lib.rbr_conv_act_maxpool_fwd(prec, act, _p(table), _p(shadow), table.shape[0], emb, _p(ids), _p(mask), None, 0,
+                                           n_docs, doc_len, _p(packed), _p(_req(bias, torch.float32, "bias")), h, k, pad,
+                                           _p(feat), _p(amax), h, _stream()), "rbr_conv_act_maxpool_fwd")
+    return feat, amax
