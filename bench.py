@@ -1,0 +1,379 @@
+#!/usr/bin/env python
+"""bench.py — fwd+bwd samples/s of the review-encoder hot path on N B200s (one process per GPU).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--model deepconn|narre] [--impl ours|reference]
+
+One "step" = optimizer.zero_grad() + forward + nn.MSELoss + backward (+ the gradient all-reduce when N > 1),
+i.e. trainer/train_deepconn_pp.py:161-165 of the reference, on BASELINE.json's configs[1]:
+DeepCoNN, B=4096 per GPU, doc 500 tokens, vocab 50k, emb 300, 100 filters k=3, bf16 conv, synthetic ratings.
+N > 1 is launched by torchrun (RANK/LOCAL_RANK/WORLD_SIZE/MASTER_* from the env); the per-GPU batch is fixed
+(weak scaling) and the only collective is the parameter-gradient all-reduce.
+
+Rank 0 prints ONE JSON line: value = device-timed whole-job samples/s with inputs resident in HBM; e2e = the
+same step driven from pinned HOST buffers through the public nn.Module API (H2D of every input and a D2H read
+of the loss inside the timed region); roofline = the dominant kernel (tcgen05 conv) against the measured
+bf16 peak; cpu_baseline = the CPU oracle (a port of the reference's path) timed on this box's host cores.
+`--impl reference` times that CPU path alone, as the reference arm.
+"""
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+CFG = {
+    "deepconn": dict(B=4096, L=500, V=50000, E=300, H=100, K=32, U=20000, I=12000, ks=(3,)),
+    "narre": dict(B=4096, R=10, T=60, V=50000, E=300, H=150, A=32, K=32, U=20000, I=12000, ks=(3,)),
+}
+METRIC = {"deepconn": "DeepCoNN fwd+bwd samples/sec", "narre": "NARRE fwd+bwd samples/sec"}
+
+
+def workload_name(model):
+    c = CFG[model]
+    if model == "deepconn":
+        return (f"DeepCoNN train step B={c['B']}/GPU doc={c['L']} vocab={c['V']} emb={c['E']} filters={c['H']} k=3 "
+                f"latent={c['K']} (BASELINE.json configs[1])")
+    return (f"NARRE train step B={c['B']}/GPU reviews={c['R']}x{c['T']} vocab={c['V']} emb={c['E']} filters={c['H']} k=3 "
+            f"att={c['A']} latent={c['K']} (BASELINE.json configs[2])")
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm=p["hbm_gbs"], tf=p["bf16_tflops"], tf_sus=p.get("bf16_tflops_sustained", p["bf16_tflops"]),
+                    src="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, tf=1590.0, tf_sus=1400.0, src="fallback (B200_PROFILING.md)")
+
+
+# ----------------------------------------------------------------------------------------------------
+# CPU arm: the oracle (port of the reference's PyTorch path) on the host cores
+# ----------------------------------------------------------------------------------------------------
+def cpu_arm(model, sample_b, steps, warmup):
+    from oracle import rbr_oracle as orc
+    from rbr_b200 import synth
+    c = CFG[model]
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    if model == "deepconn":
+        params = synth.deepconn_params(c["U"], c["I"], c["V"], c["E"], c["H"], c["K"], c["ks"], seed=0)
+        batch, ratings = synth.deepconn_batch(sample_b, c["L"], c["V"], c["U"], c["I"], seed=synth.SEED_BASE)
+    else:
+        params = synth.narre_params(c["U"], c["I"], c["V"], c["E"], c["H"], c["A"], c["K"], c["ks"], seed=0)
+        batch, ratings = synth.narre_batch(sample_b, c["R"], c["T"], c["V"], c["U"], c["I"], seed=synth.SEED_BASE)
+    sec = orc.time_fwd_bwd(model, params, batch, ratings, steps=steps, warmup=warmup)
+    return dict(value=sample_b / sec, unit="samples/s", cores=torch.get_num_threads(), kind="port",
+                sample=f"{sample_b} samples of the same workload per step, {steps} timed steps after {warmup} warm-up "
+                       f"(oracle/rbr_oracle.py, torch CPU, {torch.get_num_threads()} threads of {os.cpu_count()} cores)"), sec
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample_b = 128
+    steps = max(1, min(args.steps, 5))
+    warm = max(1, min(args.warmup, 2))
+    cb, sec = cpu_arm(args.model, sample_b, steps, warm)
+    line = {
+        "impl": "reference", "metric": METRIC[args.model], "value": cb["value"], "unit": "samples/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args.model), "sample_per_step": sample_b},
+        "cpu_baseline": cb,
+        "e2e": {"value": cb["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------
+# clocks sampler (NVML in a background thread, ~20 ms period, during the timed regions only)
+# ----------------------------------------------------------------------------------------------------
+class ClockSampler:
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+               0x80: "hw_power_brake_slowdown"}
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        while not self._stop.is_set():
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                mask = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def start(self):
+        if self.nv is not None:
+            self._stop.clear()
+            self._thr = threading.Thread(target=self._loop, daemon=True)
+            self._thr.start()
+
+    def stop(self):
+        if self._thr is not None:
+            self._stop.set()
+            self._thr.join()
+            self._thr = None
+
+    def summary(self):
+        return {"sm_mhz": statistics.median(self.samples) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ----------------------------------------------------------------------------------------------------
+def build(model_name, dev, precision):
+    import rbr_b200
+    from rbr_b200 import synth
+    c = CFG[model_name]
+    if model_name == "deepconn":
+        params = synth.deepconn_params(c["U"], c["I"], c["V"], c["E"], c["H"], c["K"], c["ks"], seed=0)
+        model = rbr_b200.DeepCoNNpp(c["U"], c["I"], c["V"], list(c["ks"]), c["E"], c["H"], c["K"], c["L"], None, 0.5,
+                                    precision=precision)
+    else:
+        params = synth.narre_params(c["U"], c["I"], c["V"], c["E"], c["H"], c["A"], c["K"], c["ks"], seed=0)
+        model = rbr_b200.NARRE(c["U"], c["I"], c["V"], list(c["ks"]), c["H"], c["E"], c["A"], c["K"], c["R"], c["T"], 0.5,
+                               0, 0, 0, None, "CNN", precision=precision)
+    model.load_state_dict(params)
+    return model.to(dev).train()
+
+
+def make_batches(model_name, n, rank):
+    from rbr_b200 import synth
+    c = CFG[model_name]
+    out = []
+    for i in range(n):
+        seed = synth.SEED_BASE + rank * 1000 + i
+        if model_name == "deepconn":
+            out.append(synth.deepconn_batch(c["B"], c["L"], c["V"], c["U"], c["I"], seed=seed))
+        else:
+            out.append(synth.narre_batch(c["B"], c["R"], c["T"], c["V"], c["U"], c["I"], seed=seed))
+    return out
+
+
+def step(model, batch, ratings, loss_fn, world):
+    from rbr_b200 import parallel
+    model.zero_grad(set_to_none=True)
+    out = model(*batch)
+    pred = out[0] if isinstance(out, tuple) else out
+    loss = loss_fn(pred, ratings)
+    loss.backward()
+    if world > 1:
+        parallel.allreduce_gradients(model)
+    return loss
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--model", default="deepconn", choices=["deepconn", "narre"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the NARRE / per-kernel extras")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch.distributed as dist
+    import rbr_b200
+    from rbr_b200 import ops, parallel
+    from rbr_b200._lib import lib
+
+    rank, local, world = parallel.init_from_env("nccl")
+    if world != args.gpus and rank == 0 and world > 1:
+        print(f"[bench] note: --gpus {args.gpus} but WORLD_SIZE={world}", file=sys.stderr)
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    peaks = load_peaks()
+    K, W = args.steps, max(args.warmup, 3)
+    c = CFG[args.model]
+    loss_fn = torch.nn.MSELoss()
+
+    model = build(args.model, dev, args.precision)
+    parallel.broadcast_parameters(model)
+    NB = 4   # distinct input batches rotated through: 4 x 37 MB of ids+masks > L2 together with table/grad traffic
+    host_batches = make_batches(args.model, NB, rank)
+    dev_batches = [([t.to(dev) for t in b], r.to(dev)) for b, r in host_batches]
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+
+    # ------------------------------ device-resident timing (value) ------------------------------
+    for i in range(W):
+        step(model, *dev_batches[i % NB], loss_fn, world)
+    sync_all()
+    l0 = lib.rbr_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.start()
+    e0.record()
+    for i in range(K):
+        loss = step(model, *dev_batches[i % NB], loss_fn, world)
+    e1.record()
+    sync_all()
+    sampler.stop()
+    launches = lib.rbr_launch_count() - l0
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    total_ms = float(ms.item())
+    value = world * c["B"] * K / (total_ms * 1e-3)
+    final_loss = float(loss.item())
+
+    # ------------------------------ end-to-end timing from pinned host buffers (e2e) ------------------------------
+    pinned = [([t.pin_memory() for t in b], r.pin_memory()) for b, r in host_batches]
+    h2d_bytes = sum(t.numel() * t.element_size() for t in pinned[0][0]) + pinned[0][1].numel() * 4
+    copy_stream = torch.cuda.Stream(device=dev)
+    loss_host = torch.zeros(2, dtype=torch.float32).pin_memory()
+
+    def upload(i):
+        with torch.cuda.stream(copy_stream):
+            b, r = pinned[i % NB]
+            d = [t.to(dev, non_blocking=True) for t in b], r.to(dev, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        return d, ev
+
+    def e2e_loop(n):
+        nxt = upload(0)
+        last = None
+        for i in range(n):
+            (b, r), ev = nxt
+            if i + 1 < n:
+                nxt = upload(i + 1)                      # H2D of step i+1 overlaps the compute of step i
+            torch.cuda.current_stream().wait_event(ev)
+            for t in b + [r]:
+                t.record_stream(torch.cuda.current_stream())
+            loss = step(model, b, r, loss_fn, world)
+            loss_host[i & 1].copy_(loss.detach(), non_blocking=True)     # D2H read of the step's result
+            done = torch.cuda.Event()
+            done.record()
+            if last is not None:
+                last.synchronize()                       # the host consumes step i-1's loss while step i runs
+            last = done
+        if last is not None:
+            last.synchronize()
+
+    e2e_loop(W)
+    sync_all()
+    sampler.start()
+    t0 = time.perf_counter()
+    e2e_loop(K)
+    sync_all()
+    t1 = time.perf_counter()
+    sampler.stop()
+    et = torch.tensor([t1 - t0], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(et, op=dist.ReduceOp.MAX)
+    e2e_value = world * c["B"] * K / float(et.item())
+
+    # ------------------------------ dominant kernel: tcgen05 conv forward, timed alone ------------------------------
+    roofline, extras = None, {}
+    if rank == 0:
+        we = model.word_embeddings
+        conv = model.ngram.conv
+        table = we.embedding.weight.detach()
+        shadow = we.bf16_shadow()
+        packed = conv.packed(0)
+        w0, b0 = conv.list_of_conv1d[0].weight.detach(), conv.list_of_conv1d[0].bias.detach()
+        if args.model == "deepconn":
+            sides = [(dev_batches[i][0][0], dev_batches[i][0][2]) for i in range(NB)]
+        else:
+            sides = [(dev_batches[i][0][0].view(-1, c["T"]), dev_batches[i][0][2].view(-1, c["T"])) for i in range(NB)]
+        n_tok = sides[0][0].numel()
+        flops = 2.0 * n_tok * c["H"] * c["E"] * 3
+        reps = 20
+        for i in range(3):
+            ops.conv_act_maxpool(table, *sides[i % NB], w0, b0, 1, precision=args.precision, shadow=shadow, packed=packed)
+        torch.cuda.synchronize()
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k0.record()
+        for i in range(reps):
+            ops.conv_act_maxpool(table, *sides[i % NB], w0, b0, 1, precision=args.precision, shadow=shadow, packed=packed)
+        k1.record()
+        torch.cuda.synchronize()
+        kms = k0.elapsed_time(k1) / reps
+        achieved = flops / (kms * 1e-3) / 1e12
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "conv_tc_traffic.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get(args.model)
+        roofline = {"kernel": "conv_tc_kernel (gather+conv+bias+ReLU+max-over-time, tcgen05)" if args.precision == "bf16"
+                    else "conv_fp32_kernel", "bound": "tensor", "achieved": achieved, "peak": peaks["tf"], "unit": "TFLOP/s",
+                    "frac": achieved / peaks["tf"], "traffic": traffic, "peak_source": peaks["src"] + ", burst (kernel timed alone)",
+                    "ms_per_launch": kms, "algorithmic_flops_per_launch": flops, "launches_per_step": 2}
+        if not args.no_extras:
+            # standalone fp32 gather (K1) against the HBM peak: tokens * (8 + 2*E*4) bytes
+            ids = sides[0][0]
+            g_bytes = n_tok * (8 + 2 * c["E"] * 4)
+            for _ in range(2):
+                out = ops.gather_rows(table, ids)
+            torch.cuda.synchronize()
+            k0.record()
+            for i in range(5):
+                out = ops.gather_rows(table, sides[i % NB][0])
+            k1.record()
+            torch.cuda.synchronize()
+            gms = k0.elapsed_time(k1) / 5
+            del out
+            extras["gather_fp32"] = {"bound": "hbm", "achieved": g_bytes / (gms * 1e-3) / 1e9, "peak": peaks["hbm"], "unit": "GB/s",
+                                     "frac": g_bytes / (gms * 1e-3) / 1e9 / peaks["hbm"], "ms_per_launch": gms}
+
+    # ------------------------------ CPU baseline on this box's host cores (rank 0, N=1 only) ------------------------------
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu_baseline, _ = cpu_arm(args.model, 128, 5, 1)
+
+    if rank == 0:
+        line = {
+            "metric": METRIC[args.model], "value": value, "unit": "samples/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": args.precision, "data": "synthetic",
+            "config": {"workload": workload_name(args.model), "global_batch": world * c["B"], "parallelism": f"dp{world}",
+                       "l2": f"inputs rotate over {NB} distinct batches ({NB * h2d_bytes / 1e6:.0f} MB of ids+masks) on top of "
+                             f"a 60 MB table, 30 MB bf16 shadow and 66 MB gradient buffer per step: larger than the 126 MB L2",
+                       "step": "zero_grad + forward + MSELoss + backward" + (" + gradient all-reduce" if world > 1 else "")},
+            "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
+                    "how": "pinned host buffers → H2D on a copy stream (prefetch depth 1) → nn.Module forward/backward → "
+                           "loss read back to pinned host memory every step; wall clock, max over ranks"},
+            "gpu_launches": int(launches), "gpu_launches_per_step": launches / K,
+            "clocks": sampler.summary(), "roofline": roofline, "cpu_baseline": cpu_baseline, "final_loss": final_loss,
+            "roofline_other": extras,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

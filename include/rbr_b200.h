@@ -46,6 +46,9 @@ const char* rbr_last_error(void);
 /* Number of out-of-range token/id values seen by any kernel since the last call (they are treated as
  * padding rows); synchronises `stream`.  The reference raises IndexError / a device assert instead. */
 int rbr_consume_oob_count(void* stream);
+/* Cumulative number of CUDA kernels this library has launched in this process (host-side counter,
+ * incremented at every launch site); bench.py reports the delta over its timed region. */
+int64_t rbr_launch_count(void);
 
 /* ---- K1: embedding row gather -------------------------------------------------------------------
  * Replaces nn.Embedding forward: WordEmbedding.forward, models/deepconn/layers.py:22-24

@@ -2,6 +2,7 @@
 #include "rbr_common.cuh"
 
 #include <string.h>
+#include <atomic>
 
 namespace rbr {
 
@@ -13,6 +14,9 @@ void set_error(const char* fmt, ...) {
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
 }
+
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 int cuda_fail(cudaError_t e, const char* what) {
     set_error("%s: %s", what, cudaGetErrorString(e));
@@ -40,6 +44,8 @@ using namespace rbr;
 extern "C" int rbr_version(void) { return 100; }   // 0.1.0
 
 extern "C" const char* rbr_last_error(void) { return g_err; }
+
+extern "C" int64_t rbr_launch_count(void) { return (int64_t)g_launches.load(std::memory_order_relaxed); }
 
 extern "C" int rbr_consume_oob_count(void* stream) {
     cudaStream_t s = as_stream(stream);

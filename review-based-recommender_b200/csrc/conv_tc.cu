@@ -120,6 +120,10 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
+__device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
@@ -178,6 +182,15 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
         : "r"(taddr)
         : "memory");
 }
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // order-preserving float → uint (and back)
@@ -225,6 +238,7 @@ __device__ __forceinline__ bool tc_row_source(const TcPlan& p, int64_t unit, int
     return true;
 }
 
+template <int KT>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
     const TcPlan& p = a.p;
@@ -262,18 +276,28 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcArgs a) 
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 8) {
-        // =========================== MMA issuer (one elected lane) ===========================
-        if (lane == 0 && my_tiles > 0) {
-            // resident B operand: one TMA bulk stream, <= 32 KB per copy
-            mbar_expect_tx(bar_w, (uint32_t)p.w_bytes);
-            const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(a.wpack) + (size_t)pass * p.w_bytes;
-            for (int off = 0; off < p.w_bytes; off += 32768) {
-                const int n = min(32768, p.w_bytes - off);
-                bulk_g2s(w_s + off, wsrc + off, (uint32_t)n, bar_w);
+        // =========================== MMA issuer ===========================
+        // The whole warp runs the (warp-uniform) control flow so every operand lives in uniform registers; one elected
+        // lane issues tcgen05.mma / tcgen05.commit.  Descriptors are advanced by integer adds on their low word.
+        if (my_tiles > 0) {
+            const bool leader = elect_one();
+            if (leader) {
+                // resident B operand: one TMA bulk stream, <= 32 KB per copy
+                mbar_expect_tx(bar_w, (uint32_t)p.w_bytes);
+                const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(a.wpack) + (size_t)pass * p.w_bytes;
+                for (int off = 0; off < p.w_bytes; off += 32768) {
+                    const int n = min(32768, p.w_bytes - off);
+                    bulk_g2s(w_s + off, wsrc + off, (uint32_t)n, bar_w);
+                }
             }
+            __syncwarp();
             mbar_wait(bar_w, 0);
             const uint32_t idesc = umma_idesc(TC_M, p.Nb);
-            const uint32_t a_lbo = (uint32_t)p.RS * 16u, b_lbo = (uint32_t)p.Nb * 16u;
+            const uint64_t a_desc0 = umma_desc(ring_s, (uint32_t)p.RS * 16u, 128u);      // stage 0, tap 0
+            const uint64_t b_desc0 = umma_desc(w_s, (uint32_t)p.Nb * 16u, 128u);         // tap 0, K-step 0
+            const uint32_t a_stage_inc = (uint32_t)p.stage_bytes >> 4;                    // descriptor address units (16 B)
+            const uint32_t b_tap_inc = (uint32_t)(p.C * p.Nb);                            // one tap = C chunk columns of Nb rows
+            const uint32_t b_step_inc = (uint32_t)(2 * p.Nb);                             // one K-step = 2 chunk columns
             int stage = 0;
             uint32_t ph = 0;
             for (int64_t g = 0; g < my_tiles; ++g) {
@@ -283,24 +307,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcArgs a) 
                 const uint32_t d_tmem = tmem_base + (uint32_t)(buf * p.acc_stride);
                 for (int s = 0; s < p.ksteps; ++s) {
                     mbar_wait(bar_full + 8 * stage, ph);
+                    fence_proxy_async();        // cp.async wrote through the generic proxy; the tensor core reads via the async proxy
                     tc_fence_after();
-                    const uint32_t a_base = ring_s + (uint32_t)(stage * p.stage_bytes);
-                    for (int j = 0; j < p.K; ++j) {
-                        const uint64_t ad = umma_desc(a_base + 16u * j, a_lbo, 128u);
-                        const uint64_t bd = umma_desc(w_s + (uint32_t)((j * p.C + 2 * s) * p.Nb * 16), b_lbo, 128u);
-                        umma_bf16(d_tmem, ad, bd, idesc, (uint32_t)((s | j) != 0));
+                    if (leader) {
+                        const uint64_t ad = a_desc0 + (uint64_t)((uint32_t)stage * a_stage_inc);
+                        const uint64_t bd = b_desc0 + (uint64_t)((uint32_t)s * b_step_inc);
+#pragma unroll
+                        for (int j = 0; j < KT; ++j)
+                            umma_bf16(d_tmem, ad + (uint64_t)j, bd + (uint64_t)(j * b_tap_inc), idesc, (uint32_t)((s | j) != 0));
+                        umma_commit(bar_empty + 8 * stage);                          // frees the ring slot when the MMAs retire
+                        if (s == p.ksteps - 1) umma_commit(bar_accf + 8 * buf);      // accumulator complete → epilogue
                     }
-                    umma_commit(bar_empty + 8 * stage);                              // frees the ring slot when the MMAs retire
+                    __syncwarp();
                     if (++stage == p.nst) { stage = 0; ph ^= 1; }
                 }
-                umma_commit(bar_accf + 8 * buf);                                     // accumulator complete → epilogue
             }
         }
         __syncwarp();
     } else if (warp >= 4) {
         // =========================== gather producers (128 threads) ===========================
         const int ptid = threadIdx.x - 128;
-        const int lag = p.nst - 1 < 7 ? p.nst - 1 : 7;       // cp.async groups kept in flight before signalling "full"
         // this thread stages pieces ptid, ptid+128, ptid+256 of each stage: piece → (row = piece>>1, half = piece&1)
         const char* src[3];
         uint32_t nbytes[3];
@@ -335,7 +361,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcArgs a) 
         };
         int stage = 0;
         uint32_t ph = 0;
-        int64_t issued = 0, signalled = 0;          // stages issued / stages whose "full" arrive was done
         prefetch_ids(0);
         for (int64_t g = 0; g < my_tiles; ++g) {
 #pragma unroll
@@ -358,20 +383,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcArgs a) 
                 const uint32_t sb = ring_s + (uint32_t)(stage * p.stage_bytes);
                 for (int i = 0; i < 3; ++i)
                     if (i < npieces) cp_async16(sb + dst_off[i], src[i] + (nbytes[i] ? s * 32 : 0), nbytes[i]);
-                cp_async_commit();
-                ++issued;
-                if (issued - signalled > lag) {
-                    cp_async_wait_dyn(lag);                         // the oldest un-signalled group has landed
-                    fence_proxy_async();                            // generic-proxy writes → visible to the tensor core (async proxy)
-                    mbar_arrive(bar_full + 8 * (int)(signalled % p.nst));
-                    ++signalled;
-                }
+                // hardware arrives on full[stage] when this thread's copies have landed: no software wait, so the
+                // ring depth (not an issue-side lag) bounds the bytes in flight
+                cp_async_arrive_noinc(bar_full + 8 * stage);
                 if (++stage == p.nst) { stage = 0; ph ^= 1; }
             }
         }
-        cp_async_wait<0>();
-        fence_proxy_async();
-        for (; signalled < issued; ++signalled) mbar_arrive(bar_full + 8 * (int)(signalled % p.nst));
+        cp_async_wait_all();
     } else {
         // =========================== epilogue (warps 0-3; warp w owns TMEM lanes 32w..32w+31) ===========================
         const int m = warp * 32 + lane;                       // tile row = TMEM lane
@@ -513,14 +531,28 @@ int conv_tc_dispatch(const __nv_bfloat16* shadow, int64_t vocab, int E, const in
         int dev = 0;
         RBR_CUDA(cudaGetDevice(&dev));
         RBR_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-        RBR_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_MAX));
     }
     // persistent grid: one CTA per SM (a multiple of the pass count), never more CTAs than units
     int64_t grid = num_sms / a.p.P * a.p.P;
     if (grid < a.p.P) grid = a.p.P;
     const int64_t max_useful = a.p.n_units * a.p.P;
     if (grid > max_useful) grid = max_useful;
-    conv_tc_kernel<<<(unsigned)grid, TC_THREADS, a.p.smem_bytes, s>>>(a);
+#define RBR_TC(KT_)                                                                                               \
+    case KT_: {                                                                                                   \
+        static bool attr = false;                                                                                 \
+        if (!attr) {                                                                                              \
+            RBR_CUDA(cudaFuncSetAttribute(conv_tc_kernel<KT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_MAX)); \
+            attr = true;                                                                                          \
+        }                                                                                                         \
+        conv_tc_kernel<KT_><<<(unsigned)grid, TC_THREADS, a.p.smem_bytes, s>>>(a);                                \
+    } break;
+    switch (K) {
+        RBR_TC(1) RBR_TC(2) RBR_TC(3) RBR_TC(4) RBR_TC(5) RBR_TC(7)
+        default:
+            set_error("conv_fwd[bf16]: kernel size %d not supported (1,2,3,4,5,7)", K);
+            return RBR_EUNSUPPORTED;
+    }
+#undef RBR_TC
     RBR_LAUNCH_CHECK("conv_tc_kernel");
     return RBR_OK;
 }

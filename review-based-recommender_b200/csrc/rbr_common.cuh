@@ -28,8 +28,10 @@ int cuda_fail(cudaError_t e, const char* what);
         if (e__ != cudaSuccess) return rbr::cuda_fail(e__, #call);       \
     } while (0)
 
+void count_launch();
 #define RBR_LAUNCH_CHECK(name)                                           \
     do {                                                                 \
+        rbr::count_launch();                                             \
         cudaError_t e__ = cudaGetLastError();                            \
         if (e__ != cudaSuccess) return rbr::cuda_fail(e__, name);        \
     } while (0)
