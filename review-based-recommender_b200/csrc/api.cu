@@ -27,7 +27,7 @@ int conv_fp32_dispatch(const float* table, int64_t vocab, int E, const int64_t* 
                        int gate_mode, int64_t n_docs, int L, const float* keh, int Hpad4, const float* bias, int H, int K,
                        int pad, int act, float* feat, int32_t* argmax, int feat_ld, cudaStream_t s);
 int conv_tc_dispatch(const __nv_bfloat16* shadow, int64_t vocab, int E, const int64_t* ids, const uint8_t* mask,
-                     const float* gate, int gate_mode, int64_t n_docs, int L, const __nv_bfloat16* umma_w, int Npad,
+                     const float* gate, int gate_mode, int64_t n_docs, int L, const __nv_bfloat16* umma_w, const void* zero_row,
                      const float* bias, int H, int K, int pad, int act, float* feat, int32_t* argmax, int feat_ld,
                      cudaStream_t s);
 
@@ -86,7 +86,7 @@ extern "C" int rbr_conv_act_maxpool_fwd(int precision, int activation, const voi
     if (precision == RBR_PREC_BF16) {
         RBR_REQUIRE(shadow_bf16, RBR_EINVAL, "conv_fwd: bf16 precision needs the bf16 shadow table");
         return conv_tc_dispatch(reinterpret_cast<const __nv_bfloat16*>(shadow_bf16), vocab, (int)emb, ids, mask, gate, gate_mode,
-                                n_docs, (int)doc_len, reinterpret_cast<const __nv_bfloat16*>(pk + pl.off_umma), (int)pl.Npad,
+                                n_docs, (int)doc_len, reinterpret_cast<const __nv_bfloat16*>(pk + pl.off_umma), pk + pl.off_zero,
                                 bias, (int)filters, (int)ksize, (int)pad, activation, feat, argmax, (int)feat_ld, s);
     }
     set_error("conv_fwd: unknown precision %d", precision);

@@ -17,12 +17,12 @@
 // warp 8 = TMEM allocator + single-thread tcgen05.mma issuer.  mbarrier pipelines: full/empty per ring stage,
 // acc_full/acc_empty per TMEM buffer.
 //
-// Max-over-time without cross-lane shuffles of floats: positions are TMEM lanes, so the max over positions is a max over
-// the 32 threads of a warp.  Each value is turned into an order-preserving 32-bit key whose low IB bits are replaced by
-// (2^IB-1 - t): one redux.sync.max.u32 per column then yields max value AND first arg-max; warps/tiles of a document
-// are merged with shared-memory atomicMax.  Replacing the low IB mantissa bits costs <= 2^(IB-23) relative error (IB=9 for
-// L=500: 6e-5), far inside the bf16 tolerance of this variant (1e-2).  Bias and activation are applied once per
-// (doc, filter) after the max (both monotone), not per position.
+// Max-over-time without shuffling floats: positions are TMEM lanes, so the max over positions is a max over the 32 threads
+// of a warp.  Each fp32 accumulator is mapped to an order-preserving uint32; one redux.sync.max.u32 per column gives the
+// exact max, a ballot + ffs gives the FIRST position attaining it (nn.MaxPool1d's tie rule), and the (value, ~position)
+// pair is merged across warps and across the tiles of a document with a 64-bit shared-memory atomicMax.  The pooled value
+// is therefore the exact fp32 accumulator.  Bias and activation are applied once per (doc, filter) after the max (both
+// monotone), not per position.
 #include "rbr_common.cuh"
 
 namespace rbr {
@@ -32,7 +32,13 @@ namespace rbr {
 // ------------------------------------------------------------------------------------------------
 constexpr int TC_SMEM_MAX = 232448;        // 227 KB opt-in dynamic shared memory per CTA
 constexpr int TC_M = 128;                  // UMMA M (positions per tile)
-constexpr int TC_THREADS = 288;
+constexpr int TC_EPI_WARPS = 8;             // two per TMEM lane quadrant, each takes half of the 16-column chunks
+constexpr int TC_EPI_THREADS = TC_EPI_WARPS * 32;
+constexpr int TC_PROD_WARP0 = TC_EPI_WARPS;   // 4 producer warps
+constexpr int TC_MMA_WARP = TC_EPI_WARPS + 4;
+constexpr int TC_THREADS = (TC_MMA_WARP + 1) * 32;
+// TC_KPS (template parameter KPS of the kernel): UMMA K-steps per ring stage — one mbarrier round trip feeds KPS * k
+// MMAs.  2 when the ring can still hold >= 5 stages (small weight tiles), else 1.
 constexpr int TC_MAX_SLOTS = 6;            // documents packed into one tile (short-document mode)
 
 struct TcPlan {
@@ -42,7 +48,9 @@ struct TcPlan {
     int P, Nb;        // filter passes, filters per pass (multiple of 16)
     int RS;           // staged rows per chunk column (>= 128 + K - 1, == 4 mod 8 → conflict-free cp.async stores)
     int rows;         // 128 + K - 1
-    int stage_bytes;  // 2 * RS * 16
+    int kps;          // K-steps per ring stage (1 or 2)
+    int stage_bytes;  // 2 * kps * RS * 16
+    int nstages_k;    // ring stages consumed per tile = ceil(ksteps / TC_KPS)
     int nst;          // ring stages
     int w_bytes;      // K * C * Nb * 16
     int mode_b;       // 1 = several short docs per tile
@@ -55,9 +63,12 @@ struct TcPlan {
     int act;
 };
 
-__host__ __device__ inline int tc_rs(int K) {
+// rows per chunk column: >= 128 + K - 1, and == 4 (mod 8) for 2 chunk columns per stage / == 2 (mod 8) for 4, so that
+// the chunk columns x rows written by a quarter-warp of cp.async lanes land in 8 distinct 16-byte bank groups
+__host__ __device__ inline int tc_rs(int K, int kps) {
     const int need = TC_M + K - 1;
-    int s = (need / 8) * 8 + 4;
+    const int rem = kps == 1 ? 4 : 2;
+    int s = (need / 8) * 8 + rem;
     return s >= need ? s : s + 8;
 }
 
@@ -65,8 +76,8 @@ __host__ __device__ inline int tc_rs(int K) {
 void tc_pass_split(int64_t E, int64_t H, int64_t K, int64_t* P, int64_t* Nb) {
     const int64_t epad16 = round_up(E, 16);
     const int64_t bytes_per_n = K * epad16 * 2;
-    const int64_t ring_min = 4 * 2 * tc_rs((int)K) * 16;
-    const int64_t budget = TC_SMEM_MAX - ring_min - 4096;
+    const int64_t ring_min = 4 * 2 * tc_rs((int)K, 1) * 16;
+    const int64_t budget = TC_SMEM_MAX - ring_min - 6144;
     int64_t nb_max = budget / bytes_per_n / 16 * 16;
     if (nb_max > 256) nb_max = 256;
     if (nb_max < 16) { *P = 0; *Nb = 0; return; }          // tensor-core variant unavailable for this shape
@@ -100,16 +111,12 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
-// Bounded wait: a pipeline bug must surface as a launch failure, not as a hung GPU.
+// Bounded wait: a pipeline bug must surface as a launch failure (trap), not as a hung GPU.  try_wait suspends the
+// thread in hardware for a bounded time per poll, so the poll counter stays cheap (one add per failed poll).
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    if (mbar_try_wait(bar, parity)) return;
-    const long long t0 = clock64();
+    uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 4000000000ll) {   // ~2 s at 2 GHz
-            printf("rbr conv_tc: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar,
-                   parity);
-            __trap();
-        }
+        if (++spins > (1u << 22)) __trap();
     }
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
@@ -119,6 +126,10 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+template <int OFF>
+__device__ __forceinline__ void cp_async16_imm(uint32_t dst, const void* src, uint32_t src_bytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1+%2], 16, %3;" ::"r"(dst), "l"(src), "n"(OFF), "r"(src_bytes) : "memory");
 }
 __device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
@@ -197,6 +208,25 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 __device__ __forceinline__ uint32_t f2ord(uint32_t b) { return b ^ ((uint32_t)((int32_t)b >> 31) | 0x80000000u); }
 __device__ __forceinline__ uint32_t ord2f(uint32_t u) { return (u & 0x80000000u) ? (u ^ 0x80000000u) : ~u; }
 
+// Column-wise max over the 32 rows (lanes) of a warp for 16 accumulator columns held as raw fp32 bits.
+// Positive floats order like signed ints, so one redux.sync.max.s32 gives the exact max whenever any candidate is >= 0;
+// an all-negative column (rare: it pools to relu(...)=0 unless the bias rescues it) takes a second redux.min.u32.
+// keep_v/keep_b: lane i (< 16) ends up holding column i's max bits and the ballot of rows attaining it.
+template <bool FULL>
+__device__ __forceinline__ void tc_colmax(const uint32_t (&v)[16], bool mine, int lane, uint32_t& keep_v, uint32_t& keep_b) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const int x = (FULL || mine) ? (int)v[i] : (int)0x80000000;
+        int r = __reduce_max_sync(0xffffffffu, x);
+        if (r < 0) {                                                   // warp-uniform
+            const uint32_t y = (FULL || mine) ? v[i] : 0xFFFFFFFFu;
+            r = (int)__reduce_min_sync(0xffffffffu, y);                // smallest magnitude among negatives
+        }
+        const uint32_t b = __ballot_sync(0xffffffffu, (FULL || mine) && (int)v[i] == r);
+        if ((lane & 15) == i) { keep_v = (uint32_t)r; keep_b = b; }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------
@@ -207,6 +237,7 @@ struct TcArgs {
     const uint8_t* mask;
     int64_t n_docs;
     const __nv_bfloat16* wpack;      // [P][K][C][Nb][8]
+    const void* zero_row;            // >= emb_pad*2 zero bytes (global): source of rows that must read as zeros
     const float* bias;
     float* feat;
     int32_t* argmax;
@@ -238,15 +269,16 @@ __device__ __forceinline__ bool tc_row_source(const TcPlan& p, int64_t unit, int
     return true;
 }
 
-template <int KT>
+template <int KT, int TC_KPS>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcArgs a) {
+    constexpr int TC_CPS = 2 * TC_KPS;          // 16-byte chunk columns per stage
     extern __shared__ __align__(128) uint8_t smem[];
     const TcPlan& p = a.p;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t sbase = smem_u32(smem);
     const uint32_t w_s = sbase + p.off_w, ring_s = sbase + p.off_ring;
     float* bias_s = reinterpret_cast<float*>(smem + p.off_bias);
-    uint32_t* keys_s = reinterpret_cast<uint32_t*>(smem + p.off_keys);
+    unsigned long long* keys_s = reinterpret_cast<unsigned long long*>(smem + p.off_keys);
     const uint32_t bars = sbase + p.off_bars;
     // barrier slots: full[nst], empty[nst], acc_full[2], acc_empty[2], w_ready
     const uint32_t bar_full = bars, bar_empty = bars + 8 * p.nst, bar_accf = bars + 16 * p.nst, bar_acce = bar_accf + 16,
@@ -263,19 +295,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcArgs a) 
     if (threadIdx.x == 0) {
         for (int i = 0; i < p.nst; ++i) { mbar_init(bar_full + 8 * i, 128); mbar_init(bar_empty + 8 * i, 1); }
         mbar_init(bar_accf, 1); mbar_init(bar_accf + 8, 1);
-        mbar_init(bar_acce, 128); mbar_init(bar_acce + 8, 128);
+        mbar_init(bar_acce, TC_EPI_THREADS); mbar_init(bar_acce + 8, TC_EPI_THREADS);
         mbar_init(bar_w, 1);
         fence_barrier_init();
     }
     for (int i = threadIdx.x; i < p.Nb; i += blockDim.x) bias_s[i] = (h0 + i < p.H) ? a.bias[h0 + i] : 0.f;
-    for (int i = threadIdx.x; i < p.D * p.Nb; i += blockDim.x) keys_s[i] = 0u;
-    if (warp == 8) tmem_alloc(smem_u32((const void*)tmem_slot), (uint32_t)p.tmem_cols);
+    for (int i = threadIdx.x; i < p.D * p.Nb; i += blockDim.x) keys_s[i] = 0ull;
+    if (warp == TC_MMA_WARP) tmem_alloc(smem_u32((const void*)tmem_slot), (uint32_t)p.tmem_cols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 8) {
+    if (warp == TC_MMA_WARP) {
         // =========================== MMA issuer ===========================
         // The whole warp runs the (warp-uniform) control flow so every operand lives in uniform registers; one elected
         // lane issues tcgen05.mma / tcgen05.commit.  Descriptors are advanced by integer adds on their low word.
@@ -300,60 +332,77 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcArgs a) 
             const uint32_t b_step_inc = (uint32_t)(2 * p.Nb);                             // one K-step = 2 chunk columns
             int stage = 0;
             uint32_t ph = 0;
+            uint32_t full_bar = bar_full, empty_bar = bar_empty;
+            uint64_t ad = a_desc0;
+            const int last = p.nstages_k - 1;
+            const uint32_t a_kstep_inc = (uint32_t)(2 * p.RS);                       // one K-step = 2 chunk columns of RS rows
             for (int64_t g = 0; g < my_tiles; ++g) {
                 const int buf = (int)(g & 1);
                 mbar_wait(bar_acce + 8 * buf, (uint32_t)(((g >> 1) & 1) ^ 1));      // epilogue drained this accumulator
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(buf * p.acc_stride);
-                for (int s = 0; s < p.ksteps; ++s) {
-                    mbar_wait(bar_full + 8 * stage, ph);
-                    fence_proxy_async();        // cp.async wrote through the generic proxy; the tensor core reads via the async proxy
+                uint64_t bd = b_desc0;
+                for (int s = 0; s <= last; ++s) {
+                    // No proxy fence here: the ring is written by cp.async whose completion is what flips this mbarrier
+                    // (cp.async.mbarrier.arrive), the same producer/consumer protocol CUTLASS's sm100 cp.async mainloop uses.
+                    mbar_wait(full_bar, ph);
                     tc_fence_after();
                     if (leader) {
-                        const uint64_t ad = a_desc0 + (uint64_t)((uint32_t)stage * a_stage_inc);
-                        const uint64_t bd = b_desc0 + (uint64_t)((uint32_t)s * b_step_inc);
 #pragma unroll
-                        for (int j = 0; j < KT; ++j)
-                            umma_bf16(d_tmem, ad + (uint64_t)j, bd + (uint64_t)(j * b_tap_inc), idesc, (uint32_t)((s | j) != 0));
-                        umma_commit(bar_empty + 8 * stage);                          // frees the ring slot when the MMAs retire
-                        if (s == p.ksteps - 1) umma_commit(bar_accf + 8 * buf);      // accumulator complete → epilogue
+                        for (int ks = 0; ks < TC_KPS; ++ks) {
+                            if (s * TC_KPS + ks < p.ksteps) {
+#pragma unroll
+                                for (int j = 0; j < KT; ++j)
+                                    umma_bf16(d_tmem, ad + (uint64_t)(ks * a_kstep_inc + j),
+                                              bd + (uint64_t)(ks * b_step_inc + j * b_tap_inc), idesc, (uint32_t)((s | ks | j) != 0));
+                            }
+                        }
+                        umma_commit(empty_bar);                                      // frees the ring slot when the MMAs retire
+                        if (s == last) umma_commit(bar_accf + 8 * buf);              // accumulator complete → epilogue
                     }
                     __syncwarp();
-                    if (++stage == p.nst) { stage = 0; ph ^= 1; }
+                    bd += (uint64_t)(TC_KPS * b_step_inc);
+                    ad += a_stage_inc;
+                    full_bar += 8;
+                    empty_bar += 8;
+                    if (++stage == p.nst) { stage = 0; ph ^= 1; ad = a_desc0; full_bar = bar_full; empty_bar = bar_empty; }
                 }
             }
         }
         __syncwarp();
-    } else if (warp >= 4) {
+    } else if (warp >= TC_PROD_WARP0) {
         // =========================== gather producers (128 threads) ===========================
-        const int ptid = threadIdx.x - 128;
-        // this thread stages pieces ptid, ptid+128, ptid+256 of each stage: piece → (row = piece>>1, half = piece&1)
-        const char* src[3];
-        uint32_t nbytes[3];
-        uint32_t dst_off[3];
+        // Each thread owns up to 3 fixed 16-byte pieces (row, half) of every stage.  The loop is issue-latency bound (one warp
+        // per scheduler), so it is kept to a handful of instructions per stage: row pointers are resolved once per tile,
+        // rows that must read as zeros (conv padding, masked tokens, bad ids) point at a zero row so every copy is an
+        // unconditional 16-byte cp.async, and four stages are unrolled so the K offset is an immediate.
+        const int ptid = threadIdx.x - TC_PROD_WARP0 * 32;
+        // piece → (row = piece / TC_CPS, chunk column c = piece % TC_CPS): TC_CPS adjacent lanes fetch 16*TC_CPS contiguous
+        // bytes of one token row.  Pieces ptid + 128*i, i < PP; a thread's pieces all share c and rows step by 128/TC_CPS.
+        constexpr int PP = (TC_CPS * (TC_M + 8) + 127) / 128;          // covers rows up to 128 + 7 (k <= 7... see plan check)
+        constexpr int ROWSTEP = 128 / TC_CPS;
+        const int my_c = ptid % TC_CPS;
+        const int my_r0 = ptid / TC_CPS;
+        const uint32_t d0 = (uint32_t)(my_c * p.RS * 16 + my_r0 * 16);
         int npieces = 0;
-        for (int i = 0; i < 3; ++i) {
-            const int piece = ptid + 128 * i;
-            if (piece < 2 * p.rows) {
-                dst_off[i] = (uint32_t)((piece & 1) * p.RS * 16 + (piece >> 1) * 16);
-                npieces = i + 1;
-            }
-        }
+#pragma unroll
+        for (int i = 0; i < PP; ++i)
+            if (my_r0 + ROWSTEP * i < p.rows) npieces = i + 1;
         // token ids / mask bytes of tile g+1 are fetched while tile g streams, so the id → row-address dependency
         // (two dependent global loads) never stalls the ring.
-        int64_t id_next[3];
-        uint8_t ok_next[3];
+        int64_t id_next[PP];
+        uint8_t ok_next[PP];
         auto prefetch_ids = [&](int64_t g) {
             const int64_t unit = cta_in_pass + (g / p.tpu) * ctas_per_pass;
             const int tt = (int)(g % p.tpu);
 #pragma unroll
-            for (int i = 0; i < 3; ++i) {
+            for (int i = 0; i < PP; ++i) {
                 id_next[i] = -1;
                 ok_next[i] = 0;
                 if (i >= npieces || g >= my_tiles) continue;
                 int64_t doc;
                 int t;
-                if (tc_row_source(p, unit, tt, (ptid + 128 * i) >> 1, a.n_docs, &doc, &t)) {
+                if (tc_row_source(p, unit, tt, my_r0 + ROWSTEP * i, a.n_docs, &doc, &t)) {
                     id_next[i] = a.ids[doc * p.L + t];
                     ok_next[i] = a.mask ? a.mask[doc * p.L + t] : (uint8_t)1;
                 }
@@ -361,39 +410,47 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcArgs a) 
         };
         int stage = 0;
         uint32_t ph = 0;
+        uint32_t sb = ring_s + d0;
         prefetch_ids(0);
         for (int64_t g = 0; g < my_tiles; ++g) {
+            // rows that must read as zeros (conv padding, masked tokens, bad ids) keep src_bytes = 0: cp.async then
+            // zero-fills the 16 bytes without issuing a memory request (a shared "zero row" would be an L2 hot spot)
+            const char* src[PP];
+            uint32_t nb[PP];
 #pragma unroll
-            for (int i = 0; i < 3; ++i) {
+            for (int i = 0; i < PP; ++i) {
                 src[i] = reinterpret_cast<const char*>(a.shadow);
-                nbytes[i] = 0;
+                nb[i] = 0;
                 if (ok_next[i]) {
                     const int64_t id = id_next[i];
-                    if (id >= 0 && id < a.vocab) {
-                        src[i] = reinterpret_cast<const char*>(a.shadow + id * a.emb_pad) + ((ptid + 128 * i) & 1) * 16;
-                        nbytes[i] = 16;
-                    } else if (((ptid + 128 * i) & 1) == 0) {
-                        note_oob();
-                    }
+                    if (id >= 0 && id < a.vocab) { src[i] = reinterpret_cast<const char*>(a.shadow + id * a.emb_pad) + my_c * 16; nb[i] = 16; }
+                    else if (my_c == 0) note_oob();
                 }
             }
             prefetch_ids(g + 1);
-            for (int s = 0; s < p.ksteps; ++s) {
+            // the last stage of an odd K-step count copies one K-step of row padding (zeros inside the 128-byte aligned
+            // shadow row) that no MMA reads
+            for (int s = 0; s < p.nstages_k; ++s) {
                 mbar_wait(bar_empty + 8 * stage, ph ^ 1);
-                const uint32_t sb = ring_s + (uint32_t)(stage * p.stage_bytes);
-                for (int i = 0; i < 3; ++i)
-                    if (i < npieces) cp_async16(sb + dst_off[i], src[i] + (nbytes[i] ? s * 32 : 0), nbytes[i]);
-                // hardware arrives on full[stage] when this thread's copies have landed: no software wait, so the
-                // ring depth (not an issue-side lag) bounds the bytes in flight
+#pragma unroll
+                for (int i = 0; i < PP; ++i)
+                    if (i < npieces) cp_async16_imm<0>(sb + (uint32_t)(i * ROWSTEP * 16), src[i], nb[i]);
                 cp_async_arrive_noinc(bar_full + 8 * stage);
-                if (++stage == p.nst) { stage = 0; ph ^= 1; }
+#pragma unroll
+                for (int i = 0; i < PP; ++i) src[i] += 16 * TC_CPS;
+                sb += (uint32_t)p.stage_bytes;
+                if (++stage == p.nst) { stage = 0; ph ^= 1; sb = ring_s + d0; }
             }
         }
         cp_async_wait_all();
     } else {
         // =========================== epilogue (warps 0-3; warp w owns TMEM lanes 32w..32w+31) ===========================
-        const int m = warp * 32 + lane;                       // tile row = TMEM lane
-        const uint32_t idx_mask = (1u << p.ib) - 1u;
+        const int quad = warp & 3;                            // TMEM lane quadrant this warp may read
+        const int half = warp >> 2;                           // which share of the 16-column chunks it reduces
+        const int m = quad * 32 + lane;                       // tile row = TMEM lane
+        const int n_chunks = p.Nb / 16;
+        const int chunk_lo = half ? (n_chunks + 1) / 2 : 0;
+        const int chunk_hi = half ? n_chunks : (n_chunks + 1) / 2;
         for (int64_t g = 0; g < my_tiles; ++g) {
             const int64_t unit = cta_in_pass + (g / p.tpu) * ctas_per_pass;
             const int tt = (int)(g % p.tpu);
@@ -402,59 +459,62 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcArgs a) 
             int slot, t;
             if (p.mode_b) { slot = m / p.Lext; t = m - slot * p.Lext; } else { slot = 0; t = tt * TC_M + m; }
             const bool valid = (t < p.Lout) && (slot < p.D) && ((p.mode_b ? unit * p.D + slot : unit) < a.n_docs);
-            const uint32_t tbits = idx_mask - (uint32_t)t;    // smaller t → larger key on ties
             // slots this warp's 32 rows touch
-            const int slot_lo = p.mode_b ? (warp * 32) / p.Lext : 0;
-            int slot_hi = p.mode_b ? (warp * 32 + 31) / p.Lext : 0;
+            const int slot_lo = p.mode_b ? (quad * 32) / p.Lext : 0;
+            int slot_hi = p.mode_b ? (quad * 32 + 31) / p.Lext : 0;
             if (slot_hi >= p.D) slot_hi = p.D - 1;
 
             mbar_wait(bar_accf + 8 * buf, (uint32_t)((g >> 1) & 1));
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * p.acc_stride);
-            for (int c0 = 0; c0 < p.Nb; c0 += 16) {
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * p.acc_stride);
+            for (int ch = chunk_lo; ch < chunk_hi; ++ch) {
+                const int c0 = ch * 16;
                 uint32_t v[16];
                 tmem_ld16(taddr + (uint32_t)c0, v);
                 tmem_ld_wait();
-                if (c0 + 16 >= p.Nb) {                        // last chunk is in registers: release the accumulator
+                if (ch == chunk_hi - 1) {                     // this warp's last chunk is in registers: release the accumulator
                     tc_fence_before();
                     mbar_arrive(bar_acce + 8 * buf);
                 }
-#pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] = (f2ord(v[i]) & ~idx_mask) | tbits;
                 for (int sl = slot_lo; sl <= slot_hi; ++sl) {
                     const bool mine = valid && slot == sl;
-                    uint32_t keep = 0;
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const uint32_t r = __reduce_max_sync(0xffffffffu, mine ? v[i] : 0u);
-                        if ((lane & 15) == i) keep = r;        // lane i (and i+16) keeps column c0+i
+                    uint32_t keep_v = 0, keep_b = 0;
+                    if (__all_sync(0xffffffffu, mine)) tc_colmax<true>(v, true, lane, keep_v, keep_b);
+                    else tc_colmax<false>(v, mine, lane, keep_v, keep_b);
+                    if (lane < 16 && keep_b) {
+                        // first (smallest-position) row attaining the max; rows of one slot are consecutive lanes
+                        const int first = __ffs(keep_b) - 1;
+                        const int tf = p.mode_b ? (quad * 32 + first - sl * p.Lext) : (tt * TC_M + quad * 32 + first);
+                        const unsigned long long key =
+                            ((unsigned long long)f2ord(keep_v) << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)tf);
+                        atomicMax(keys_s + sl * p.Nb + c0 + lane, key);
                     }
-                    if (lane < 16 && keep) atomicMax(keys_s + sl * p.Nb + c0 + lane, keep);
                 }
             }
+            if (chunk_lo == chunk_hi) { tc_fence_before(); mbar_arrive(bar_acce + 8 * buf); }   // Nb == 16: upper half idle
             if (tt == p.tpu - 1) {
                 // ---- unit finished: merge is complete once all 4 epilogue warps have posted their keys
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                for (int o = threadIdx.x; o < p.D * p.Nb; o += 128) {
+                asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_THREADS) : "memory");
+                for (int o = threadIdx.x; o < p.D * p.Nb; o += TC_EPI_THREADS) {
                     const int sl = o / p.Nb, c = o - sl * p.Nb;
                     const int64_t doc = p.mode_b ? unit * p.D + sl : unit;
-                    const uint32_t key = keys_s[o];
-                    keys_s[o] = 0u;
+                    const unsigned long long key = keys_s[o];
+                    keys_s[o] = 0ull;
                     if (doc < a.n_docs && h0 + c < p.H) {
-                        const float raw = __uint_as_float(ord2f(key & ~idx_mask));
-                        const int tbest = (int)(idx_mask - (key & idx_mask));
+                        const float raw = __uint_as_float(ord2f((uint32_t)(key >> 32)));
+                        const int tbest = (int)(0xFFFFFFFFu - (uint32_t)key);
                         a.feat[doc * a.feat_ld + h0 + c] = act_apply(p.act, raw + bias_s[c]);
                         a.argmax[doc * a.feat_ld + h0 + c] = tbest;
                     }
                 }
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+                asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_THREADS) : "memory");
             }
         }
     }
     // teardown
     tc_fence_before();
     __syncthreads();
-    if (warp == 8) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+    if (warp == TC_MMA_WARP) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
 }
 
 static bool tc_make_plan(int E, int H, int K, int L, int pad, int act, int64_t n_docs, TcPlan* out) {
@@ -471,13 +531,11 @@ static bool tc_make_plan(int E, int H, int K, int L, int pad, int act, int64_t n
     if (P == 0) return false;
     p.P = (int)P; p.Nb = (int)Nb;
     p.rows = TC_M + K - 1;
-    p.RS = tc_rs(K);
-    p.stage_bytes = 2 * p.RS * 16;
     p.w_bytes = K * p.C * p.Nb * 16;
     if (p.Lext <= TC_M + K - 1 && p.Lext * 2 <= TC_M + K - 1) {
         p.mode_b = 1;
         p.D = (TC_M + K - 1) / p.Lext;
-        int dmax = 3072 / (p.Nb * 4);
+        int dmax = 4096 / (p.Nb * 8);
         if (dmax > TC_MAX_SLOTS) dmax = TC_MAX_SLOTS;
         if (dmax < 1) dmax = 1;
         if (p.D > dmax) p.D = dmax;
@@ -489,25 +547,31 @@ static bool tc_make_plan(int E, int H, int K, int L, int pad, int act, int64_t n
         p.tpu = (p.Lout + TC_M - 1) / TC_M;
         p.n_units = n_docs;
     }
-    p.ib = 7;
-    while ((1 << p.ib) < p.Lout) ++p.ib;
-    if (p.mode_b) { p.ib = 7; while ((1 << p.ib) < p.Lext) ++p.ib; }
-    if (p.ib > 14) return false;                 // would eat too much mantissa; fp32 variant handles it
+    p.ib = 0;                                    // (unused since the pooled key carries value and position separately)
     p.acc_stride = p.Nb <= 128 ? 128 : 256;
     p.tmem_cols = 2 * p.acc_stride;
     int off = 0;
     p.off_w = off; off += p.w_bytes;
     off = (off + 127) / 128 * 128;
     p.off_ring = off;
-    const int fixed_tail = p.Nb * 4 + p.D * p.Nb * 4 + 8 * (2 * 8 + 5) + 16 + 256;
-    int nst = (TC_SMEM_MAX - off - fixed_tail) / p.stage_bytes;
-    if (nst > 8) nst = 8;
+    const int fixed_tail = p.Nb * 4 + p.D * p.Nb * 8 + 8 * (2 * 8 + 5) + 16 + 256;
+    // two K-steps per stage when at least 5 such stages fit, else one
+    int nst = 0;
+    for (int kps = 2; kps >= 1; --kps) {
+        p.kps = kps;
+        p.RS = tc_rs(K, kps);
+        p.stage_bytes = 2 * kps * p.RS * 16;
+        nst = (TC_SMEM_MAX - off - fixed_tail) / p.stage_bytes;
+        if (nst > 8) nst = 8;
+        if (nst >= 5) break;
+    }
     if (nst < 3) return false;
+    p.nstages_k = (p.ksteps + p.kps - 1) / p.kps;
     p.nst = nst;
     off += nst * p.stage_bytes;
     p.off_bias = off; off += p.Nb * 4;
-    p.off_keys = off; off += p.D * p.Nb * 4;
     off = (off + 7) / 8 * 8;
+    p.off_keys = off; off += p.D * p.Nb * 8;
     p.off_bars = off; off += 8 * (2 * nst + 5);
     p.off_slot = off; off += 16;
     p.smem_bytes = off;
@@ -517,15 +581,15 @@ static bool tc_make_plan(int E, int H, int K, int L, int pad, int act, int64_t n
 }
 
 int conv_tc_dispatch(const __nv_bfloat16* shadow, int64_t vocab, int E, const int64_t* ids, const uint8_t* mask,
-                     const float* gate, int gate_mode, int64_t n_docs, int L, const __nv_bfloat16* umma_w, int /*Npad*/,
+                     const float* gate, int gate_mode, int64_t n_docs, int L, const __nv_bfloat16* umma_w, const void* zero_row,
                      const float* bias, int H, int K, int pad, int act, float* feat, int32_t* argmax, int feat_ld,
                      cudaStream_t s) {
     RBR_REQUIRE(gate_mode == 0 && !gate, RBR_EUNSUPPORTED, "conv_fwd[bf16]: gated conv not implemented in the tensor-core variant");
     TcArgs a{};
     RBR_REQUIRE(tc_make_plan(E, H, K, L, pad, act, n_docs, &a.p), RBR_EUNSUPPORTED,
                 "conv_fwd[bf16]: shape (E=%d H=%d k=%d L=%d) outside the tensor-core variant; use precision fp32", E, H, K, L);
-    a.shadow = shadow; a.vocab = vocab; a.ids = ids; a.mask = mask; a.n_docs = n_docs; a.wpack = umma_w; a.bias = bias;
-    a.feat = feat; a.argmax = argmax; a.feat_ld = feat_ld; a.emb_pad = (int)round_up(E, 16);
+    a.shadow = shadow; a.vocab = vocab; a.ids = ids; a.mask = mask; a.n_docs = n_docs; a.wpack = umma_w; a.zero_row = zero_row; a.bias = bias;
+    a.feat = feat; a.argmax = argmax; a.feat_ld = feat_ld; a.emb_pad = (int)rbr_emb_pad(E);
     static int num_sms = 0;
     if (num_sms == 0) {
         int dev = 0;
@@ -541,10 +605,12 @@ int conv_tc_dispatch(const __nv_bfloat16* shadow, int64_t vocab, int E, const in
     case KT_: {                                                                                                   \
         static bool attr = false;                                                                                 \
         if (!attr) {                                                                                              \
-            RBR_CUDA(cudaFuncSetAttribute(conv_tc_kernel<KT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_MAX)); \
+            RBR_CUDA(cudaFuncSetAttribute(conv_tc_kernel<KT_, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_MAX)); \
+            RBR_CUDA(cudaFuncSetAttribute(conv_tc_kernel<KT_, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_MAX)); \
             attr = true;                                                                                          \
         }                                                                                                         \
-        conv_tc_kernel<KT_><<<(unsigned)grid, TC_THREADS, a.p.smem_bytes, s>>>(a);                                \
+        if (a.p.kps == 2) conv_tc_kernel<KT_, 2><<<(unsigned)grid, TC_THREADS, a.p.smem_bytes, s>>>(a);           \
+        else conv_tc_kernel<KT_, 1><<<(unsigned)grid, TC_THREADS, a.p.smem_bytes, s>>>(a);                        \
     } break;
     switch (K) {
         RBR_TC(1) RBR_TC(2) RBR_TC(3) RBR_TC(4) RBR_TC(5) RBR_TC(7)

@@ -291,7 +291,9 @@ extern "C" int rbr_embgrad_scatter_add(const int64_t* ids, const float* grad_row
     return RBR_OK;
 }
 
-extern "C" int64_t rbr_emb_pad(int64_t emb) { return round_up(emb, 16); }
+// bf16 shadow rows are padded to a multiple of 64 elements = 128 bytes, so every 64-byte piece the conv kernel
+// gathers lies inside one 128-byte line
+extern "C" int64_t rbr_emb_pad(int64_t emb) { return round_up(emb, 64); }
 
 extern "C" int rbr_table_to_bf16(const float* table, int64_t vocab, int64_t emb, void* shadow_bf16, void* stream) {
     RBR_REQUIRE(table && shadow_bf16, RBR_EINVAL, "rbr_table_to_bf16: null pointer");
@@ -314,6 +316,7 @@ extern "C" int rbr_conv_pack(const float* weight, int64_t emb, int64_t filters, 
     RBR_REQUIRE((uintptr_t)packed % 256 == 0, RBR_EINVAL, "rbr_conv_pack: packed buffer must be 256-byte aligned");
     const PackLayout p = pack_layout(emb, filters, ksize);
     char* base = reinterpret_cast<char*>(packed);
+    RBR_CUDA(cudaMemsetAsync(base + p.off_zero, 0, (size_t)(p.total - p.off_zero), as_stream(stream)));
     const int64_t total = ksize * emb * p.Hpad4 + filters * ksize * p.Epad4 + ksize * p.Epad16 * p.Npad;
     conv_pack_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(
         weight, (int)emb, (int)filters, (int)ksize, (int)p.Hpad4, (int)p.Epad4, (int)p.Epad16, (int)p.Npad, (int)(p.Nb > 0 ? p.Nb : 1),

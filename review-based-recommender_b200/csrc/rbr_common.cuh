@@ -69,7 +69,7 @@ struct PackLayout {
     int64_t Epad4;      // E rounded up to 4
     int64_t Epad16;     // E rounded up to 16 (UMMA K granularity for bf16)
     int64_t Npad;       // P * Nb
-    int64_t off_keh, off_hke, off_umma, total;
+    int64_t off_keh, off_hke, off_umma, off_zero, total;   // off_zero: a zero row of rbr_emb_pad(E) bf16 (conv_tc zero source)
 };
 __host__ __device__ inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 inline PackLayout pack_layout(int64_t E, int64_t H, int64_t k) {
@@ -86,6 +86,8 @@ inline PackLayout pack_layout(int64_t E, int64_t H, int64_t k) {
     b = p.off_hke + H * k * p.Epad4 * 4;
     p.off_umma = round_up(b, 256);
     b = p.off_umma + k * p.Epad16 * p.Npad * 2;
+    p.off_zero = round_up(b, 256);
+    b = p.off_zero + round_up(E, 64) * 2 + 256;
     p.total = round_up(b, 256);
     return p;
 }

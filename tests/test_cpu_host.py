@@ -22,7 +22,7 @@ def test_cabi_loads_and_exports_every_declared_symbol():
     for name in lib.protos:
         assert getattr(lib, name) is not None, name
     assert lib.rbr_version() >= 100
-    assert lib.rbr_emb_pad(300) == 304 and lib.rbr_emb_pad(100) == 112
+    assert lib.rbr_emb_pad(300) == 320 and lib.rbr_emb_pad(100) == 128
     assert lib.rbr_conv_pack_bytes(300, 100, 3) > 0
     assert lib.rbr_conv_bwd_workspace_bytes(8, 100, 3, 300, 50000) > 0
     assert lib.rbr_embgrad_workspace_bytes(1000, 50000) > 0

@@ -53,10 +53,10 @@ def test_conv_tc_vs_bf16_rounded_oracle(shape):
     y = orc.conv1d_same(x, _bf16_round(w), b)
     ref, ref_arg = orc.first_argmax_pool(torch.relu(y))
     assert rel_err(feat.cpu(), ref) < 1e-3
-    # arg-max: identical wherever the winner is not a near-tie (the packed key drops <= 14 mantissa bits)
+    # arg-max: the position the kernel reports attains the oracle's max up to fp32 summation-order noise
     pre = y.max(dim=1).values
     got = torch.gather(y, 1, amax.cpu().long().unsqueeze(1)).squeeze(1)
-    assert float(((pre - got).abs() / pre.abs().clamp_min(1e-3)).max()) < 2e-3
+    assert float(((pre - got).abs() / pre.abs().clamp_min(1e-3)).max()) < 1e-5
     if n > 2:
         assert torch.allclose(feat[2].cpu(), torch.relu(b), atol=1e-6)
 
