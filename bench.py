@@ -176,6 +176,7 @@ def make_batches(model_name, n, rank):
 def step(model, batch, ratings, loss_fn, world):
     from rbr_b200 import parallel
     model.zero_grad(set_to_none=True)
+    model.invalidate_operand_cache()      # as after an optimizer step: re-stage the bf16 table shadow + packed weights
     out = model(*batch)
     pred = out[0] if isinstance(out, tuple) else out
     loss = loss_fn(pred, ratings)

@@ -50,17 +50,35 @@ __global__ void __launch_bounds__(256) conv_bwd_table_kernel(const int32_t* __re
                                                              int e4 /* E/4 */, float4* __restrict__ table_grad, int chunk) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    int64_t i = warp * chunk;
-    if (i >= n_entries) return;
-    const int64_t end = min(i + (int64_t)chunk, n_entries);
+    const int64_t i0 = warp * 32;                        // one lane-batch of 32 sorted entries per warp
+    if (i0 >= n_entries) return;
+    (void)chunk;
+    // lane l resolves entry i0+l (entry id → token key, coefficient, weight row) with independent loads; the warp
+    // then walks the 32 entries with shuffles, so only the weight-row loads sit on the per-entry critical path.
+    int key_l = -1, row_l = 0;
+    float g_l = 0.f;
+    if (i0 + lane < n_entries) {
+        const int ent = __ldg(order + i0 + lane);
+        key_l = __ldg(keys + ent);
+        g_l = __ldg(coef + ent);
+        row_l = ent % (H * K);                           // ent = (n*H + h)*K + j → packed weight row h*K + j
+    }
     float4 acc[NQ];
 #pragma unroll
     for (int q = 0; q < NQ; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
     int cur = -1;
-    for (; i < end; ++i) {
-        const int ent = __ldg(order + i);
-        const int key = __ldg(keys + ent);
-        if (key < 0) break;                                // skipped entries are sorted last
+#pragma unroll 4
+    for (int d = 0; d < 32; ++d) {
+        const int key = __shfl_sync(0xffffffffu, key_l, d);
+        if (key < 0) break;                              // skipped entries are sorted last (warp-uniform)
+        const float g = __shfl_sync(0xffffffffu, g_l, d);
+        const float4* wrow = whke + (int64_t)__shfl_sync(0xffffffffu, row_l, d) * e4w;
+        float4 w[NQ];
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            const int c = lane + 32 * q;
+            w[q] = (c < e4) ? __ldg(wrow + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
         if (key != cur) {
             if (cur >= 0) {
 #pragma unroll
@@ -72,16 +90,10 @@ __global__ void __launch_bounds__(256) conv_bwd_table_kernel(const int32_t* __re
             }
             cur = key;
         }
-        const float g = __ldg(coef + ent);
-        const float4* wrow = whke + (int64_t)ent % ((int64_t)H * K) * e4w;   // ent = (n*H + h)*K + j → row (h*K + j)
 #pragma unroll
         for (int q = 0; q < NQ; ++q) {
-            const int c = lane + 32 * q;
-            if (c < e4) {
-                const float4 w = __ldg(wrow + c);
-                acc[q].x = fmaf(g, w.x, acc[q].x); acc[q].y = fmaf(g, w.y, acc[q].y);
-                acc[q].z = fmaf(g, w.z, acc[q].z); acc[q].w = fmaf(g, w.w, acc[q].w);
-            }
+            acc[q].x = fmaf(g, w[q].x, acc[q].x); acc[q].y = fmaf(g, w[q].y, acc[q].y);
+            acc[q].z = fmaf(g, w[q].z, acc[q].z); acc[q].w = fmaf(g, w[q].w, acc[q].w);
         }
     }
     if (cur >= 0) {
@@ -115,39 +127,60 @@ __global__ void __launch_bounds__(128) conv_bwd_weight_kernel(
 #pragma unroll
         for (int q = 0; q < NQ; ++q) acc[j][q] = make_float4(0.f, 0.f, 0.f, 0.f);
     float bsum = 0.f;
-    for (int64_t n = n0; n < n1; ++n) {
-        const float y = __ldg(feat + n * feat_ld + h);
-        const float g = __ldg(feat_grad + n * feat_ld + h) * act_grad_from_out(act, y);
-        if (g == 0.f) continue;                                  // warp-uniform
-        bsum += g;
-        const int ts = __ldg(argmax + n * feat_ld + h) - pad;
+    // Documents are taken 32 at a time: lane l resolves document nb+l's (coefficient, arg-max → K token ids) with
+    // independent loads (one latency round for the metadata, one for the ids) instead of a dependent chain per
+    // document; the warp then walks the 32 documents with shuffles, K row loads in flight per document.
+    for (int64_t nb = n0; nb < n1; nb += 32) {
+        const int64_t n = nb + lane;
+        float g_l = 0.f;
+        int ts_l = 0;
+        if (n < n1) {
+            const float y = __ldg(feat + n * feat_ld + h);
+            g_l = __ldg(feat_grad + n * feat_ld + h) * act_grad_from_out(act, y);
+            ts_l = __ldg(argmax + n * feat_ld + h) - pad;
+        }
+        int64_t id_l[K];
 #pragma unroll
         for (int j = 0; j < K; ++j) {
-            const int t = ts + j;
-            if (t < 0 || t >= L) continue;
-            if (mask && !mask[n * L + t]) continue;
-            const int64_t id = __ldg(ids + n * L + t);
-            if (id < 0 || id >= vocab) continue;
+            id_l[j] = -1;
+            const int t = ts_l + j;
+            if (g_l != 0.f && t >= 0 && t < L && (!mask || mask[n * L + t])) {
+                const int64_t id = __ldg(ids + n * L + t);
+                if (id >= 0 && id < vocab) id_l[j] = id;
+            }
+        }
+        bsum += g_l;
+        const int cnt = (int)min((int64_t)32, n1 - nb);
+#pragma unroll 2
+        for (int d = 0; d < cnt; ++d) {
+            const float g = __shfl_sync(0xffffffffu, g_l, d);
+            if (g == 0.f) continue;                                  // warp-uniform
 #pragma unroll
-            for (int q = 0; q < NQ; ++q) {
-                const int c = lane + 32 * q;
-                if (c < e4) {
-                    float4 x;
-                    if (BF16) {
-                        const uint2 raw = __ldg(reinterpret_cast<const uint2*>(shadow + id * emb_pad16) + c);
-                        const __nv_bfloat162 lo = *reinterpret_cast<const __nv_bfloat162*>(&raw.x);
-                        const __nv_bfloat162 hi = *reinterpret_cast<const __nv_bfloat162*>(&raw.y);
-                        const float2 a = __bfloat1622float2(lo), b = __bfloat1622float2(hi);
-                        x = make_float4(a.x, a.y, b.x, b.y);
-                    } else {
-                        x = __ldg(reinterpret_cast<const float4*>(table + id * E) + c);
+            for (int j = 0; j < K; ++j) {
+                const int64_t id = __shfl_sync(0xffffffffu, id_l[j], d);
+                if (id < 0) continue;                                // warp-uniform
+#pragma unroll
+                for (int q = 0; q < NQ; ++q) {
+                    const int c = lane + 32 * q;
+                    if (c < e4) {
+                        float4 x;
+                        if (BF16) {
+                            const uint2 raw = __ldg(reinterpret_cast<const uint2*>(shadow + id * emb_pad16) + c);
+                            const __nv_bfloat162 lo = *reinterpret_cast<const __nv_bfloat162*>(&raw.x);
+                            const __nv_bfloat162 hi = *reinterpret_cast<const __nv_bfloat162*>(&raw.y);
+                            const float2 a = __bfloat1622float2(lo), b = __bfloat1622float2(hi);
+                            x = make_float4(a.x, a.y, b.x, b.y);
+                        } else {
+                            x = __ldg(reinterpret_cast<const float4*>(table + id * E) + c);
+                        }
+                        acc[j][q].x = fmaf(g, x.x, acc[j][q].x); acc[j][q].y = fmaf(g, x.y, acc[j][q].y);
+                        acc[j][q].z = fmaf(g, x.z, acc[j][q].z); acc[j][q].w = fmaf(g, x.w, acc[j][q].w);
                     }
-                    acc[j][q].x = fmaf(g, x.x, acc[j][q].x); acc[j][q].y = fmaf(g, x.y, acc[j][q].y);
-                    acc[j][q].z = fmaf(g, x.z, acc[j][q].z); acc[j][q].w = fmaf(g, x.w, acc[j][q].w);
                 }
             }
         }
     }
+    bsum = warp_sum(bsum);
     float4* dst = reinterpret_cast<float4*>(dw_hke + (int64_t)h * K * epad4);
 #pragma unroll
     for (int j = 0; j < K; ++j)

@@ -57,6 +57,10 @@ class WordEmbedding(nn.Module):
             self._shadow = (key, ops.table_to_bf16(w.detach()))
         return self._shadow[1]
 
+    def invalidate_operand_cache(self):
+        """Drop the bf16 shadow (as an optimizer step would, by bumping the table's version)."""
+        self._shadow = None
+
 
 class MyConv1d(nn.Module):
     """Holder of one nn.Conv1d per kernel size; the arithmetic runs inside NgramFeat's fused kernel."""
@@ -82,6 +86,9 @@ class MyConv1d(nn.Module):
             hit = (key, ops.conv_pack(w.detach()))
             self._packed[i] = hit
         return hit[1]
+
+    def invalidate_operand_cache(self):
+        self._packed.clear()
 
     def forward(self, inputs):
         raise RuntimeError("rbr_b200.MyConv1d is a parameter holder: the [N,H,L] conv output is never materialised; "
