@@ -45,11 +45,12 @@ __global__ void __launch_bounds__(256) conv_bwd_entries_kernel(
 // ---- table gradient: warp-segmented reduction over token-sorted entries ----------------------------------
 template <int NQ>
 __global__ void __launch_bounds__(256) conv_bwd_table_kernel(const int32_t* __restrict__ order, const int32_t* __restrict__ keys,
-                                                             const float* __restrict__ coef, int64_t n_entries, int H, int K,
-                                                             const float4* __restrict__ whke, int e4w /* Epad4/4 */,
+                                                             const float* __restrict__ coef, int64_t n_entries, const int32_t* __restrict__ n_kept,
+                                                             int H, int K, const float4* __restrict__ whke, int e4w /* Epad4/4 */,
                                                              int e4 /* E/4 */, float4* __restrict__ table_grad, int chunk) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    n_entries = min(n_entries, (int64_t)__ldg(n_kept));   // entries with key < 0 were dropped by the sort
     const int64_t i0 = warp * 32;                        // one lane-batch of 32 sorted entries per warp
     if (i0 >= n_entries) return;
     (void)chunk;
@@ -371,7 +372,7 @@ extern "C" int rbr_conv_act_maxpool_bwd(int precision, int activation, const voi
             const int64_t warps = (ne + chunk - 1) / chunk;
             const int blocks = (int)((warps * 32 + 255) / 256);
 #define RBR_T(NQ)                                                                                                            \
-    conv_bwd_table_kernel<NQ><<<blocks, 256, 0, s>>>(ts.order, w.keys, w.coef, ne, H, K, reinterpret_cast<const float4*>(whke), \
+    conv_bwd_table_kernel<NQ><<<blocks, 256, 0, s>>>(ts.order, w.keys, w.coef, ne, ts.start + vocab, H, K, reinterpret_cast<const float4*>(whke), \
                                                      epad4 >> 2, E >> 2, reinterpret_cast<float4*>(table_grad), chunk)
             if (nq == 1) RBR_T(1); else if (nq == 2) RBR_T(2); else if (nq == 3) RBR_T(3); else RBR_T(4);
 #undef RBR_T

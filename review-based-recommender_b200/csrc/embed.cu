@@ -77,10 +77,11 @@ __global__ void __launch_bounds__(256) gather_rows_scalar_kernel(const float* __
 template <int NQ>   // NQ = ceil(E/4 / 32) float4 accumulators per lane
 __global__ void __launch_bounds__(256) embgrad_segment_reduce_kernel(const int32_t* __restrict__ order,
                                                                       const int32_t* __restrict__ keys,
-                                                                      int64_t n_sorted, const float4* __restrict__ grad_rows,
+                                                                      int64_t n_sorted, const int32_t* __restrict__ n_kept, const float4* __restrict__ grad_rows,
                                                                       int e4, float4* __restrict__ table_grad, int chunk) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    n_sorted = min(n_sorted, (int64_t)__ldg(n_kept));     // entries with key < 0 were dropped by the sort
     int64_t i = warp * chunk;
     if (i >= n_sorted) return;
     const int64_t end = min(i + (int64_t)chunk, n_sorted);
@@ -281,7 +282,7 @@ extern "C" int rbr_embgrad_scatter_add(const int64_t* ids, const float* grad_row
     const int blocks = (int)((warps * 32 + 255) / 256);
     const int nq = (e4 + 31) / 32;
 #define RBR_SEG(NQ)                                                                                              \
-    embgrad_segment_reduce_kernel<NQ><<<blocks, 256, 0, s>>>(ts.order, keys, n_tokens, /* n_sorted upper bound */ \
+    embgrad_segment_reduce_kernel<NQ><<<blocks, 256, 0, s>>>(ts.order, keys, n_tokens, ts.start + vocab,           \
                                                              reinterpret_cast<const float4*>(grad_rows), e4,     \
                                                              reinterpret_cast<float4*>(table_grad), chunk)
     // entries with key -1 are placed at the END of `order` by token_sort, and the kernel stops at key < 0

@@ -1,4 +1,4 @@
-// token_sort.cuh — counting sort of int32 keys in [0, n_bins) (key < 0 = "skip", placed last).
+// token_sort.cuh — counting sort of int32 keys in [0, n_bins); entries with key < 0 are dropped ("skip").
 // Produces `order`: entry indices grouped by key, so that a warp walking a slice of `order` sees
 // equal keys adjacent (the "segments" of the warp-segmented scatter-add).  Three launches:
 // histogram → single-CTA exclusive scan → fill.
@@ -14,8 +14,8 @@
 namespace rbr {
 
 struct TokenSort {
-    int32_t* order;   // [n]     entry indices, grouped by key; skipped entries at the end
-    int32_t* start;   // [bins+2] start[b] = first slot of bin b; start[bins] = first skipped slot
+    int32_t* order;   // [n]      entry indices grouped by key; only the first start[bins] slots are written
+    int32_t* start;   // [bins+2] start[b] = first slot of bin b; start[bins] = number of kept (key >= 0) entries
 };
 
 constexpr int TS_SMEM_BINS = 4096;     // hot bins privatised per CTA (16 KB of counters + 16 KB of bases)
@@ -25,8 +25,6 @@ inline int64_t token_sort_workspace_bytes(int64_t n, int64_t bins) {
     return round_up((bins + 2) * 4, 256) * 2 + round_up(n * 4, 256);
 }
 
-// bin of a key: the extra bin `bins` collects skipped entries
-__device__ __forceinline__ int ts_bin(int k, int bins) { return k < 0 ? bins : k; }
 
 static __global__ void __launch_bounds__(TS_THREADS) tsort_hist_kernel(const int32_t* __restrict__ keys, int64_t n, int bins,
                                                                        int32_t* __restrict__ counts) {
@@ -36,12 +34,13 @@ static __global__ void __launch_bounds__(TS_THREADS) tsort_hist_kernel(const int
     const int64_t per = (n + gridDim.x - 1) / gridDim.x;      // contiguous slice per CTA
     const int64_t lo = (int64_t)blockIdx.x * per, hi = min(lo + per, n);
     for (int64_t i = lo + threadIdx.x; i < hi; i += TS_THREADS) {
-        const int b = ts_bin(keys[i], bins);
+        const int b = keys[i];
+        if (b < 0) continue;                       // skipped entry (padding / masked / zero coefficient): not sorted at all
         if (b < TS_SMEM_BINS) atomicAdd(hot + b, 1);
         else atomicAdd(counts + b, 1);
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < TS_SMEM_BINS && i <= bins; i += TS_THREADS) {
+    for (int i = threadIdx.x; i < TS_SMEM_BINS && i < bins; i += TS_THREADS) {
         const int c = hot[i];
         if (c) atomicAdd(counts + i, c);
     }
@@ -106,18 +105,19 @@ static __global__ void __launch_bounds__(TS_THREADS) tsort_fill_kernel(const int
     const int64_t per = (n + gridDim.x - 1) / gridDim.x;
     const int64_t lo = (int64_t)blockIdx.x * per, hi = min(lo + per, n);
     for (int64_t i = lo + threadIdx.x; i < hi; i += TS_THREADS) {
-        const int b = ts_bin(keys[i], bins);
-        if (b < TS_SMEM_BINS) atomicAdd(hot + b, 1);
+        const int b = keys[i];
+        if (b >= 0 && b < TS_SMEM_BINS) atomicAdd(hot + b, 1);
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < TS_SMEM_BINS && i <= bins; i += TS_THREADS) {
+    for (int i = threadIdx.x; i < TS_SMEM_BINS && i < bins; i += TS_THREADS) {
         const int c = hot[i];
         base[i] = c ? atomicAdd(cursor + i, c) : 0;           // one global atomic per (CTA, non-empty hot bin)
         hot[i] = 0;
     }
     __syncthreads();
     for (int64_t i = lo + threadIdx.x; i < hi; i += TS_THREADS) {
-        const int b = ts_bin(keys[i], bins);
+        const int b = keys[i];
+        if (b < 0) continue;
         const int pos = (b < TS_SMEM_BINS) ? base[b] + atomicAdd(hot + b, 1) : atomicAdd(cursor + b, 1);
         order[pos] = (int32_t)i;
     }
