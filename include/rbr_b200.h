@@ -86,12 +86,14 @@ int rbr_conv_pack(const float* weight, int64_t emb, int64_t filters, int64_t ksi
  *   gate  optional fp32 multiplier applied to every (unmasked) token row before the conv:
  *         gate_mode 0 = none, 1 = per token [n_docs, doc_len], 2 = per doc [n_docs]  (D-ATT gates)
  *   feat  [n_docs, feat_ld] fp32, columns [0, filters) written;  argmax [n_docs, feat_ld] int32 with
- *         the FIRST position attaining the max (nn.MaxPool1d tie rule).                               */
+ *         the FIRST position attaining the max (nn.MaxPool1d tie rule);  preact (optional, same shape):
+ *         the pooled value before the activation (needed by the backward of a gated conv).            */
 int rbr_conv_act_maxpool_fwd(int precision, int activation, const void* table, const void* shadow_bf16,
                              int64_t vocab, int64_t emb, const int64_t* ids, const uint8_t* mask,
                              const float* gate, int gate_mode, int64_t n_docs, int64_t doc_len,
                              const void* packed, const float* bias, int64_t filters, int64_t ksize,
-                             int64_t pad, float* feat, int32_t* argmax, int64_t feat_ld, void* stream);
+                             int64_t pad, float* feat, int32_t* argmax, float* preact, int64_t feat_ld,
+                             void* stream);
 
 /* ---- K2b: arg-max-sparse backward of K2 ------------------------------------------------------------
  * Replaces aten::convolution_backward + max_pool1d backward + relu backward + masked_fill backward +
@@ -100,13 +102,16 @@ int rbr_conv_act_maxpool_fwd(int precision, int activation, const void* table, c
  *   weight_grad[h,:,j] += g[n,h] * x[n, t*+j-pad, :],  bias_grad[h] += g[n,h],
  *   table_grad[ids[n, t*+j-pad], :] += g[n,h] * W[h,:,j]            (mask true, id != padding_idx)
  * with g = feat_grad * act'(feat), t* = argmax[n,h].
- * gate / gate_grad: as in the forward; gate_grad (same shape as gate) receives d loss / d gate.       */
+ * gate / gate_grad: as in the forward; gate_grad (same shape as gate, +=) receives d loss / d gate =
+ * sum_h g * (preact - bias) / gate, which is why a gated backward also needs `preact` and `bias`
+ * (both may be NULL when gate_mode == 0).                                                             */
 int64_t rbr_conv_bwd_workspace_bytes(int64_t n_docs, int64_t filters, int64_t ksize, int64_t emb, int64_t vocab);
 int rbr_conv_act_maxpool_bwd(int precision, int activation, const void* table, const void* shadow_bf16,
                              int64_t vocab, int64_t emb, const int64_t* ids, const uint8_t* mask,
                              const float* gate, int gate_mode, int64_t n_docs, int64_t doc_len,
                              const void* packed, int64_t filters, int64_t ksize, int64_t pad,
-                             const float* feat, const int32_t* argmax, const float* feat_grad, int64_t feat_ld,
+                             const float* feat, const int32_t* argmax, const float* feat_grad,
+                             const float* preact, const float* bias, int64_t feat_ld,
                              int64_t padding_idx, float* weight_grad, float* bias_grad, float* table_grad,
                              float* gate_grad, void* ws, int64_t ws_bytes, void* stream);
 
@@ -149,6 +154,26 @@ int rbr_head_bwd(const float* u_text, const float* i_text, const int64_t* u_id, 
                  int64_t users, int64_t items, const float* pred_grad, float* u_text_grad, float* i_text_grad, float* Wu_grad, float* bu_grad,
                  float* ebd_u_grad, float* Wi_grad, float* bi_grad, float* ebd_i_grad, float* fm_h_grad,
                  float* user_bias_grad, float* item_bias_grad, float* g_bias_grad, void* stream);
+
+/* ---- K5: D-ATT gates -------------------------------------------------------------------------------
+ * Replaces LocalAttention.attn = Conv1d(E,1,k=window,pad=(window-1)/2)+Sigmoid (models/dual_att/layers.py:34-36,49)
+ * → gate_local [n_docs, doc_len], and GlobalAttention.attn = Conv1d(E,1,k=doc_len)+Sigmoid (layers.py:65-67,83)
+ * → gate_global [n_docs] (one scalar per document), computed from the token ids and the fp32 table.  The gated
+ * convolutions themselves are rbr_conv_act_maxpool_fwd with RBR_ACT_TANH and gate_mode 1 (local, k=1) / 2 (global).
+ *   w_local [1,E,window], b_local [1], w_global [1,E,doc_len], b_global [1]  (nn.Conv1d layouts).
+ * Backward: gate_*_grad are d loss / d gate (filled by rbr_conv_act_maxpool_bwd's gate_grad); produces the four
+ * parameter gradients (+=) and the gates' contribution to the table gradient (+=, padding row skipped).          */
+int64_t rbr_datt_gate_workspace_bytes(int64_t n_docs, int64_t doc_len, int64_t emb, int64_t window, int64_t vocab);
+int rbr_datt_gate_fwd(const float* table, int64_t vocab, int64_t emb, const int64_t* ids, int64_t n_docs,
+                      int64_t doc_len, const float* w_local, const float* b_local, int64_t window,
+                      const float* w_global, const float* b_global, float* gate_local, float* gate_global,
+                      void* ws, int64_t ws_bytes, void* stream);
+int rbr_datt_gate_bwd(const float* table, int64_t vocab, int64_t emb, const int64_t* ids, int64_t n_docs,
+                      int64_t doc_len, const float* w_local, int64_t window, const float* w_global,
+                      const float* gate_local, const float* gate_global, const float* gate_local_grad,
+                      const float* gate_global_grad, int64_t padding_idx, float* w_local_grad, float* b_local_grad,
+                      float* w_global_grad, float* b_global_grad, float* table_grad, void* ws, int64_t ws_bytes,
+                      void* stream);
 
 #ifdef __cplusplus
 }

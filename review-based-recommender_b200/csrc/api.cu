@@ -25,10 +25,10 @@ int cuda_fail(cudaError_t e, const char* what) {
 
 int conv_fp32_dispatch(const float* table, int64_t vocab, int E, const int64_t* ids, const uint8_t* mask, const float* gate,
                        int gate_mode, int64_t n_docs, int L, const float* keh, int Hpad4, const float* bias, int H, int K,
-                       int pad, int act, float* feat, int32_t* argmax, int feat_ld, cudaStream_t s);
+                       int pad, int act, float* feat, int32_t* argmax, float* preact, int feat_ld, cudaStream_t s);
 int conv_tc_dispatch(const __nv_bfloat16* shadow, int64_t vocab, int E, const int64_t* ids, const uint8_t* mask,
                      const float* gate, int gate_mode, int64_t n_docs, int L, const __nv_bfloat16* umma_w, const void* zero_row,
-                     const float* bias, int H, int K, int pad, int act, float* feat, int32_t* argmax, int feat_ld,
+                     const float* bias, int H, int K, int pad, int act, float* feat, int32_t* argmax, float* preact, int feat_ld,
                      cudaStream_t s);
 
 int oob_consume_embed(cudaStream_t, unsigned int*);
@@ -36,6 +36,7 @@ int oob_consume_conv_fp32(cudaStream_t, unsigned int*);
 int oob_consume_conv_tc(cudaStream_t, unsigned int*);
 int oob_consume_head(cudaStream_t, unsigned int*);
 int oob_consume_attn(cudaStream_t, unsigned int*);
+int oob_consume_datt(cudaStream_t, unsigned int*);
 
 }  // namespace rbr
 
@@ -51,7 +52,7 @@ extern "C" int rbr_consume_oob_count(void* stream) {
     cudaStream_t s = as_stream(stream);
     unsigned long long total = 0;
     int (*const fns[])(cudaStream_t, unsigned int*) = {oob_consume_embed, oob_consume_conv_fp32, oob_consume_conv_tc,
-                                                       oob_consume_head, oob_consume_attn};
+                                                       oob_consume_head, oob_consume_attn, oob_consume_datt};
     for (auto fn : fns) {
         unsigned int h = 0;
         if (fn(s, &h) != RBR_OK) return cuda_fail(cudaGetLastError(), "rbr_consume_oob_count");
@@ -64,7 +65,7 @@ extern "C" int rbr_conv_act_maxpool_fwd(int precision, int activation, const voi
                                         int64_t vocab, int64_t emb, const int64_t* ids, const uint8_t* mask, const float* gate,
                                         int gate_mode, int64_t n_docs, int64_t doc_len, const void* packed, const float* bias,
                                         int64_t filters, int64_t ksize, int64_t pad, float* feat, int32_t* argmax,
-                                        int64_t feat_ld, void* stream) {
+                                        float* preact, int64_t feat_ld, void* stream) {
     RBR_REQUIRE(ids && packed && bias && feat && argmax, RBR_EINVAL, "conv_fwd: null pointer");
     RBR_REQUIRE(n_docs >= 0 && doc_len > 0 && filters > 0 && ksize > 0 && emb > 0 && vocab > 0 && pad >= 0, RBR_EINVAL,
                 "conv_fwd: bad sizes");
@@ -81,13 +82,13 @@ extern "C" int rbr_conv_act_maxpool_fwd(int precision, int activation, const voi
         RBR_REQUIRE(table, RBR_EINVAL, "conv_fwd: fp32 precision needs the fp32 table");
         return conv_fp32_dispatch(reinterpret_cast<const float*>(table), vocab, (int)emb, ids, mask, gate, gate_mode, n_docs,
                                   (int)doc_len, reinterpret_cast<const float*>(pk + pl.off_keh), (int)pl.Hpad4, bias,
-                                  (int)filters, (int)ksize, (int)pad, activation, feat, argmax, (int)feat_ld, s);
+                                  (int)filters, (int)ksize, (int)pad, activation, feat, argmax, preact, (int)feat_ld, s);
     }
     if (precision == RBR_PREC_BF16) {
         RBR_REQUIRE(shadow_bf16, RBR_EINVAL, "conv_fwd: bf16 precision needs the bf16 shadow table");
         return conv_tc_dispatch(reinterpret_cast<const __nv_bfloat16*>(shadow_bf16), vocab, (int)emb, ids, mask, gate, gate_mode,
                                 n_docs, (int)doc_len, reinterpret_cast<const __nv_bfloat16*>(pk + pl.off_umma), pk + pl.off_zero,
-                                bias, (int)filters, (int)ksize, (int)pad, activation, feat, argmax, (int)feat_ld, s);
+                                bias, (int)filters, (int)ksize, (int)pad, activation, feat, argmax, preact, (int)feat_ld, s);
     }
     set_error("conv_fwd: unknown precision %d", precision);
     return RBR_EINVAL;

@@ -21,7 +21,9 @@ namespace rbr {
 __global__ void __launch_bounds__(256) conv_bwd_entries_kernel(
     const int64_t* __restrict__ ids, const uint8_t* __restrict__ mask, int64_t n_docs, int L, int H, int K, int pad,
     int64_t vocab, int64_t padding_idx, const float* __restrict__ feat, const int32_t* __restrict__ argmax,
-    const float* __restrict__ feat_grad, int feat_ld, int act, int32_t* __restrict__ keys, float* __restrict__ coef) {
+    const float* __restrict__ feat_grad, int feat_ld, int act, const float* __restrict__ gate, int gate_mode,
+    const float* __restrict__ preact, const float* __restrict__ bias, float* __restrict__ gate_grad,
+    int32_t* __restrict__ keys, float* __restrict__ coef) {
     const int64_t total = n_docs * H * K;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += stride) {
@@ -30,8 +32,16 @@ __global__ void __launch_bounds__(256) conv_bwd_entries_kernel(
         const int h = (int)(nh % H);
         const int64_t n = nh / H;
         const float y = feat[n * feat_ld + h];
-        const float g = feat_grad[n * feat_ld + h] * act_grad_from_out(act, y);
-        const int t = argmax[n * feat_ld + h] + j - pad;
+        float g = feat_grad[n * feat_ld + h] * act_grad_from_out(act, y);
+        const int ts = argmax[n * feat_ld + h];
+        const int t = ts + j - pad;
+        if (gate_mode) {
+            // y = gate * conv_nobias(x) + bias  →  d/d gate = g * (preact - bias) / gate;  d/d x, d/d W scale by gate
+            const int64_t gi = gate_mode == 1 ? n * L + ts : n;
+            const float gv = gate[gi];
+            if (j == 0 && gate_grad && g != 0.f) atomicAdd(gate_grad + gi, g * (preact[n * feat_ld + h] - bias[h]) / gv);
+            g *= gv;
+        }
         int32_t key = -1;
         if (g != 0.f && t >= 0 && t < L && (!mask || mask[n * L + t])) {
             const int64_t id = ids[n * L + t];
@@ -113,7 +123,8 @@ __global__ void __launch_bounds__(128) conv_bwd_weight_kernel(
     const float* __restrict__ table, const __nv_bfloat16* __restrict__ shadow, int emb_pad16, int64_t vocab, int E,
     const int64_t* __restrict__ ids, const uint8_t* __restrict__ mask, int64_t n_docs, int L, int H, int pad,
     const float* __restrict__ feat, const int32_t* __restrict__ argmax, const float* __restrict__ feat_grad, int feat_ld,
-    int act, int docs_per_warp, float* __restrict__ dw_hke /* [H][K][Epad4] */, int epad4, float* __restrict__ bias_grad) {
+    int act, const float* __restrict__ gate, int gate_mode, int docs_per_warp, float* __restrict__ dw_hke /* [H][K][Epad4] */,
+    int epad4, float* __restrict__ bias_grad) {
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
     const int h = blockIdx.x;
@@ -138,7 +149,10 @@ __global__ void __launch_bounds__(128) conv_bwd_weight_kernel(
         if (n < n1) {
             const float y = __ldg(feat + n * feat_ld + h);
             g_l = __ldg(feat_grad + n * feat_ld + h) * act_grad_from_out(act, y);
-            ts_l = __ldg(argmax + n * feat_ld + h) - pad;
+            const int ts = __ldg(argmax + n * feat_ld + h);
+            ts_l = ts - pad;
+            bsum += g_l;                                             // the bias gradient is not gated
+            if (gate_mode) g_l *= gate[gate_mode == 1 ? n * L + ts : n];
         }
         int64_t id_l[K];
 #pragma unroll
@@ -150,7 +164,6 @@ __global__ void __launch_bounds__(128) conv_bwd_weight_kernel(
                 if (id >= 0 && id < vocab) id_l[j] = id;
             }
         }
-        bsum += g_l;
         const int cnt = (int)min((int64_t)32, n1 - nb);
 #pragma unroll 2
         for (int d = 0; d < cnt; ++d) {
@@ -198,14 +211,15 @@ __global__ void __launch_bounds__(128) conv_bwd_weight_scalar_kernel(
     const float* __restrict__ table, int64_t vocab, int E, const int64_t* __restrict__ ids,
     const uint8_t* __restrict__ mask, int64_t n_docs, int L, int H, int K, int pad, const float* __restrict__ feat,
     const int32_t* __restrict__ argmax, const float* __restrict__ feat_grad, int feat_ld, int act,
-    float* __restrict__ dw_hke, int epad4, float* __restrict__ bias_grad) {
+    const float* __restrict__ gate, int gate_mode, float* __restrict__ dw_hke, int epad4, float* __restrict__ bias_grad) {
     // one CTA per (filter, doc): thread-strided over e; atomics per element.  Slow path, small shapes only.
     const int h = blockIdx.y;
     const int64_t n = blockIdx.x;
     const float y = feat[n * feat_ld + h];
-    const float g = feat_grad[n * feat_ld + h] * act_grad_from_out(act, y);
+    float g = feat_grad[n * feat_ld + h] * act_grad_from_out(act, y);
     if (g == 0.f) return;
     if (threadIdx.x == 0) atomicAdd(bias_grad + h, g);
+    if (gate_mode) g *= gate[gate_mode == 1 ? n * L + argmax[n * feat_ld + h] : n];
     const int ts = argmax[n * feat_ld + h] - pad;
     for (int j = 0; j < K; ++j) {
         const int t = ts + j;
@@ -275,12 +289,12 @@ extern "C" int64_t rbr_conv_bwd_workspace_bytes(int64_t n_docs, int64_t filters,
 template <int K, bool BF16>
 static int launch_weight(int nq, dim3 grid, cudaStream_t s, const float* table, const __nv_bfloat16* shadow, int emb_pad16,
                          int64_t vocab, int E, const int64_t* ids, const uint8_t* mask, int64_t n_docs, int L, int H, int pad,
-                         const float* feat, const int32_t* argmax, const float* feat_grad, int feat_ld, int act, int dpw,
-                         float* dw_hke, int epad4, float* bias_grad) {
+                         const float* feat, const int32_t* argmax, const float* feat_grad, int feat_ld, int act,
+                         const float* gate, int gate_mode, int dpw, float* dw_hke, int epad4, float* bias_grad) {
 #define RBR_W(NQ)                                                                                                     \
     conv_bwd_weight_kernel<K, NQ, BF16><<<grid, 128, 0, s>>>(table, shadow, emb_pad16, vocab, E, ids, mask, n_docs, L, H, \
-                                                             pad, feat, argmax, feat_grad, feat_ld, act, dpw, dw_hke, epad4, \
-                                                             bias_grad)
+                                                             pad, feat, argmax, feat_grad, feat_ld, act, gate, gate_mode, dpw, dw_hke, \
+                                                             epad4, bias_grad)
     if (nq == 1) RBR_W(1); else if (nq == 2) RBR_W(2); else if (nq == 3) RBR_W(3); else RBR_W(4);
 #undef RBR_W
     RBR_LAUNCH_CHECK("conv_bwd_weight_kernel");
@@ -291,12 +305,14 @@ extern "C" int rbr_conv_act_maxpool_bwd(int precision, int activation, const voi
                                         int64_t vocab, int64_t emb, const int64_t* ids, const uint8_t* mask,
                                         const float* gate, int gate_mode, int64_t n_docs, int64_t doc_len,
                                         const void* packed, int64_t filters, int64_t ksize, int64_t pad, const float* feat,
-                                        const int32_t* argmax, const float* feat_grad, int64_t feat_ld, int64_t padding_idx,
-                                        float* weight_grad, float* bias_grad, float* table_grad, float* gate_grad, void* ws,
+                                        const int32_t* argmax, const float* feat_grad, const float* preact, const float* bias,
+                                        int64_t feat_ld, int64_t padding_idx, float* weight_grad, float* bias_grad, float* table_grad, float* gate_grad, void* ws,
                                         int64_t ws_bytes, void* stream) {
     RBR_REQUIRE(table && ids && packed && feat && argmax && feat_grad, RBR_EINVAL, "conv_bwd: null pointer");
     RBR_REQUIRE(weight_grad && bias_grad, RBR_EINVAL, "conv_bwd: null weight/bias grad");
-    RBR_REQUIRE(gate_mode == 0 && !gate && !gate_grad, RBR_EUNSUPPORTED, "conv_bwd: gated conv backward not implemented yet");
+    RBR_REQUIRE(gate_mode >= 0 && gate_mode <= 2 && (gate_mode == 0) == (gate == nullptr), RBR_EINVAL, "conv_bwd: gate / gate_mode mismatch");
+    RBR_REQUIRE(gate_mode == 0 || (preact && bias), RBR_EINVAL, "conv_bwd: a gated conv backward needs preact and bias");
+    RBR_REQUIRE(gate_mode != 1 || ksize == 1, RBR_EUNSUPPORTED, "conv_bwd: per-token gate needs ksize == 1");
     RBR_REQUIRE(precision == RBR_PREC_FP32 || shadow_bf16, RBR_EINVAL, "conv_bwd: bf16 precision needs the shadow table");
     RBR_REQUIRE(n_docs >= 0 && doc_len > 0 && filters > 0 && ksize > 0 && emb > 0, RBR_EINVAL, "conv_bwd: bad sizes");
     if (n_docs == 0) return RBR_OK;
@@ -318,7 +334,8 @@ extern "C" int rbr_conv_act_maxpool_bwd(int precision, int activation, const voi
         int blocks = (int)((ne + 255) / 256);
         if (blocks > 148 * 8) blocks = 148 * 8;
         conv_bwd_entries_kernel<<<blocks, 256, 0, s>>>(ids, mask, n_docs, L, H, K, (int)pad, vocab, padding_idx, feat, argmax,
-                                                       feat_grad, (int)feat_ld, activation, w.keys, w.coef);
+                                                       feat_grad, (int)feat_ld, activation, gate, gate_mode, preact, bias, gate_grad,
+                                                       w.keys, w.coef);
         RBR_LAUNCH_CHECK("conv_bwd_entries_kernel");
     }
     // ---- weight + bias gradient
@@ -334,9 +351,9 @@ extern "C" int rbr_conv_act_maxpool_bwd(int precision, int activation, const voi
         int rc = RBR_OK;
 #define RBR_WK(K_)                                                                                                         \
     rc = bf ? launch_weight<K_, true>(nq, grid, s, tb, sh, ep16, vocab, E, ids, mask, n_docs, L, H, (int)pad, feat, argmax, \
-                                      feat_grad, (int)feat_ld, activation, dpw, w.dw_hke, epad4, bias_grad)                 \
+                                      feat_grad, (int)feat_ld, activation, gate, gate_mode, dpw, w.dw_hke, epad4, bias_grad) \
             : launch_weight<K_, false>(nq, grid, s, tb, sh, ep16, vocab, E, ids, mask, n_docs, L, H, (int)pad, feat, argmax, \
-                                       feat_grad, (int)feat_ld, activation, dpw, w.dw_hke, epad4, bias_grad)
+                                       feat_grad, (int)feat_ld, activation, gate, gate_mode, dpw, w.dw_hke, epad4, bias_grad)
         switch (K) {
             case 1: RBR_WK(1); break;
             case 2: RBR_WK(2); break;
@@ -352,7 +369,7 @@ extern "C" int rbr_conv_act_maxpool_bwd(int precision, int activation, const voi
         dim3 grid((unsigned)n_docs, (unsigned)H);
         conv_bwd_weight_scalar_kernel<<<grid, 128, 0, s>>>(reinterpret_cast<const float*>(table), vocab, E, ids, mask, n_docs, L,
                                                            H, K, (int)pad, feat, argmax, feat_grad, (int)feat_ld, activation,
-                                                           w.dw_hke, epad4, bias_grad);
+                                                           gate, gate_mode, w.dw_hke, epad4, bias_grad);
         RBR_LAUNCH_CHECK("conv_bwd_weight_scalar_kernel");
     }
     {

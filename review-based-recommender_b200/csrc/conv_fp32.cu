@@ -32,7 +32,7 @@ __global__ void __launch_bounds__(32 * (TM / 8)) conv_fp32_kernel(
     const float* __restrict__ table, int64_t vocab, int E, const int64_t* __restrict__ ids,
     const uint8_t* __restrict__ mask, const float* __restrict__ gate, int gate_mode, int L,
     const float* __restrict__ keh, int Hpad4, const float* __restrict__ bias, int H, int pad, int Lout, int act,
-    float* __restrict__ feat, int32_t* __restrict__ argmax, int feat_ld, int TX) {
+    float* __restrict__ feat, int32_t* __restrict__ argmax, float* __restrict__ preact, int feat_ld, int TX) {
     constexpr int TY = TM / 8;
     constexpr int XS = cf_xs_stride(TM, K);
     constexpr int XROWS = TM + K - 1;
@@ -178,6 +178,7 @@ __global__ void __launch_bounds__(32 * (TM / 8)) conv_fp32_kernel(
             if (v > bv || (v == bv && t < bt)) { bv = v; bt = t; }
         }
         feat[doc * feat_ld + h] = act_apply(act, bv);
+        if (preact) preact[doc * feat_ld + h] = bv;
         argmax[doc * feat_ld + h] = bt;
     }
 }
@@ -185,8 +186,8 @@ __global__ void __launch_bounds__(32 * (TM / 8)) conv_fp32_kernel(
 template <int TM, int K>
 static int launch_conv_fp32(const float* table, int64_t vocab, int E, const int64_t* ids, const uint8_t* mask,
                             const float* gate, int gate_mode, int64_t n_docs, int L, const float* keh, int Hpad4,
-                            const float* bias, int H, int pad, int Lout, int act, float* feat, int32_t* argmax, int feat_ld,
-                            cudaStream_t s) {
+                            const float* bias, int H, int pad, int Lout, int act, float* feat, int32_t* argmax, float* preact,
+                            int feat_ld, cudaStream_t s) {
     constexpr int TY = TM / 8;
     constexpr int XS = cf_xs_stride(TM, K);
     const int hblocks = (H + 255) / 256;
@@ -205,14 +206,14 @@ static int launch_conv_fp32(const float* table, int64_t vocab, int E, const int6
     RBR_REQUIRE(smem <= 200 * 1024, RBR_EUNSUPPORTED, "conv_fp32: shared memory %zu too large", smem);
     dim3 grid((unsigned)n_docs, (unsigned)hblocks);
     kern<<<grid, 32 * TY, smem, s>>>(table, vocab, E, ids, mask, gate, gate_mode, L, keh, Hpad4, bias, H, pad, Lout, act,
-                                     feat, argmax, feat_ld, TX);
+                                     feat, argmax, preact, feat_ld, TX);
     RBR_LAUNCH_CHECK("conv_fp32_kernel");
     return RBR_OK;
 }
 
 int conv_fp32_dispatch(const float* table, int64_t vocab, int E, const int64_t* ids, const uint8_t* mask,
                        const float* gate, int gate_mode, int64_t n_docs, int L, const float* keh, int Hpad4,
-                       const float* bias, int H, int K, int pad, int act, float* feat, int32_t* argmax, int feat_ld,
+                       const float* bias, int H, int K, int pad, int act, float* feat, int32_t* argmax, float* preact, int feat_ld,
                        cudaStream_t s) {
     const int Lout = L + 2 * pad - K + 1;
     RBR_REQUIRE(Lout >= 1, RBR_EINVAL, "conv: doc_len %d too short for kernel size %d", L, K);
@@ -220,7 +221,7 @@ int conv_fp32_dispatch(const float* table, int64_t vocab, int E, const int64_t* 
     // TX*TY threads must fit one CTA: TX <= 32, TY = TM/8
 #define RBR_CF(TM_, K_)                                                                                          \
     return launch_conv_fp32<TM_, K_>(table, vocab, E, ids, mask, gate, gate_mode, n_docs, L, keh, Hpad4, bias, H, \
-                                     pad, Lout, act, feat, argmax, feat_ld, s)
+                                     pad, Lout, act, feat, argmax, preact, feat_ld, s)
 #define RBR_CF_K(TM_)                                     \
     switch (K) {                                          \
         case 1: RBR_CF(TM_, 1);                           \

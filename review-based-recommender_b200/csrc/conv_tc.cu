@@ -241,6 +241,9 @@ struct TcArgs {
     const float* bias;
     float* feat;
     int32_t* argmax;
+    float* preact;                   // optional: pooled value before the activation
+    const float* gate;               // optional multiplicative gate (D-ATT): mode 1 per token (k == 1), mode 2 per doc
+    int gate_mode;
     int feat_ld;
     int emb_pad;                     // shadow row pitch in elements
     TcPlan p;
@@ -459,6 +462,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcArgs a) 
             int slot, t;
             if (p.mode_b) { slot = m / p.Lext; t = m - slot * p.Lext; } else { slot = 0; t = tt * TC_M + m; }
             const bool valid = (t < p.Lout) && (slot < p.D) && ((p.mode_b ? unit * p.D + slot : unit) < a.n_docs);
+            float row_gate = 1.f;
+            if (a.gate_mode == 1 && valid) row_gate = a.gate[(p.mode_b ? unit * p.D + slot : unit) * p.L + t];
             // slots this warp's 32 rows touch
             const int slot_lo = p.mode_b ? (quad * 32) / p.Lext : 0;
             int slot_hi = p.mode_b ? (quad * 32 + 31) / p.Lext : 0;
@@ -475,6 +480,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcArgs a) 
                 if (ch == chunk_hi - 1) {                     // this warp's last chunk is in registers: release the accumulator
                     tc_fence_before();
                     mbar_arrive(bar_acce + 8 * buf);
+                }
+                if (a.gate_mode == 1) {                       // per-token gate (k == 1): conv(g_t * x_t) = g_t * conv(x_t)
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * row_gate);
                 }
                 for (int sl = slot_lo; sl <= slot_hi; ++sl) {
                     const bool mine = valid && slot == sl;
@@ -503,7 +512,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcArgs a) 
                     if (doc < a.n_docs && h0 + c < p.H) {
                         const float raw = __uint_as_float(ord2f((uint32_t)(key >> 32)));
                         const int tbest = (int)(0xFFFFFFFFu - (uint32_t)key);
-                        a.feat[doc * a.feat_ld + h0 + c] = act_apply(p.act, raw + bias_s[c]);
+                        const float pre = (a.gate_mode == 2 ? raw * a.gate[doc] : raw) + bias_s[c];   // per-doc gate > 0: monotone
+                        a.feat[doc * a.feat_ld + h0 + c] = act_apply(p.act, pre);
+                        if (a.preact) a.preact[doc * a.feat_ld + h0 + c] = pre;
                         a.argmax[doc * a.feat_ld + h0 + c] = tbest;
                     }
                 }
@@ -582,14 +593,13 @@ static bool tc_make_plan(int E, int H, int K, int L, int pad, int act, int64_t n
 
 int conv_tc_dispatch(const __nv_bfloat16* shadow, int64_t vocab, int E, const int64_t* ids, const uint8_t* mask,
                      const float* gate, int gate_mode, int64_t n_docs, int L, const __nv_bfloat16* umma_w, const void* zero_row,
-                     const float* bias, int H, int K, int pad, int act, float* feat, int32_t* argmax, int feat_ld,
+                     const float* bias, int H, int K, int pad, int act, float* feat, int32_t* argmax, float* preact, int feat_ld,
                      cudaStream_t s) {
-    RBR_REQUIRE(gate_mode == 0 && !gate, RBR_EUNSUPPORTED, "conv_fwd[bf16]: gated conv not implemented in the tensor-core variant");
     TcArgs a{};
     RBR_REQUIRE(tc_make_plan(E, H, K, L, pad, act, n_docs, &a.p), RBR_EUNSUPPORTED,
                 "conv_fwd[bf16]: shape (E=%d H=%d k=%d L=%d) outside the tensor-core variant; use precision fp32", E, H, K, L);
     a.shadow = shadow; a.vocab = vocab; a.ids = ids; a.mask = mask; a.n_docs = n_docs; a.wpack = umma_w; a.zero_row = zero_row; a.bias = bias;
-    a.feat = feat; a.argmax = argmax; a.feat_ld = feat_ld; a.emb_pad = (int)rbr_emb_pad(E);
+    a.feat = feat; a.argmax = argmax; a.preact = preact; a.gate = gate; a.gate_mode = gate_mode; a.feat_ld = feat_ld; a.emb_pad = (int)rbr_emb_pad(E);
     static int num_sms = 0;
     if (num_sms == 0) {
         int dev = 0;

@@ -191,7 +191,7 @@ class EncodeDocsFn(torch.autograd.Function):
                 lib.check(lib.rbr_conv_act_maxpool_fwd(
                     prec, act, _p(table), _p(shadow), vocab, emb, _p(ids), _p(mask), None, 0, n_docs, doc_len, _p(pk),
                     _p(_req(b, torch.float32, "conv bias")), h, k, pad, feat.data_ptr() + 4 * col, amax.data_ptr() + 4 * col,
-                    h_total, _stream()), "rbr_conv_act_maxpool_fwd")
+                    None, h_total, _stream()), "rbr_conv_act_maxpool_fwd")
                 col += h
             feats.append(feat)
             argmaxes.append(amax)
@@ -239,7 +239,7 @@ class EncodeDocsFn(torch.autograd.Function):
                 lib.check(lib.rbr_conv_act_maxpool_bwd(
                     prec, cfg["act"], _p(table), _p(ctx.shadow), vocab, emb, _p(ids), _p(mask), None, 0, n_docs, doc_len,
                     _p(ctx.packed[i]), h, k, cfg["pads"][i], feats[s].data_ptr() + 4 * col, argmaxes[s].data_ptr() + 4 * col,
-                    fg.data_ptr() + 4 * col, h_total, cfg["padding_idx"], _p(g_w[i]), _p(g_b[i]), _p(g_table), None,
+                    fg.data_ptr() + 4 * col, None, None, h_total, cfg["padding_idx"], _p(g_w[i]), _p(g_b[i]), _p(g_table), None,
                     _p(ws), ws_bytes, _stream()), "rbr_conv_act_maxpool_bwd")
                 col += h
         return (g_table, None, *g_w, *g_b, *([None] * (2 * ns)))
@@ -347,5 +347,109 @@ def conv_act_maxpool(table: torch.Tensor, ids: torch.Tensor, mask: Optional[torc
     amax = torch.empty(n_docs, h, dtype=torch.int32, device=table.device)
     lib.check(lib.rbr_conv_act_maxpool_fwd(prec, act, _p(table), _p(shadow), table.shape[0], emb, _p(ids), _p(mask), None, 0,
                                            n_docs, doc_len, _p(packed), _p(_req(bias, torch.float32, "bias")), h, k, pad,
-                                           _p(feat), _p(amax), h, _stream()), "rbr_conv_act_maxpool_fwd")
+                                           _p(feat), _p(amax), None, h, _stream()), "rbr_conv_act_maxpool_fwd")
     return feat, amax
+
+
+# ---------------------------------------------------------------------------------------------------
+# K5 + gated K2: one side of the D-ATT encoder (local attention + global attention), ids → [N, l_out + 3*g_out]
+# ---------------------------------------------------------------------------------------------------
+class DattEncodeFn(torch.autograd.Function):
+    """feats[s] = cat(LocalAttention_s(x_s), *GlobalAttention_s(x_s)) for x_s = table[ids_s], s in (user, item)
+    (reference models/dual_att/layers.py:43-53, 81-89 and dual_att.py:45-50, 53-56), without materialising x, its
+    permuted copy or the gated copies.  Both sides go through ONE autograd node because they share the embedding table
+    (dual_att.py:22): its gradient buffer is accumulated into by both and handed to autograd once.
+
+    Inputs after (table, cfg): per side (ids, then 12 parameters: local attn w, b; local conv w, b; global attn w, b;
+    conv1 w, b; conv2 w, b; conv3 w, b)."""
+
+    N_PRM = 12
+
+    @staticmethod
+    def forward(ctx, table, cfg, *rest):
+        table = _req(table, torch.float32, "embedding table")
+        stride = 1 + DattEncodeFn.N_PRM
+        n_sides = len(rest) // stride
+        prec = _PREC[cfg["precision"]]
+        vocab, emb = table.shape
+        dev = table.device
+        shadow = cfg["shadow_fn"]() if prec == PREC_BF16 else None
+        saved, feats, side_ctx = [], [], []
+        for s in range(n_sides):
+            ids = _req(rest[s * stride], torch.int64, "token ids")
+            prm = [_req(t, torch.float32, "D-ATT parameter") for t in rest[s * stride + 1:(s + 1) * stride]]
+            la_w, la_b, lc_w, lc_b, ga_w, ga_b = prm[:6]
+            g_convs = [(prm[6 + 2 * i], prm[7 + 2 * i]) for i in range(3)]
+            n_docs, doc_len = ids.shape
+            win = la_w.shape[2]
+            ws_bytes = lib.rbr_datt_gate_workspace_bytes(n_docs, doc_len, emb, win, vocab)
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            gate_l = torch.empty(n_docs, doc_len, dtype=torch.float32, device=dev)
+            gate_g = torch.empty(n_docs, dtype=torch.float32, device=dev)
+            lib.check(lib.rbr_datt_gate_fwd(_p(table), vocab, emb, _p(ids), n_docs, doc_len, _p(la_w), _p(la_b), win, _p(ga_w),
+                                            _p(ga_b), _p(gate_l), _p(gate_g), _p(ws), ws_bytes, _stream()), "rbr_datt_gate_fwd")
+            convs = [(lc_w, lc_b, gate_l, 1)] + [(w, b, gate_g, 2) for w, b in g_convs]
+            packed = [conv_pack(w) for w, _, _, _ in convs]
+            h_total = sum(w.shape[0] for w, _, _, _ in convs)
+            feat = torch.empty(n_docs, h_total, dtype=torch.float32, device=dev)
+            amax = torch.empty(n_docs, h_total, dtype=torch.int32, device=dev)
+            pre = torch.empty(n_docs, h_total, dtype=torch.float32, device=dev)
+            col = 0
+            for (w, b, gate, mode), pk in zip(convs, packed):
+                h, _, k = w.shape
+                lib.check(lib.rbr_conv_act_maxpool_fwd(prec, ACT_TANH, _p(table), _p(shadow), vocab, emb, _p(ids), None, _p(gate),
+                                                       mode, n_docs, doc_len, _p(pk), _p(b), h, k, 0, feat.data_ptr() + 4 * col,
+                                                       amax.data_ptr() + 4 * col, pre.data_ptr() + 4 * col, h_total, _stream()),
+                          "rbr_conv_act_maxpool_fwd")
+                col += h
+            saved += [ids, gate_l, gate_g, feat, amax, pre]
+            feats.append(feat)
+            side_ctx.append((prm, packed))
+        ctx.cfg, ctx.table, ctx.shadow, ctx.side_ctx, ctx.n_sides = cfg, table, shadow, side_ctx, n_sides
+        ctx.save_for_backward(*saved)
+        return tuple(feats)
+
+    @staticmethod
+    def backward(ctx, *feat_grads):
+        cfg, table = ctx.cfg, ctx.table
+        arena: Optional[GradArena] = cfg.get("arena")
+        prec = _PREC[cfg["precision"]]
+        vocab, emb = table.shape
+        dev = table.device
+        need_table = ctx.needs_input_grad[0]
+        g_table = _grad_buf(arena, cfg["table_param"], need_table)
+        ret = []
+        for s in range(ctx.n_sides):
+            ids, gate_l, gate_g, feat, amax, pre = ctx.saved_tensors[6 * s:6 * s + 6]
+            prm, packed = ctx.side_ctx[s]
+            grads = [_grad_buf(arena, p, True) for p in cfg["params"][s]]
+            ret += [None, *grads]
+            if feat_grads[s] is None:
+                continue
+            n_docs, doc_len = ids.shape
+            fg = feat_grads[s].contiguous()
+            la_w, la_b, lc_w, lc_b, ga_w, ga_b = prm[:6]
+            convs = [(lc_w, lc_b, gate_l, 1, 2, 3)] + [(prm[6 + 2 * i], prm[7 + 2 * i], gate_g, 2, 6 + 2 * i, 7 + 2 * i)
+                                                       for i in range(3)]
+            d_gate_l = torch.zeros_like(gate_l)
+            d_gate_g = torch.zeros_like(gate_g)
+            h_total = feat.shape[1]
+            col = 0
+            for (w, b, gate, mode, wi, bi), pk in zip(convs, packed):
+                h, _, k = w.shape
+                ws_bytes = lib.rbr_conv_bwd_workspace_bytes(n_docs, h, k, emb, vocab)
+                ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+                lib.check(lib.rbr_conv_act_maxpool_bwd(
+                    prec, ACT_TANH, _p(table), _p(ctx.shadow), vocab, emb, _p(ids), None, _p(gate), mode, n_docs, doc_len, _p(pk),
+                    h, k, 0, feat.data_ptr() + 4 * col, amax.data_ptr() + 4 * col, fg.data_ptr() + 4 * col,
+                    pre.data_ptr() + 4 * col, _p(b), h_total, cfg["padding_idx"], _p(grads[wi]), _p(grads[bi]), _p(g_table),
+                    _p(d_gate_l if mode == 1 else d_gate_g), _p(ws), ws_bytes, _stream()), "rbr_conv_act_maxpool_bwd")
+                col += h
+            win = la_w.shape[2]
+            ws_bytes = lib.rbr_datt_gate_workspace_bytes(n_docs, doc_len, emb, win, vocab)
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            lib.check(lib.rbr_datt_gate_bwd(_p(table), vocab, emb, _p(ids), n_docs, doc_len, _p(la_w), win, _p(ga_w), _p(gate_l),
+                                            _p(gate_g), _p(d_gate_l), _p(d_gate_g), cfg["padding_idx"], _p(grads[0]), _p(grads[1]),
+                                            _p(grads[4]), _p(grads[5]), _p(g_table), _p(ws), ws_bytes, _stream()),
+                      "rbr_datt_gate_bwd")
+        return (g_table, None, *ret)
