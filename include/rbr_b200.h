@@ -88,6 +88,10 @@ int rbr_conv_pack(const float* weight, int64_t emb, int64_t filters, int64_t ksi
  *   feat  [n_docs, feat_ld] fp32, columns [0, filters) written;  argmax [n_docs, feat_ld] int32 with
  *         the FIRST position attaining the max (nn.MaxPool1d tie rule);  preact (optional, same shape):
  *         the pooled value before the activation (needed by the backward of a gated conv).            */
+/* Tensor-core (RBR_PREC_BF16) kernel selection: 0 = best available (default: the CTA-pair cta_group::2 / TMA-gather kernel,
+ * falling back to the single-CTA cp.async kernel for shapes outside it), 1 = single-CTA kernel only, 2 = CTA-pair kernel
+ * only.  Returns the previous setting.  Both kernels compute the same function (tests run every case on both).          */
+int rbr_set_conv_tc_variant(int variant);
 int rbr_conv_act_maxpool_fwd(int precision, int activation, const void* table, const void* shadow_bf16,
                              int64_t vocab, int64_t emb, const int64_t* ids, const uint8_t* mask,
                              const float* gate, int gate_mode, int64_t n_docs, int64_t doc_len,

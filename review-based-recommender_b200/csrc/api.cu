@@ -1,4 +1,6 @@
 // api.cu — C-ABI plumbing: version, thread-local error text, out-of-range counter, conv forward dispatch.
+#include <stdlib.h>
+
 #include "rbr_common.cuh"
 
 #include <string.h>
@@ -31,9 +33,14 @@ int conv_tc_dispatch(const __nv_bfloat16* shadow, int64_t vocab, int E, const in
                      const float* bias, int H, int K, int pad, int act, float* feat, int32_t* argmax, float* preact, int feat_ld,
                      cudaStream_t s);
 
+int conv_tc2_dispatch(const __nv_bfloat16* shadow, int64_t vocab, int E, const int64_t* ids, const uint8_t* mask,
+                      const float* gate, int gate_mode, int64_t n_docs, int L, const __nv_bfloat16* umma_w2, const float* bias,
+                      int H, int K, int pad, int act, float* feat, int32_t* argmax, float* preact, int feat_ld, cudaStream_t s);
+
 int oob_consume_embed(cudaStream_t, unsigned int*);
 int oob_consume_conv_fp32(cudaStream_t, unsigned int*);
 int oob_consume_conv_tc(cudaStream_t, unsigned int*);
+int oob_consume_conv_tc2(cudaStream_t, unsigned int*);
 int oob_consume_head(cudaStream_t, unsigned int*);
 int oob_consume_attn(cudaStream_t, unsigned int*);
 int oob_consume_datt(cudaStream_t, unsigned int*);
@@ -41,6 +48,24 @@ int oob_consume_datt(cudaStream_t, unsigned int*);
 }  // namespace rbr
 
 using namespace rbr;
+
+// which tensor-core conv variant rbr_conv_act_maxpool_fwd uses: 0 = best available (CTA-pair/TMA first), 1 = single-CTA
+// cp.async variant only, 2 = CTA-pair variant only (error when the shape is outside it).  Initial value from the
+// environment variable RBR_CONV_TC_VARIANT; rbr_set_conv_tc_variant() changes it at run time (tests, A/B timing).
+static int g_conv_tc_variant = -1;
+static int conv_tc_variant() {
+    if (g_conv_tc_variant < 0) {
+        const char* e = getenv("RBR_CONV_TC_VARIANT");
+        g_conv_tc_variant = (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 0;
+    }
+    return g_conv_tc_variant;
+}
+extern "C" int rbr_set_conv_tc_variant(int variant) {
+    RBR_REQUIRE(variant >= 0 && variant <= 2, RBR_EINVAL, "rbr_set_conv_tc_variant: variant must be 0, 1 or 2");
+    const int prev = conv_tc_variant();
+    g_conv_tc_variant = variant;
+    return prev;
+}
 
 extern "C" int rbr_version(void) { return 100; }   // 0.1.0
 
@@ -51,7 +76,7 @@ extern "C" int64_t rbr_launch_count(void) { return (int64_t)g_launches.load(std:
 extern "C" int rbr_consume_oob_count(void* stream) {
     cudaStream_t s = as_stream(stream);
     unsigned long long total = 0;
-    int (*const fns[])(cudaStream_t, unsigned int*) = {oob_consume_embed, oob_consume_conv_fp32, oob_consume_conv_tc,
+    int (*const fns[])(cudaStream_t, unsigned int*) = {oob_consume_embed, oob_consume_conv_fp32, oob_consume_conv_tc, oob_consume_conv_tc2,
                                                        oob_consume_head, oob_consume_attn, oob_consume_datt};
     for (auto fn : fns) {
         unsigned int h = 0;
@@ -86,6 +111,17 @@ extern "C" int rbr_conv_act_maxpool_fwd(int precision, int activation, const voi
     }
     if (precision == RBR_PREC_BF16) {
         RBR_REQUIRE(shadow_bf16, RBR_EINVAL, "conv_fwd: bf16 precision needs the bf16 shadow table");
+        // CTA-pair / TMA-gather variant first; RBR_CONV_TC_VARIANT=1 pins the single-CTA cp.async variant (A/B timing)
+        const int variant = conv_tc_variant();
+        if (variant != 1 && pl.P2 > 0) {
+            const int rc2 = conv_tc2_dispatch(reinterpret_cast<const __nv_bfloat16*>(shadow_bf16), vocab, (int)emb, ids, mask, gate,
+                                              gate_mode, n_docs, (int)doc_len,
+                                              reinterpret_cast<const __nv_bfloat16*>(pk + pl.off_umma2), bias, (int)filters,
+                                              (int)ksize, (int)pad, activation, feat, argmax, preact, (int)feat_ld, s);
+            if (rc2 != RBR_EUNSUPPORTED) return rc2;
+            RBR_REQUIRE(variant != 2, RBR_EUNSUPPORTED, "conv_fwd[bf16]: shape outside the CTA-pair variant");
+        }
+        RBR_REQUIRE(variant != 2, RBR_EUNSUPPORTED, "conv_fwd[bf16]: shape outside the CTA-pair variant");
         return conv_tc_dispatch(reinterpret_cast<const __nv_bfloat16*>(shadow_bf16), vocab, (int)emb, ids, mask, gate, gate_mode,
                                 n_docs, (int)doc_len, reinterpret_cast<const __nv_bfloat16*>(pk + pl.off_umma), pk + pl.off_zero,
                                 bias, (int)filters, (int)ksize, (int)pad, activation, feat, argmax, preact, (int)feat_ld, s);

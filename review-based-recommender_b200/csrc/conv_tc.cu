@@ -24,6 +24,7 @@
 // is therefore the exact fp32 accumulator.  Bias and activation are applied once per (doc, filter) after the max (both
 // monotone), not per position.
 #include "rbr_common.cuh"
+#include "tc_ptx.cuh"
 
 namespace rbr {
 
@@ -84,147 +85,6 @@ void tc_pass_split(int64_t E, int64_t H, int64_t K, int64_t* P, int64_t* Nb) {
     const int64_t npad = round_up(H, 16);
     *P = (npad + nb_max - 1) / nb_max;
     *Nb = round_up((H + *P - 1) / *P, 16);
-}
-
-// ------------------------------------------------------------------------------------------------
-// PTX wrappers
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-// Bounded wait: a pipeline bug must surface as a launch failure (trap), not as a hung GPU.  try_wait suspends the
-// thread in hardware for a bounded time per poll, so the poll counter stays cheap (one add per failed poll).
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t spins = 0;
-    while (!mbar_try_wait(bar, parity)) {
-        if (++spins > (1u << 22)) __trap();
-    }
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
-}
-template <int OFF>
-__device__ __forceinline__ void cp_async16_imm(uint32_t dst, const void* src, uint32_t src_bytes) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1+%2], 16, %3;" ::"r"(dst), "l"(src), "n"(OFF), "r"(src_bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
-    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-__device__ __forceinline__ void cp_async_wait_dyn(int n) {
-    switch (n) {
-        case 0: cp_async_wait<0>(); break;
-        case 1: cp_async_wait<1>(); break;
-        case 2: cp_async_wait<2>(); break;
-        case 3: cp_async_wait<3>(); break;
-        case 4: cp_async_wait<4>(); break;
-        case 5: cp_async_wait<5>(); break;
-        case 6: cp_async_wait<6>(); break;
-        default: cp_async_wait<7>(); break;
-    }
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
-                 "r"(bytes), "r"(bar)
-                 : "memory");
-}
-
-__device__ __forceinline__ void tmem_alloc(uint32_t slot_smem, uint32_t cols) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem), "r"(cols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
-}
-// UMMA shared-memory descriptor, K-major, SWIZZLE_NONE (cute::UMMA::SmemDescriptor layout):
-// [0,14) start>>4 | [16,30) leading byte offset>>4 (stride between the two K core matrices) |
-// [32,46) stride byte offset>>4 (stride between 8-row groups) | [46,48) version=1 | [61,64) layout=0
-__device__ __forceinline__ uint64_t umma_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
-    return (uint64_t)((addr >> 4) & 0x3FFFu) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) |
-           (1ull << 46);
-}
-// tcgen05 instruction descriptor (cute::UMMA::InstrDescriptor): D=F32, A=B=BF16, both K-major, N>>3 at [17,23), M>>4 at [24,29)
-__device__ __forceinline__ uint32_t umma_idesc(int M, int N) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
-          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-        : "r"(taddr)
-        : "memory");
-}
-__device__ __forceinline__ bool elect_one() {
-    uint32_t pred;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "elect.sync _|p, 0xffffffff;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(pred));
-    return pred != 0;
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// order-preserving float → uint (and back)
-__device__ __forceinline__ uint32_t f2ord(uint32_t b) { return b ^ ((uint32_t)((int32_t)b >> 31) | 0x80000000u); }
-__device__ __forceinline__ uint32_t ord2f(uint32_t u) { return (u & 0x80000000u) ? (u ^ 0x80000000u) : ~u; }
-
-// Column-wise max over the 32 rows (lanes) of a warp for 16 accumulator columns held as raw fp32 bits.
-// Positive floats order like signed ints, so one redux.sync.max.s32 gives the exact max whenever any candidate is >= 0;
-// an all-negative column (rare: it pools to relu(...)=0 unless the bias rescues it) takes a second redux.min.u32.
-// keep_v/keep_b: lane i (< 16) ends up holding column i's max bits and the ballot of rows attaining it.
-template <bool FULL>
-__device__ __forceinline__ void tc_colmax(const uint32_t (&v)[16], bool mine, int lane, uint32_t& keep_v, uint32_t& keep_b) {
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-        const int x = (FULL || mine) ? (int)v[i] : (int)0x80000000;
-        int r = __reduce_max_sync(0xffffffffu, x);
-        if (r < 0) {                                                   // warp-uniform
-            const uint32_t y = (FULL || mine) ? v[i] : 0xFFFFFFFFu;
-            r = (int)__reduce_min_sync(0xffffffffu, y);                // smallest magnitude among negatives
-        }
-        const uint32_t b = __ballot_sync(0xffffffffu, (FULL || mine) && (int)v[i] == r);
-        if ((lane & 15) == i) { keep_v = (uint32_t)r; keep_b = b; }
-    }
 }
 
 // ------------------------------------------------------------------------------------------------

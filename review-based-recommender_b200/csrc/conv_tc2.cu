@@ -1,0 +1,526 @@
+// conv_tc2.cu — K2, CTA-pair tensor-core variant: gather → mask → Conv1d → bias → activation → max-over-time as an
+// implicit GEMM on tcgen05 with cta_group::2 (two SMs, M = 256 positions per MMA), operands staged by TMA.  sm_100a only.
+//
+// Same contract and same maths as conv_tc.cu (reference models/deepconn/layers.py:22-24,123-136); what changes is how
+// the operands reach the tensor cores, because conv_tc.cu is bound by shared-memory bandwidth, not by the MMA pipe:
+//   * A operand (gathered token rows): TMA `cp.async.bulk.tensor.2d…tile::gather4` pulls 4 table rows x 64 bf16 columns
+//     (4 x 128 B) per instruction straight from the bf16 shadow table into a K-major SWIZZLE_128B tile — one full
+//     128-byte shared-memory line per row instead of eight scattered 16-byte cp.async granules.  Rows that must read as
+//     zeros (conv padding, masked tokens, bad ids, tail tiles) use row index -1: the TMA unit zero-fills out-of-range
+//     rows without touching memory.  The operand of tap j is still the SAME tile with the descriptor start advanced by
+//     j rows (j * 128 B): the 128B swizzle is a function of absolute shared-memory address bits (tools/probe_umma.cu).
+//   * B operand (conv weights, K-major no-swizzle core-matrix tiles, resident for the whole persistent kernel): each CTA
+//     of the pair keeps only HALF of the filters (cta_group::2 reads N/2 rows of B from each SM), which halves the
+//     per-SM operand read traffic of every MMA and frees ~100 KB for a 7-stage ring of 64-wide K blocks.
+//   * D: each CTA owns the accumulator rows of its own 128-position tile (TMEM, double buffered); the epilogue (exact
+//     fp32 max-over-time with first-arg-max via redux/ballot) is per CTA, unchanged from conv_tc.cu.
+// Pipeline: per CTA four TMA producer warps, 8 epilogue warps; the LEADER CTA's MMA warp issues every tcgen05.mma for the
+// pair.  full[s] lives in the leader (both CTAs' TMA bytes complete on it), empty[s] / acc_full[b] are multicast by
+// tcgen05.commit to both CTAs, acc_empty[b] collects one arrive per epilogue warp of both CTAs.
+#include <cuda.h>   // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint, no -lcuda)
+
+#include "rbr_common.cuh"
+#include "tc_ptx.cuh"
+
+namespace rbr {
+
+constexpr int T2_SMEM_MAX = 232448;        // 227 KB opt-in dynamic shared memory per CTA
+constexpr int T2_M = 128;                  // positions per CTA tile (UMMA M = 256 over the pair)
+constexpr int T2_EPI_WARPS = 8;
+constexpr int T2_EPI_THREADS = T2_EPI_WARPS * 32;
+constexpr int T2_PROD_WARP0 = T2_EPI_WARPS;      // 4 TMA producer warps (one per SM sub-partition: TMA issue is serialised per warp)
+constexpr int T2_PROD_WARPS = 4;
+constexpr int T2_MMA_WARP = T2_EPI_WARPS + T2_PROD_WARPS;
+constexpr int T2_THREADS = (T2_MMA_WARP + 1) * 32;
+constexpr int T2_MAX_SLOTS = 6;            // documents packed into one tile (short-document mode)
+constexpr int T2_MIN_STAGES = 3;
+
+struct Tc2Plan {
+    int E, H, K, L, pad, Lout, Lext;
+    int nkb;          // 64-element K blocks per staged row = emb_pad / 64
+    int ksteps;       // UMMA K-steps (16 elements) = Epad16 / 16
+    int C;            // 16-byte K chunks per weight row = Epad16 / 8
+    int P, Nb, NL;    // filter passes, filters per pass (multiple of 16), filters per CTA = Nb / 2
+    int rows;         // 128 + K - 1 staged rows carry data
+    int groups;       // gather4 groups per stage = ceil(rows / 4)   (<= 64)
+    int stage_bytes;  // groups * 512 rounded up to 1024 (stages stay swizzle-atom aligned)
+    int stage_tx;     // bytes one CTA's TMA delivers per stage = groups * 512
+    int nst;          // ring stages
+    int w_bytes;      // resident weights per CTA = K * C * NL * 16
+    int mode_b, D, tpu;
+    int64_t n_units;
+    int tmem_cols, acc_stride;
+    int off_ring, off_w, off_bias, off_keys, off_bars, off_slot, smem_bytes;   // offsets from the 1024-aligned base
+    int act;
+};
+
+static inline int t2_stage_bytes(int K) {
+    const int groups = (T2_M + K - 1 + 3) / 4;
+    return (int)round_up(groups * 512, 1024);
+}
+
+// filters-per-pass decision shared with rbr_conv_pack (the packed B operand is laid out per pass and per CTA half)
+void tc2_pass_split(int64_t E, int64_t H, int64_t K, int64_t* P, int64_t* Nb) {
+    *P = 0; *Nb = 0;
+    if (K < 1 || K > 8) return;
+    const int64_t epad16 = round_up(E, 16);
+    const int64_t bytes_per_row = K * epad16 * 2;                    // one local filter row of B
+    const int64_t budget = T2_SMEM_MAX - 1024 - T2_MIN_STAGES * t2_stage_bytes((int)K) - 8192;
+    int64_t nl_max = budget / bytes_per_row / 8 * 8;
+    if (nl_max > 128) nl_max = 128;                                  // UMMA N <= 256
+    if (nl_max < 8) return;
+    const int64_t npad = round_up(H, 16);
+    *P = (npad + 2 * nl_max - 1) / (2 * nl_max);
+    *Nb = round_up((H + *P - 1) / *P, 16);
+}
+
+struct Tc2Args {
+    int64_t vocab;
+    const int64_t* ids;
+    const uint8_t* mask;
+    int64_t n_docs;
+    const __nv_bfloat16* wpack;      // [P][2][K][C][NL][8]
+    const float* bias;
+    float* feat;
+    int32_t* argmax;
+    float* preact;
+    const float* gate;
+    int gate_mode;
+    int feat_ld;
+    Tc2Plan p;
+};
+
+// row r of the staged tile → (document, input position), or false = "reads as zeros"
+__device__ __forceinline__ bool t2_row_source(const Tc2Plan& p, int64_t unit, int tt, int r, int64_t n_docs, int64_t* doc, int* t_in) {
+    if (r >= p.rows || unit >= p.n_units) return false;
+    int64_t d;
+    int ext;
+    if (p.mode_b) {
+        const int q = r / p.Lext;
+        if (q >= p.D) return false;
+        d = unit * p.D + q;
+        ext = r - q * p.Lext;
+    } else {
+        d = unit;
+        ext = tt * T2_M + r;
+        if (ext >= p.Lext) return false;
+    }
+    if (d >= n_docs) return false;
+    const int t = ext - p.pad;
+    if (t < 0 || t >= p.L) return false;
+    *doc = d;
+    *t_in = t;
+    return true;
+}
+
+template <int KT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1)
+conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const Tc2Args a) {
+    extern __shared__ uint8_t smem_raw[];
+    const Tc2Plan& p = a.p;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t sbase = (raw + 1023u) & ~1023u;                   // SWIZZLE_128B atoms are 1024-byte aligned
+    uint8_t* smem = smem_raw + (sbase - raw);
+    const uint32_t ring_s = sbase + p.off_ring, w_s = sbase + p.off_w;
+    float* bias_s = reinterpret_cast<float*>(smem + p.off_bias);
+    unsigned long long* keys_s = reinterpret_cast<unsigned long long*>(smem + p.off_keys);
+    const uint32_t bars = sbase + p.off_bars;
+    // barrier slots: full[nst] (used in the leader), empty[nst], acc_full[2], acc_empty[2] (used in the leader), w_ready
+    const uint32_t bar_full = bars, bar_empty = bars + 8 * p.nst, bar_accf = bars + 16 * p.nst, bar_acce = bar_accf + 16,
+                   bar_w = bar_acce + 16;
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + p.off_slot);
+
+    const uint32_t rank = cluster_ctarank();
+    const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+    const int pass = pair % p.P;
+    const int ctas_per_pass = (n_pairs / p.P) * 2;
+    const int ci = (pair / p.P) * 2 + (int)rank;                     // this CTA's index among the CTAs of its pass
+    const int h0 = pass * p.Nb;
+    // units this CTA owns: ci, ci + ctas_per_pass, ...; the pair runs as many tiles as its even CTA (never fewer than the odd one)
+    const int ci_even = ci & ~1;
+    const int64_t pair_units = (p.n_units > ci_even) ? (p.n_units - ci_even + ctas_per_pass - 1) / ctas_per_pass : 0;
+    const int64_t pair_tiles = pair_units * p.tpu;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < p.nst; ++i) { mbar_init(bar_full + 8 * i, 2); mbar_init(bar_empty + 8 * i, 1); }
+        mbar_init(bar_accf, 1); mbar_init(bar_accf + 8, 1);
+        mbar_init(bar_acce, 2 * T2_EPI_WARPS); mbar_init(bar_acce + 8, 2 * T2_EPI_WARPS);
+        mbar_init(bar_w, 1);
+        fence_barrier_init();
+    }
+    for (int i = threadIdx.x; i < p.Nb; i += blockDim.x) bias_s[i] = (h0 + i < p.H) ? a.bias[h0 + i] : 0.f;
+    for (int i = threadIdx.x; i < p.D * p.Nb; i += blockDim.x) keys_s[i] = 0ull;
+    if (warp == T2_MMA_WARP) tmem_alloc2(smem_u32((const void*)tmem_slot), (uint32_t)p.tmem_cols);
+    if (warp == T2_PROD_WARP0 && lane == 0) tma_prefetch_desc(&tmap);
+    tc_fence_before();
+    cluster_sync_all();              // barriers of BOTH CTAs initialised before any remote arrive / multicast commit
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == T2_MMA_WARP) {
+        // =========================== resident weights (each CTA its half) + MMA issuer (leader CTA only) ===========================
+        if (pair_tiles > 0) {
+            const bool leader_lane = elect_one();
+            if (leader_lane) {
+                mbar_expect_tx(bar_w, (uint32_t)p.w_bytes);
+                const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(a.wpack) + (size_t)(pass * 2 + (int)rank) * p.w_bytes;
+                for (int off = 0; off < p.w_bytes; off += 32768) {
+                    const int n = min(32768, p.w_bytes - off);
+                    bulk_g2s(w_s + off, wsrc + off, (uint32_t)n, bar_w);
+                }
+            }
+            __syncwarp();
+            if (rank == 0) {
+                mbar_wait(bar_w, 0);
+                const uint32_t idesc = umma_idesc(2 * T2_M, p.Nb);
+                const uint64_t a_desc0 = umma_desc_sw128(ring_s);                          // stage 0, tap 0, K-step 0
+                const uint64_t b_desc0 = umma_desc(w_s, (uint32_t)p.NL * 16u, 128u);       // tap 0, K-step 0
+                const uint32_t a_stage_inc = (uint32_t)p.stage_bytes >> 4;                 // descriptor address units (16 B)
+                const uint32_t b_tap_inc = (uint32_t)(p.C * p.NL);                         // one tap = C chunk columns of NL rows
+                const uint32_t b_step_inc = (uint32_t)(2 * p.NL);                          // one K-step = 2 chunk columns
+                int stage = 0;
+                uint32_t ph = 0;
+                uint32_t full_bar = bar_full, empty_bar = bar_empty;
+                uint64_t ad = a_desc0;
+                for (int64_t g = 0; g < pair_tiles; ++g) {
+                    const int buf = (int)(g & 1);
+                    mbar_wait(bar_acce + 8 * buf, (uint32_t)(((g >> 1) & 1) ^ 1));        // both CTAs' epilogues drained this buffer
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(buf * p.acc_stride);
+                    uint64_t bd = b_desc0;
+                    int ks_left = p.ksteps;
+                    for (int kb = 0; kb < p.nkb; ++kb) {
+                        mbar_wait(full_bar, ph);                                           // both CTAs' TMA bytes have landed
+                        tc_fence_after();
+                        if (leader_lane) {
+#pragma unroll
+                            for (int ks = 0; ks < 4; ++ks) {
+                                if (ks < ks_left) {
+#pragma unroll
+                                    for (int j = 0; j < KT; ++j)
+                                        umma_bf16_2(d_tmem, ad + (uint64_t)(ks * 2 + j * 8), bd + (uint64_t)(ks * b_step_inc + j * b_tap_inc),
+                                                    idesc, (uint32_t)((kb | ks | j) != 0));
+                                }
+                            }
+                            umma_commit2(empty_bar);                                       // frees the ring slot in both CTAs
+                            if (kb == p.nkb - 1) umma_commit2(bar_accf + 8 * buf);         // accumulators complete → both epilogues
+                        }
+                        __syncwarp();
+                        ks_left -= 4;
+                        bd += (uint64_t)(4 * b_step_inc);
+                        ad += a_stage_inc;
+                        full_bar += 8;
+                        empty_bar += 8;
+                        if (++stage == p.nst) { stage = 0; ph ^= 1; ad = a_desc0; full_bar = bar_full; empty_bar = bar_empty; }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp >= T2_PROD_WARP0) {
+        // =========================== TMA gather producers (4 warps per CTA) ===========================
+        // Producer warp pw stages tile rows 32pw..32pw+31: lane l resolves row 32pw+l once per tile (token id, or -1 = zero
+        // row), quads of lanes assemble the 4 row indices of a gather4 group with shuffles, and lanes 0,4,..,28 issue one
+        // gather4 each per K block (TMA issue is serialised per warp, hence four warps).  The k-1 halo rows (128..) belong
+        // to warp 0.  ids/mask of tile g+1 are fetched while tile g streams.
+        const int pw = warp - T2_PROD_WARP0;
+        const int halo_groups = p.groups - 32;                      // 0 (k == 1), 1 or 2
+        const bool halo_lane = (pw == 0) && (lane < 4 * halo_groups);
+        int64_t id_next[2];
+        uint8_t ok_next[2];
+        auto prefetch_ids = [&](int64_t g) {
+            const int64_t unit = ci + (g / p.tpu) * ctas_per_pass;
+            const int tt = (int)(g % p.tpu);
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                id_next[i] = -1;
+                ok_next[i] = 0;
+                if (g >= pair_tiles || (i == 1 && !halo_lane)) continue;
+                const int r = (i == 0) ? pw * 32 + lane : T2_M + lane;
+                int64_t doc;
+                int t;
+                if (t2_row_source(p, unit, tt, r, a.n_docs, &doc, &t)) {
+                    id_next[i] = a.ids[doc * p.L + t];
+                    ok_next[i] = a.mask ? a.mask[doc * p.L + t] : (uint8_t)1;
+                }
+            }
+        };
+        int stage = 0;
+        uint32_t ph = 0;
+        bool w_checked = false;
+        const uint32_t dst0 = ring_s + (uint32_t)(pw * 8) * 512u;
+        const uint32_t dst_halo = ring_s + 32u * 512u;
+        prefetch_ids(0);
+        for (int64_t g = 0; g < pair_tiles; ++g) {
+            int mine[2];
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                mine[i] = -1;
+                if (ok_next[i]) {
+                    const int64_t id = id_next[i];
+                    if (id >= 0 && id < a.vocab) mine[i] = (int)id;
+                    else note_oob();
+                }
+            }
+            prefetch_ids(g + 1);
+            // every lane gets all 32 row indices of the warp (and the halo's 8): the issuing lane then has its operands in
+            // registers and the gather4s of a stage are straight-line code (a per-lane issue loop serialises on the TMA
+            // unit accepting each instruction's uniform registers: ~100 cycles per gather4)
+            int idx[32], hidx[8];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) idx[i] = __shfl_sync(0xffffffffu, mine[0], i);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) hidx[i] = __shfl_sync(0xffffffffu, mine[1], i);
+            for (int kb = 0; kb < p.nkb; ++kb) {
+                mbar_wait(bar_empty + 8 * stage, ph ^ 1);
+                const uint32_t fb = bar_full + 8 * stage;
+                if (pw == 0 && lane == 0) {
+                    if (rank == 0) {
+                        mbar_expect_tx(fb, 2u * (uint32_t)p.stage_tx);        // this CTA's bytes + the peer's
+                    } else {
+                        if (!w_checked) { mbar_wait(bar_w, 0); w_checked = true; }   // the leader's MMAs also read OUR weights
+                        mbar_arrive_cluster(fb, 0);
+                    }
+                }
+                const uint32_t so = (uint32_t)(stage * p.stage_bytes);
+                if (elect_one()) {
+#pragma unroll
+                    for (int gi = 0; gi < 8; ++gi)
+                        tma_gather4_pair(dst0 + so + (uint32_t)gi * 512u, &tmap, kb * 64, idx[4 * gi], idx[4 * gi + 1], idx[4 * gi + 2],
+                                         idx[4 * gi + 3], fb);
+                    if (pw == 0) {
+                        if (halo_groups > 0) tma_gather4_pair(dst_halo + so, &tmap, kb * 64, hidx[0], hidx[1], hidx[2], hidx[3], fb);
+                        if (halo_groups > 1) tma_gather4_pair(dst_halo + so + 512u, &tmap, kb * 64, hidx[4], hidx[5], hidx[6], hidx[7], fb);
+                    }
+                }
+                __syncwarp();
+                if (++stage == p.nst) { stage = 0; ph ^= 1; }
+            }
+        }
+    } else {
+        // =========================== epilogue (8 warps; warp w reads TMEM lanes 32(w&3)..+31, half of the column chunks) ===========================
+        const int quad = warp & 3;
+        const int half = warp >> 2;
+        const int m = quad * 32 + lane;                       // tile row = TMEM lane
+        const int n_chunks = p.Nb / 16;
+        const int chunk_lo = half ? (n_chunks + 1) / 2 : 0;
+        const int chunk_hi = half ? n_chunks : (n_chunks + 1) / 2;
+        for (int64_t g = 0; g < pair_tiles; ++g) {
+            const int64_t unit = ci + (g / p.tpu) * ctas_per_pass;
+            const int tt = (int)(g % p.tpu);
+            const int buf = (int)(g & 1);
+            int slot, t;
+            if (p.mode_b) { slot = m / p.Lext; t = m - slot * p.Lext; } else { slot = 0; t = tt * T2_M + m; }
+            const int64_t my_doc = p.mode_b ? unit * p.D + slot : unit;
+            const bool valid = (t < p.Lout) && (slot < p.D) && (unit < p.n_units) && (my_doc < a.n_docs);
+            float row_gate = 1.f;
+            if (a.gate_mode == 1 && valid) row_gate = a.gate[my_doc * p.L + t];
+            const int slot_lo = p.mode_b ? (quad * 32) / p.Lext : 0;
+            int slot_hi = p.mode_b ? (quad * 32 + 31) / p.Lext : 0;
+            if (slot_hi >= p.D) slot_hi = p.D - 1;
+
+            mbar_wait(bar_accf + 8 * buf, (uint32_t)((g >> 1) & 1));
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * p.acc_stride);
+            for (int ch = chunk_lo; ch < chunk_hi; ++ch) {
+                const int c0 = ch * 16;
+                uint32_t v[16];
+                tmem_ld16(taddr + (uint32_t)c0, v);
+                tmem_ld_wait();
+                if (ch == chunk_hi - 1) {                     // this warp's last chunk is in registers: release the accumulator
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster(bar_acce + 8 * buf, 0);
+                }
+                if (a.gate_mode == 1) {                       // per-token gate (k == 1): conv(g_t * x_t) = g_t * conv(x_t)
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * row_gate);
+                }
+                for (int sl = slot_lo; sl <= slot_hi; ++sl) {
+                    const bool mine = valid && slot == sl;
+                    uint32_t keep_v = 0, keep_b = 0;
+                    if (__all_sync(0xffffffffu, mine)) tc_colmax<true>(v, true, lane, keep_v, keep_b);
+                    else tc_colmax<false>(v, mine, lane, keep_v, keep_b);
+                    if (lane < 16 && keep_b) {
+                        const int first = __ffs(keep_b) - 1;
+                        const int tf = p.mode_b ? (quad * 32 + first - sl * p.Lext) : (tt * T2_M + quad * 32 + first);
+                        const unsigned long long key =
+                            ((unsigned long long)f2ord(keep_v) << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)tf);
+                        atomicMax(keys_s + sl * p.Nb + c0 + lane, key);
+                    }
+                }
+            }
+            if (chunk_lo == chunk_hi) {                       // Nb == 16: the upper half has no chunk but still owes its arrive
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(bar_acce + 8 * buf, 0);
+            }
+            if (tt == p.tpu - 1) {
+                asm volatile("bar.sync 1, %0;" ::"n"(T2_EPI_THREADS) : "memory");
+                for (int o = threadIdx.x; o < p.D * p.Nb; o += T2_EPI_THREADS) {
+                    const int sl = o / p.Nb, c = o - sl * p.Nb;
+                    const int64_t doc = p.mode_b ? unit * p.D + sl : unit;
+                    const unsigned long long key = keys_s[o];
+                    keys_s[o] = 0ull;
+                    if (unit < p.n_units && doc < a.n_docs && h0 + c < p.H) {
+                        const float raw_v = __uint_as_float(ord2f((uint32_t)(key >> 32)));
+                        const int tbest = (int)(0xFFFFFFFFu - (uint32_t)key);
+                        const float pre = (a.gate_mode == 2 ? raw_v * a.gate[doc] : raw_v) + bias_s[c];   // per-doc gate > 0: monotone
+                        a.feat[doc * a.feat_ld + h0 + c] = act_apply(p.act, pre);
+                        if (a.preact) a.preact[doc * a.feat_ld + h0 + c] = pre;
+                        a.argmax[doc * a.feat_ld + h0 + c] = tbest;
+                    }
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(T2_EPI_THREADS) : "memory");
+            }
+        }
+    }
+    // teardown: neither CTA may free TMEM / exit while the pair's MMAs can still touch its shared or tensor memory
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == T2_MMA_WARP) tmem_dealloc2(tmem_base, (uint32_t)p.tmem_cols);
+}
+
+static bool tc2_make_plan(int E, int H, int K, int L, int pad, int act, int64_t n_docs, Tc2Plan* out) {
+    Tc2Plan p{};
+    p.E = E; p.H = H; p.K = K; p.L = L; p.pad = pad; p.act = act;
+    p.Lout = L + 2 * pad - K + 1;
+    p.Lext = L + 2 * pad;
+    if (p.Lout < 1) return false;
+    const int epad16 = (int)round_up(E, 16);
+    p.C = epad16 / 8;
+    p.ksteps = epad16 / 16;
+    p.nkb = (int)(rbr_emb_pad(E) / 64);
+    int64_t P, Nb;
+    tc2_pass_split(E, H, K, &P, &Nb);
+    if (P == 0) return false;
+    p.P = (int)P; p.Nb = (int)Nb; p.NL = p.Nb / 2;
+    p.rows = T2_M + K - 1;
+    p.groups = (p.rows + 3) / 4;
+    p.stage_tx = p.groups * 512;
+    p.stage_bytes = t2_stage_bytes(K);
+    p.w_bytes = K * p.C * p.NL * 16;
+    if (p.Lext * 2 <= T2_M + K - 1) {
+        p.mode_b = 1;
+        p.D = (T2_M + K - 1) / p.Lext;
+        int dmax = 4096 / (p.Nb * 8);
+        if (dmax > T2_MAX_SLOTS) dmax = T2_MAX_SLOTS;
+        if (dmax < 1) dmax = 1;
+        if (p.D > dmax) p.D = dmax;
+        p.tpu = 1;
+        p.n_units = (n_docs + p.D - 1) / p.D;
+    } else {
+        p.mode_b = 0;
+        p.D = 1;
+        p.tpu = (p.Lout + T2_M - 1) / T2_M;
+        p.n_units = n_docs;
+    }
+    p.acc_stride = p.Nb <= 128 ? 128 : 256;
+    p.tmem_cols = 2 * p.acc_stride;
+    const int tail = p.Nb * 4 + 8 + p.D * p.Nb * 8 + 8 * (2 * 16 + 5) + 16;
+    int nst = (T2_SMEM_MAX - 1024 - p.w_bytes - tail - 256) / p.stage_bytes;
+    if (nst > 16) nst = 16;
+    if (nst < T2_MIN_STAGES) return false;
+    p.nst = nst;
+    int off = 0;
+    p.off_ring = off; off += nst * p.stage_bytes;
+    p.off_w = off; off += p.w_bytes;
+    off = (off + 15) / 16 * 16;
+    p.off_bias = off; off += p.Nb * 4;
+    off = (off + 7) / 8 * 8;
+    p.off_keys = off; off += p.D * p.Nb * 8;
+    p.off_bars = off; off += 8 * (2 * nst + 5);
+    p.off_slot = off; off += 16;
+    p.smem_bytes = off + 1024;                   // slack for the manual 1024-byte alignment of the base
+    if (p.smem_bytes > T2_SMEM_MAX) return false;
+    *out = p;
+    return true;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn tc2_encoder() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(f);
+        else
+            (void)cudaGetLastError();
+    }
+    return fn;
+}
+
+template <int KT>
+static int tc2_launch(const CUtensorMap& tm, const Tc2Args& a, cudaStream_t s) {
+    static int max_clusters = -1;
+    auto kern = conv_tc2_kernel<KT>;
+    if (max_clusters < 0) {
+        RBR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM_MAX));
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(2); cfg.blockDim = dim3(T2_THREADS); cfg.dynamicSmemBytes = T2_SMEM_MAX;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        int n = 0;
+        if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n < 1) {
+            (void)cudaGetLastError();
+            int dev = 0, sms = 0;
+            RBR_CUDA(cudaGetDevice(&dev));
+            RBR_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+            n = sms / 2;
+        }
+        max_clusters = n;
+    }
+    // persistent grid: one CTA pair per co-resident cluster slot (a multiple of the pass count), never more pairs than work
+    int64_t pairs = max_clusters / a.p.P * a.p.P;
+    if (pairs < a.p.P) pairs = a.p.P;
+    const int64_t max_useful = (a.p.n_units + 1) / 2 * a.p.P;
+    if (pairs > max_useful) pairs = max_useful;
+    kern<<<(unsigned)(2 * pairs), T2_THREADS, a.p.smem_bytes, s>>>(tm, a);
+    RBR_LAUNCH_CHECK("conv_tc2_kernel");
+    return RBR_OK;
+}
+
+// returns RBR_EUNSUPPORTED (without setting an error message the caller must surface) when the shape is outside this variant
+int conv_tc2_dispatch(const __nv_bfloat16* shadow, int64_t vocab, int E, const int64_t* ids, const uint8_t* mask,
+                      const float* gate, int gate_mode, int64_t n_docs, int L, const __nv_bfloat16* umma_w2, const float* bias,
+                      int H, int K, int pad, int act, float* feat, int32_t* argmax, float* preact, int feat_ld, cudaStream_t s) {
+    Tc2Args a{};
+    if (vocab >= (1ll << 31) || !tc2_make_plan(E, H, K, L, pad, act, n_docs, &a.p)) return RBR_EUNSUPPORTED;
+    if (K != 1 && K != 2 && K != 3 && K != 4 && K != 5 && K != 7) return RBR_EUNSUPPORTED;
+    EncodeTiledFn enc = tc2_encoder();
+    if (!enc) return RBR_EUNSUPPORTED;
+    const int64_t emb_pad = rbr_emb_pad(E);
+    CUtensorMap tm;
+    cuuint64_t gdim[2] = {(cuuint64_t)emb_pad, (cuuint64_t)vocab};
+    cuuint64_t gstr[1] = {(cuuint64_t)emb_pad * 2};
+    cuuint32_t box[2] = {64, 1};
+    cuuint32_t estr[2] = {1, 1};
+    const CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(shadow), gdim, gstr, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    RBR_REQUIRE(r == CUDA_SUCCESS, RBR_ECUDA, "conv_fwd[bf16]: cuTensorMapEncodeTiled failed (%d)", (int)r);
+    a.vocab = vocab; a.ids = ids; a.mask = mask; a.n_docs = n_docs; a.wpack = umma_w2; a.bias = bias;
+    a.feat = feat; a.argmax = argmax; a.preact = preact; a.gate = gate; a.gate_mode = gate_mode; a.feat_ld = feat_ld;
+    switch (K) {
+        case 1: return tc2_launch<1>(tm, a, s);
+        case 2: return tc2_launch<2>(tm, a, s);
+        case 3: return tc2_launch<3>(tm, a, s);
+        case 4: return tc2_launch<4>(tm, a, s);
+        case 5: return tc2_launch<5>(tm, a, s);
+        default: return tc2_launch<7>(tm, a, s);
+    }
+}
+
+}  // namespace rbr
+
+RBR_DEFINE_OOB_ACCESSOR(conv_tc2)

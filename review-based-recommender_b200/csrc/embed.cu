@@ -178,11 +178,13 @@ __global__ void __launch_bounds__(256) table_to_bf16_kernel(const float* __restr
 
 // K0: conv weight packing, weight [H][E][k] (nn.Conv1d) → the three layouts of PackLayout
 __global__ void conv_pack_kernel(const float* __restrict__ w, int E, int H, int k, int Hpad4, int Epad4, int Epad16, int Npad, int Nb,
-                                 float* __restrict__ keh, float* __restrict__ hke, __nv_bfloat16* __restrict__ umma) {
+                                 int Npad2, int Nb2, float* __restrict__ keh, float* __restrict__ hke,
+                                 __nv_bfloat16* __restrict__ umma, __nv_bfloat16* __restrict__ umma2) {
     const int64_t n_keh = (int64_t)k * E * Hpad4;
     const int64_t n_hke = (int64_t)H * k * Epad4;
     const int64_t n_umma = (int64_t)k * Epad16 * Npad;
-    const int64_t total = n_keh + n_hke + n_umma;
+    const int64_t n_umma2 = (int64_t)k * Epad16 * Npad2;
+    const int64_t total = n_keh + n_hke + n_umma + n_umma2;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += stride) {
         if (q < n_keh) {
@@ -196,6 +198,20 @@ __global__ void conv_pack_kernel(const float* __restrict__ w, int E, int H, int 
             const int j = (int)((r / Epad4) % k);
             const int h = (int)(r / ((int64_t)Epad4 * k));
             hke[r] = (e < E) ? w[((int64_t)h * E + e) * k + j] : 0.f;
+        } else if (q >= n_keh + n_hke + n_umma) {
+            // CTA-pair layout: [pass][half][j][chunk c][row n < Nb2/2][e%8],  filter h = pass*Nb2 + half*Nb2/2 + n
+            const int64_t r = q - n_keh - n_hke - n_umma;
+            const int C = Epad16 >> 3, NL = Nb2 >> 1;
+            const int e8 = (int)(r & 7);
+            int64_t u = r >> 3;
+            const int n = (int)(u % NL); u /= NL;
+            const int c = (int)(u % C); u /= C;
+            const int j = (int)(u % k); u /= k;
+            const int half = (int)(u & 1); u >>= 1;
+            const int h = (int)u * Nb2 + half * NL + n;
+            const int e = c * 8 + e8;
+            const float v = (h < H && e < E) ? w[((int64_t)h * E + e) * k + j] : 0.f;
+            umma2[r] = __float2bfloat16_rn(v);
         } else {
             // [pass][j][chunk c = e/8][row n][e%8],  filter h = pass*Nb + n
             const int64_t r = q - n_keh - n_hke;
@@ -317,12 +333,13 @@ extern "C" int rbr_conv_pack(const float* weight, int64_t emb, int64_t filters, 
     RBR_REQUIRE((uintptr_t)packed % 256 == 0, RBR_EINVAL, "rbr_conv_pack: packed buffer must be 256-byte aligned");
     const PackLayout p = pack_layout(emb, filters, ksize);
     char* base = reinterpret_cast<char*>(packed);
-    RBR_CUDA(cudaMemsetAsync(base + p.off_zero, 0, (size_t)(p.total - p.off_zero), as_stream(stream)));
-    const int64_t total = ksize * emb * p.Hpad4 + filters * ksize * p.Epad4 + ksize * p.Epad16 * p.Npad;
+    RBR_CUDA(cudaMemsetAsync(base + p.off_zero, 0, (size_t)(p.off_umma2 - p.off_zero), as_stream(stream)));
+    const int64_t npad2 = p.P2 * p.Nb2;
+    const int64_t total = ksize * emb * p.Hpad4 + filters * ksize * p.Epad4 + ksize * p.Epad16 * (p.Npad + npad2);
     conv_pack_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(
         weight, (int)emb, (int)filters, (int)ksize, (int)p.Hpad4, (int)p.Epad4, (int)p.Epad16, (int)p.Npad, (int)(p.Nb > 0 ? p.Nb : 1),
-        reinterpret_cast<float*>(base + p.off_keh), reinterpret_cast<float*>(base + p.off_hke),
-        reinterpret_cast<__nv_bfloat16*>(base + p.off_umma));
+        (int)npad2, (int)(p.Nb2 > 0 ? p.Nb2 : 2), reinterpret_cast<float*>(base + p.off_keh), reinterpret_cast<float*>(base + p.off_hke),
+        reinterpret_cast<__nv_bfloat16*>(base + p.off_umma), reinterpret_cast<__nv_bfloat16*>(base + p.off_umma2));
     RBR_LAUNCH_CHECK("conv_pack");
     return RBR_OK;
 }

@@ -62,9 +62,14 @@ __device__ __forceinline__ void note_oob() { atomicAdd(&g_oob_count, 1u); }
 // (P, Nb) come from tc_pass_split (conv_tc.cu): the largest filter block whose weights stay resident in
 // shared memory next to the activation ring; P == 0 means the tensor-core variant cannot take this shape.
 void tc_pass_split(int64_t E, int64_t H, int64_t K, int64_t* P, int64_t* Nb);
+// [off_umma2]    bf16  B operand of the CTA-pair kernel (conv_tc2.cu): each CTA of a pair keeps HALF of a pass's filters:
+//                       [P2 passes][2 halves][k][Epad16/8 chunks][Nb2/2 rows][8 bf16]   (filter h = pass*Nb2 + half*Nb2/2 + row)
+void tc2_pass_split(int64_t E, int64_t H, int64_t K, int64_t* P, int64_t* Nb);
 struct PackLayout {
     int64_t E, H, k;
     int64_t P, Nb;      // tensor-core filter passes and filters per pass
+    int64_t P2, Nb2;    // the same for the CTA-pair kernel (P2 == 0: unavailable)
+    int64_t off_umma2;
     int64_t Hpad4;      // H rounded up to 4
     int64_t Epad4;      // E rounded up to 4
     int64_t Epad16;     // E rounded up to 16 (UMMA K granularity for bf16)
@@ -88,6 +93,9 @@ inline PackLayout pack_layout(int64_t E, int64_t H, int64_t k) {
     b = p.off_umma + k * p.Epad16 * p.Npad * 2;
     p.off_zero = round_up(b, 256);
     b = p.off_zero + round_up(E, 64) * 2 + 256;
+    p.off_umma2 = round_up(b, 256);
+    tc2_pass_split(E, H, k, &p.P2, &p.Nb2);
+    b = p.off_umma2 + k * p.Epad16 * p.P2 * p.Nb2 * 2;
     p.total = round_up(b, 256);
     return p;
 }

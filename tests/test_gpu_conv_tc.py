@@ -14,6 +14,16 @@ from test_gpu_parity import DEEPCONN_CASES, NARRE_CASES, build_model, run_step
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(params=[1, 2], ids=["cta1-cpasync", "pair-tma"], autouse=True)
+def tc_variant(request):
+    """Every test of this file runs on BOTH tensor-core kernels: conv_tc.cu (single CTA, cp.async operands) and
+    conv_tc2.cu (CTA pair, cta_group::2, TMA gather4 operands); variant 2 errors out instead of falling back."""
+    from rbr_b200._lib import lib
+    prev = lib.rbr_set_conv_tc_variant(request.param)
+    yield request.param
+    lib.rbr_set_conv_tc_variant(prev)
+
+
 def _bf16_round(t):
     return t.to(torch.bfloat16).to(torch.float32)
 
@@ -146,3 +156,20 @@ def test_bf16_full_batch_properties():
                 perm = torch.randperm(B, device="cuda")
                 assert torch.equal(model(*[t[perm] for t in b]), preds[prec][perm])
     assert rel_err(preds["bf16"].cpu(), preds["fp32"].cpu()) < 1e-2
+
+
+def test_variants_agree_bitwise_on_values():
+    """The two kernels issue the same K-step / tap order into fp32 TMEM accumulators: identical pooled values."""
+    from rbr_b200._lib import lib
+    gen = torch.Generator().manual_seed(12)
+    V, E, H, k, n, L = 4000, 300, 100, 3, 300, 500
+    table = torch.randn(V, E, generator=gen)
+    w = (torch.rand(H, E, k, generator=gen) * 2 - 1) / (E * k) ** 0.5
+    b = (torch.rand(H, generator=gen) * 2 - 1) * 0.1
+    ids, mask = synth.doc_batch(n, L, V, seed=99)
+    outs = []
+    for variant in (1, 2):
+        lib.rbr_set_conv_tc_variant(variant)
+        outs.append(ops.conv_act_maxpool(table.cuda(), ids.cuda(), mask.cuda(), w.cuda(), b.cuda(), 1, precision="bf16"))
+    assert torch.equal(outs[0][0], outs[1][0])
+    assert torch.equal(outs[0][1], outs[1][1])
