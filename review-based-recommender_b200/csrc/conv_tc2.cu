@@ -48,6 +48,7 @@ struct Tc2Plan {
     int nst;          // ring stages
     int w_bytes;      // resident weights per CTA = K * C * NL * 16
     int mode_b, D, tpu;
+    int S;            // mode B: tile rows between consecutive documents (Lext, or Lext rounded up to 32 when that packs as many)
     int64_t n_units;
     int tmem_cols, acc_stride;
     int off_ring, off_w, off_bias, off_keys, off_bars, off_slot, smem_bytes;   // offsets from the 1024-aligned base
@@ -96,10 +97,11 @@ __device__ __forceinline__ bool t2_row_source(const Tc2Plan& p, int64_t unit, in
     int64_t d;
     int ext;
     if (p.mode_b) {
-        const int q = r / p.Lext;
+        const int q = r / p.S;
         if (q >= p.D) return false;
         d = unit * p.D + q;
-        ext = r - q * p.Lext;
+        ext = r - q * p.S;
+        if (ext >= p.Lext) return false;
     } else {
         d = unit;
         ext = tt * T2_M + r;
@@ -150,7 +152,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const Tc2Args a) {
         fence_barrier_init();
     }
     for (int i = threadIdx.x; i < p.Nb; i += blockDim.x) bias_s[i] = (h0 + i < p.H) ? a.bias[h0 + i] : 0.f;
-    for (int i = threadIdx.x; i < p.D * p.Nb; i += blockDim.x) keys_s[i] = 0ull;
+    for (int i = threadIdx.x; i < 2 * p.D * p.Nb; i += blockDim.x) keys_s[i] = 0ull;
     if (warp == T2_MMA_WARP) tmem_alloc2(smem_u32((const void*)tmem_slot), (uint32_t)p.tmem_cols);
     if (warp == T2_PROD_WARP0 && lane == 0) tma_prefetch_desc(&tmap);
     tc_fence_before();
@@ -310,14 +312,17 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const Tc2Args a) {
             const int64_t unit = ci + (g / p.tpu) * ctas_per_pass;
             const int tt = (int)(g % p.tpu);
             const int buf = (int)(g & 1);
+            // pooled keys are double buffered by unit parity: ONE named barrier per unit (the buffer is next written two units later,
+            // i.e. after the following unit's barrier, which every thread passes only once it has finalised this unit)
+            unsigned long long* keys_u = keys_s + ((g / p.tpu) & 1) * (p.D * p.Nb);
             int slot, t;
-            if (p.mode_b) { slot = m / p.Lext; t = m - slot * p.Lext; } else { slot = 0; t = tt * T2_M + m; }
+            if (p.mode_b) { slot = m / p.S; t = m - slot * p.S; } else { slot = 0; t = tt * T2_M + m; }
             const int64_t my_doc = p.mode_b ? unit * p.D + slot : unit;
             const bool valid = (t < p.Lout) && (slot < p.D) && (unit < p.n_units) && (my_doc < a.n_docs);
             float row_gate = 1.f;
             if (a.gate_mode == 1 && valid) row_gate = a.gate[my_doc * p.L + t];
-            const int slot_lo = p.mode_b ? (quad * 32) / p.Lext : 0;
-            int slot_hi = p.mode_b ? (quad * 32 + 31) / p.Lext : 0;
+            const int slot_lo = p.mode_b ? (quad * 32) / p.S : 0;
+            int slot_hi = p.mode_b ? (quad * 32 + 31) / p.S : 0;
             if (slot_hi >= p.D) slot_hi = p.D - 1;
 
             mbar_wait(bar_accf + 8 * buf, (uint32_t)((g >> 1) & 1));
@@ -344,10 +349,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const Tc2Args a) {
                     else tc_colmax<false>(v, mine, lane, keep_v, keep_b);
                     if (lane < 16 && keep_b) {
                         const int first = __ffs(keep_b) - 1;
-                        const int tf = p.mode_b ? (quad * 32 + first - sl * p.Lext) : (tt * T2_M + quad * 32 + first);
+                        const int tf = p.mode_b ? (quad * 32 + first - sl * p.S) : (tt * T2_M + quad * 32 + first);
                         const unsigned long long key =
                             ((unsigned long long)f2ord(keep_v) << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)tf);
-                        atomicMax(keys_s + sl * p.Nb + c0 + lane, key);
+                        atomicMax(keys_u + sl * p.Nb + c0 + lane, key);
                     }
                 }
             }
@@ -361,8 +366,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const Tc2Args a) {
                 for (int o = threadIdx.x; o < p.D * p.Nb; o += T2_EPI_THREADS) {
                     const int sl = o / p.Nb, c = o - sl * p.Nb;
                     const int64_t doc = p.mode_b ? unit * p.D + sl : unit;
-                    const unsigned long long key = keys_s[o];
-                    keys_s[o] = 0ull;
+                    const unsigned long long key = keys_u[o];
+                    keys_u[o] = 0ull;
                     if (unit < p.n_units && doc < a.n_docs && h0 + c < p.H) {
                         const float raw_v = __uint_as_float(ord2f((uint32_t)(key >> 32)));
                         const int tbest = (int)(0xFFFFFFFFu - (uint32_t)key);
@@ -372,7 +377,6 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const Tc2Args a) {
                         a.argmax[doc * a.feat_ld + h0 + c] = tbest;
                     }
                 }
-                asm volatile("bar.sync 1, %0;" ::"n"(T2_EPI_THREADS) : "memory");
             }
         }
     }
@@ -401,6 +405,7 @@ static bool tc2_make_plan(int E, int H, int K, int L, int pad, int act, int64_t 
     p.stage_tx = p.groups * 512;
     p.stage_bytes = t2_stage_bytes(K);
     p.w_bytes = K * p.C * p.NL * 16;
+    p.S = p.Lext;
     if (p.Lext * 2 <= T2_M + K - 1) {
         p.mode_b = 1;
         p.D = (T2_M + K - 1) / p.Lext;
@@ -408,6 +413,9 @@ static bool tc2_make_plan(int E, int H, int K, int L, int pad, int act, int64_t 
         if (dmax > T2_MAX_SLOTS) dmax = T2_MAX_SLOTS;
         if (dmax < 1) dmax = 1;
         if (p.D > dmax) p.D = dmax;
+        // documents aligned to 32-row (epilogue-warp) boundaries when that packs as many per tile: no warp straddles two docs
+        const int s32 = (int)round_up(p.Lext, 32);
+        if ((T2_M + K - 1 - p.Lext) / s32 + 1 >= p.D) p.S = s32;
         p.tpu = 1;
         p.n_units = (n_docs + p.D - 1) / p.D;
     } else {
@@ -418,7 +426,7 @@ static bool tc2_make_plan(int E, int H, int K, int L, int pad, int act, int64_t 
     }
     p.acc_stride = p.Nb <= 128 ? 128 : 256;
     p.tmem_cols = 2 * p.acc_stride;
-    const int tail = p.Nb * 4 + 8 + p.D * p.Nb * 8 + 8 * (2 * 16 + 5) + 16;
+    const int tail = p.Nb * 4 + 8 + 2 * p.D * p.Nb * 8 + 8 * (2 * 16 + 5) + 16;
     int nst = (T2_SMEM_MAX - 1024 - p.w_bytes - tail - 256) / p.stage_bytes;
     if (nst > 16) nst = 16;
     if (nst < T2_MIN_STAGES) return false;
@@ -429,7 +437,7 @@ static bool tc2_make_plan(int E, int H, int K, int L, int pad, int act, int64_t 
     off = (off + 15) / 16 * 16;
     p.off_bias = off; off += p.Nb * 4;
     off = (off + 7) / 8 * 8;
-    p.off_keys = off; off += p.D * p.Nb * 8;
+    p.off_keys = off; off += 2 * p.D * p.Nb * 8;
     p.off_bars = off; off += 8 * (2 * nst + 5);
     p.off_slot = off; off += 16;
     p.smem_bytes = off + 1024;                   // slack for the manual 1024-byte alignment of the base

@@ -143,14 +143,15 @@ __device__ __forceinline__ void tc_colmax(const uint32_t (&v)[16], bool mine, in
         r[i] = __reduce_max_sync(0xffffffffu, x);
         neg |= r[i];
     }
-    if (neg < 0) {                                                     // warp-uniform, rare: some column has no candidate >= 0
+    if (neg < 0) {   // warp-uniform: some column has no candidate >= 0 (common when only a few rows of the warp are `mine`)
+        int rn[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-            if (r[i] < 0) {
-                const uint32_t y = (FULL || mine) ? v[i] : 0xFFFFFFFFu;
-                r[i] = (int)__reduce_min_sync(0xffffffffu, y);         // smallest magnitude among negatives
-            }
+            const uint32_t y = (FULL || mine) ? v[i] : 0xFFFFFFFFu;
+            rn[i] = (int)__reduce_min_sync(0xffffffffu, y);            // smallest magnitude among negatives
         }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) r[i] = r[i] < 0 ? rn[i] : r[i];
     }
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
