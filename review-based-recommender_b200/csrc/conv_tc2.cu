@@ -14,9 +14,10 @@
 //     per-SM operand read traffic of every MMA and frees ~100 KB for a 7-stage ring of 64-wide K blocks.
 //   * D: each CTA owns the accumulator rows of its own 128-position tile (TMEM, double buffered); the epilogue (exact
 //     fp32 max-over-time with first-arg-max via redux/ballot) is per CTA, unchanged from conv_tc.cu.
-// Pipeline: per CTA four TMA producer warps, 8 epilogue warps; the LEADER CTA's MMA warp issues every tcgen05.mma for the
+// Pipeline: per CTA four TMA producer warps, 16 epilogue warps; the LEADER CTA's MMA warp issues every tcgen05.mma for the
 // pair.  full[s] lives in the leader (both CTAs' TMA bytes complete on it), empty[s] / acc_full[b] are multicast by
 // tcgen05.commit to both CTAs, acc_empty[b] collects one arrive per epilogue warp of both CTAs.
+#include <stdlib.h>
 #include <cuda.h>   // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint, no -lcuda)
 
 #include "rbr_common.cuh"
@@ -26,12 +27,12 @@ namespace rbr {
 
 constexpr int T2_SMEM_MAX = 232448;        // 227 KB opt-in dynamic shared memory per CTA
 constexpr int T2_M = 128;                  // positions per CTA tile (UMMA M = 256 over the pair)
-constexpr int T2_EPI_WARPS = 8;
-constexpr int T2_EPI_THREADS = T2_EPI_WARPS * 32;
-constexpr int T2_PROD_WARP0 = T2_EPI_WARPS;      // 4 TMA producer warps (one per SM sub-partition: TMA issue is serialised per warp)
+// Epilogue warps EW (template parameter of the kernel): 8 or 16 = 2 or 4 per TMEM lane quadrant, each reducing a share of
+// the 16-column chunks.  The max-reduction is a chain of fixed-latency warp ops: 16 warps hide it when there is a lot of it
+// per tile (many filter chunks, or short documents = per-tile finalisation), 8 leave more issue slots to the MMA warp.
+// Warp roles: [0, EW) epilogue, [EW, EW+4) TMA producers (TMA issue is serialised per warp), EW+4 = TMEM owner + MMA issuer.
 constexpr int T2_PROD_WARPS = 4;
-constexpr int T2_MMA_WARP = T2_EPI_WARPS + T2_PROD_WARPS;
-constexpr int T2_THREADS = (T2_MMA_WARP + 1) * 32;
+constexpr int t2_threads(int ew) { return (ew + T2_PROD_WARPS + 1) * 32; }
 constexpr int T2_MAX_SLOTS = 6;            // documents packed into one tile (short-document mode)
 constexpr int T2_MIN_STAGES = 3;
 
@@ -53,6 +54,8 @@ struct Tc2Plan {
     int tmem_cols, acc_stride;
     int off_ring, off_w, off_bias, off_keys, off_bars, off_slot, smem_bytes;   // offsets from the 1024-aligned base
     int act;
+    uint32_t boff[4 * 8];   // B-descriptor offset (16-byte units) of (K-step ks, tap j) inside a K block: [ks * 8 + j]
+    int dbg;          // RBR_TC2_DEBUG bits (timing experiments only; results are wrong): 1 = skip the MMAs, 2 = skip the max-reduction
 };
 
 static inline int t2_stage_bytes(int K) {
@@ -115,9 +118,11 @@ __device__ __forceinline__ bool t2_row_source(const Tc2Plan& p, int64_t unit, in
     return true;
 }
 
-template <int KT>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1)
+template <int KT, int EW>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(t2_threads(EW), 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const Tc2Args a) {
+    constexpr int T2_EPI_WARPS = EW, T2_EPI_SHARES = EW / 4, T2_EPI_THREADS = EW * 32;
+    constexpr int T2_PROD_WARP0 = EW, T2_MMA_WARP = EW + T2_PROD_WARPS;
     extern __shared__ uint8_t smem_raw[];
     const Tc2Plan& p = a.p;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -179,7 +184,6 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const Tc2Args a) {
                 const uint64_t a_desc0 = umma_desc_sw128(ring_s);                          // stage 0, tap 0, K-step 0
                 const uint64_t b_desc0 = umma_desc(w_s, (uint32_t)p.NL * 16u, 128u);       // tap 0, K-step 0
                 const uint32_t a_stage_inc = (uint32_t)p.stage_bytes >> 4;                 // descriptor address units (16 B)
-                const uint32_t b_tap_inc = (uint32_t)(p.C * p.NL);                         // one tap = C chunk columns of NL rows
                 const uint32_t b_step_inc = (uint32_t)(2 * p.NL);                          // one K-step = 2 chunk columns
                 int stage = 0;
                 uint32_t ph = 0;
@@ -198,11 +202,11 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const Tc2Args a) {
                         if (leader_lane) {
 #pragma unroll
                             for (int ks = 0; ks < 4; ++ks) {
-                                if (ks < ks_left) {
+                                if (ks < ks_left && !(p.dbg & 1)) {
 #pragma unroll
                                     for (int j = 0; j < KT; ++j)
-                                        umma_bf16_2(d_tmem, ad + (uint64_t)(ks * 2 + j * 8), bd + (uint64_t)(ks * b_step_inc + j * b_tap_inc),
-                                                    idesc, (uint32_t)((kb | ks | j) != 0));
+                                        umma_bf16_2(d_tmem, ad + (uint64_t)(ks * 2 + j * 8), bd + (uint64_t)p.boff[ks * 8 + j], idesc,
+                                                    (uint32_t)((kb | ks | j) != 0));
                                 }
                             }
                             umma_commit2(empty_bar);                                       // frees the ring slot in both CTAs
@@ -301,13 +305,14 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const Tc2Args a) {
             }
         }
     } else {
-        // =========================== epilogue (8 warps; warp w reads TMEM lanes 32(w&3)..+31, half of the column chunks) ===========================
+        // =========================== epilogue (16 warps; warp w reads TMEM lanes 32(w&3)..+31 and reduces 1/4 of the column chunks:
+        // the reduction is a chain of fixed-latency warp ops, so it is latency- not issue-bound and more warps hide it) ===========================
         const int quad = warp & 3;
-        const int half = warp >> 2;
+        const int share = warp >> 2;
         const int m = quad * 32 + lane;                       // tile row = TMEM lane
         const int n_chunks = p.Nb / 16;
-        const int chunk_lo = half ? (n_chunks + 1) / 2 : 0;
-        const int chunk_hi = half ? n_chunks : (n_chunks + 1) / 2;
+        const int chunk_lo = n_chunks * share / T2_EPI_SHARES;
+        const int chunk_hi = n_chunks * (share + 1) / T2_EPI_SHARES;
         for (int64_t g = 0; g < pair_tiles; ++g) {
             const int64_t unit = ci + (g / p.tpu) * ctas_per_pass;
             const int tt = (int)(g % p.tpu);
@@ -342,7 +347,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const Tc2Args a) {
 #pragma unroll
                     for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * row_gate);
                 }
-                for (int sl = slot_lo; sl <= slot_hi; ++sl) {
+                for (int sl = slot_lo; sl <= slot_hi && !(p.dbg & 2); ++sl) {
                     const bool mine = valid && slot == sl;
                     uint32_t keep_v = 0, keep_b = 0;
                     if (__all_sync(0xffffffffu, mine)) tc_colmax<true>(v, true, lane, keep_v, keep_b);
@@ -356,7 +361,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const Tc2Args a) {
                     }
                 }
             }
-            if (chunk_lo == chunk_hi) {                       // Nb == 16: the upper half has no chunk but still owes its arrive
+            if (chunk_lo == chunk_hi) {                       // fewer chunks than shares: a warp without a chunk still owes its arrive
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive_cluster(bar_acce + 8 * buf, 0);
@@ -424,6 +429,8 @@ static bool tc2_make_plan(int E, int H, int K, int L, int pad, int act, int64_t 
         p.tpu = (p.Lout + T2_M - 1) / T2_M;
         p.n_units = n_docs;
     }
+    for (int ks = 0; ks < 4; ++ks)
+        for (int j = 0; j < 8; ++j) p.boff[ks * 8 + j] = (uint32_t)(ks * 2 * p.NL + j * p.C * p.NL);   // K-step = 2 chunk columns, tap = C
     p.acc_stride = p.Nb <= 128 ? 128 : 256;
     p.tmem_cols = 2 * p.acc_stride;
     const int tail = p.Nb * 4 + 8 + 2 * p.D * p.Nb * 8 + 8 * (2 * 16 + 5) + 16;
@@ -466,10 +473,11 @@ static EncodeTiledFn tc2_encoder() {
     return fn;
 }
 
-template <int KT>
+template <int KT, int EW>
 static int tc2_launch(const CUtensorMap& tm, const Tc2Args& a, cudaStream_t s) {
     static int max_clusters = -1;
-    auto kern = conv_tc2_kernel<KT>;
+    constexpr int T2_THREADS = t2_threads(EW);
+    auto kern = conv_tc2_kernel<KT, EW>;
     if (max_clusters < 0) {
         RBR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM_MAX));
         cudaLaunchConfig_t cfg{};
@@ -504,6 +512,10 @@ int conv_tc2_dispatch(const __nv_bfloat16* shadow, int64_t vocab, int E, const i
                       int H, int K, int pad, int act, float* feat, int32_t* argmax, float* preact, int feat_ld, cudaStream_t s) {
     Tc2Args a{};
     if (vocab >= (1ll << 31) || !tc2_make_plan(E, H, K, L, pad, act, n_docs, &a.p)) return RBR_EUNSUPPORTED;
+    {
+        static const char* dbg = getenv("RBR_TC2_DEBUG");
+        a.p.dbg = dbg ? atoi(dbg) : 0;
+    }
     if (K != 1 && K != 2 && K != 3 && K != 4 && K != 5 && K != 7) return RBR_EUNSUPPORTED;
     EncodeTiledFn enc = tc2_encoder();
     if (!enc) return RBR_EUNSUPPORTED;
@@ -519,14 +531,18 @@ int conv_tc2_dispatch(const __nv_bfloat16* shadow, int64_t vocab, int E, const i
     RBR_REQUIRE(r == CUDA_SUCCESS, RBR_ECUDA, "conv_fwd[bf16]: cuTensorMapEncodeTiled failed (%d)", (int)r);
     a.vocab = vocab; a.ids = ids; a.mask = mask; a.n_docs = n_docs; a.wpack = umma_w2; a.bias = bias;
     a.feat = feat; a.argmax = argmax; a.preact = preact; a.gate = gate; a.gate_mode = gate_mode; a.feat_ld = feat_ld;
+    static const char* ew_env = getenv("RBR_TC2_EPI_WARPS");                    // timing experiments: force 8 or 16
+    const bool wide = ew_env ? atoi(ew_env) == 16 : (a.p.mode_b || a.p.Nb / 16 >= 9);
+#define RBR_T2(KT_) return wide ? tc2_launch<KT_, 16>(tm, a, s) : tc2_launch<KT_, 8>(tm, a, s)
     switch (K) {
-        case 1: return tc2_launch<1>(tm, a, s);
-        case 2: return tc2_launch<2>(tm, a, s);
-        case 3: return tc2_launch<3>(tm, a, s);
-        case 4: return tc2_launch<4>(tm, a, s);
-        case 5: return tc2_launch<5>(tm, a, s);
-        default: return tc2_launch<7>(tm, a, s);
+        case 1: RBR_T2(1);
+        case 2: RBR_T2(2);
+        case 3: RBR_T2(3);
+        case 4: RBR_T2(4);
+        case 5: RBR_T2(5);
+        default: RBR_T2(7);
     }
+#undef RBR_T2
 }
 
 }  // namespace rbr
