@@ -53,7 +53,9 @@ __global__ void __launch_bounds__(256) conv_bwd_entries_kernel(
 }
 
 // ---- table gradient: warp-segmented reduction over token-sorted entries ----------------------------------
-template <int NQ>
+// WB16: weight rows are read from the bf16 copy of [H][K][Epad4] (bf16 precision mode: the same rounded weights the forward
+// multiplied by, half the bytes per entry — this kernel is bound by L1/L2 reads of weight rows, 1.2 KB each in fp32).
+template <int NQ, bool WB16>
 __global__ void __launch_bounds__(256) conv_bwd_table_kernel(const int32_t* __restrict__ order, const int32_t* __restrict__ keys,
                                                              const float* __restrict__ coef, int64_t n_entries, const int32_t* __restrict__ n_kept,
                                                              int H, int K, const float4* __restrict__ whke, int e4w /* Epad4/4 */,
@@ -83,12 +85,21 @@ __global__ void __launch_bounds__(256) conv_bwd_table_kernel(const int32_t* __re
         const int key = __shfl_sync(0xffffffffu, key_l, d);
         if (key < 0) break;                              // skipped entries are sorted last (warp-uniform)
         const float g = __shfl_sync(0xffffffffu, g_l, d);
-        const float4* wrow = whke + (int64_t)__shfl_sync(0xffffffffu, row_l, d) * e4w;
+        const int64_t wrow_i = (int64_t)__shfl_sync(0xffffffffu, row_l, d) * e4w;
         float4 w[NQ];
 #pragma unroll
         for (int q = 0; q < NQ; ++q) {
             const int c = lane + 32 * q;
-            w[q] = (c < e4) ? __ldg(wrow + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+            w[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (c < e4) {
+                if (WB16) {
+                    const uint2 u = __ldg(reinterpret_cast<const uint2*>(whke) + wrow_i + c);      // 4 bf16
+                    w[q] = make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xFFFF0000u), __uint_as_float(u.y << 16),
+                                       __uint_as_float(u.y & 0xFFFF0000u));
+                } else {
+                    w[q] = __ldg(whke + wrow_i + c);
+                }
+            }
         }
         if (key != cur) {
             if (cur >= 0) {
@@ -388,8 +399,13 @@ extern "C" int rbr_conv_act_maxpool_bwd(int precision, int activation, const voi
             const int chunk = 32;
             const int64_t warps = (ne + chunk - 1) / chunk;
             const int blocks = (int)((warps * 32 + 255) / 256);
+            const bool wb16 = precision == RBR_PREC_BF16;
+            const float4* wsrc = wb16 ? reinterpret_cast<const float4*>(reinterpret_cast<const char*>(packed) + pl.off_hke16)
+                                      : reinterpret_cast<const float4*>(whke);
 #define RBR_T(NQ)                                                                                                            \
-    conv_bwd_table_kernel<NQ><<<blocks, 256, 0, s>>>(ts.order, w.keys, w.coef, ne, ts.start + vocab, H, K, reinterpret_cast<const float4*>(whke), \
+    if (wb16) conv_bwd_table_kernel<NQ, true><<<blocks, 256, 0, s>>>(ts.order, w.keys, w.coef, ne, ts.start + vocab, H, K, wsrc, \
+                                                     epad4 >> 2, E >> 2, reinterpret_cast<float4*>(table_grad), chunk);      \
+    else conv_bwd_table_kernel<NQ, false><<<blocks, 256, 0, s>>>(ts.order, w.keys, w.coef, ne, ts.start + vocab, H, K, wsrc, \
                                                      epad4 >> 2, E >> 2, reinterpret_cast<float4*>(table_grad), chunk)
             if (nq == 1) RBR_T(1); else if (nq == 2) RBR_T(2); else if (nq == 3) RBR_T(3); else RBR_T(4);
 #undef RBR_T

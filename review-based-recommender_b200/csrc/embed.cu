@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(256) table_to_bf16_kernel(const float* __restr
 // K0: conv weight packing, weight [H][E][k] (nn.Conv1d) → the three layouts of PackLayout
 __global__ void conv_pack_kernel(const float* __restrict__ w, int E, int H, int k, int Hpad4, int Epad4, int Epad16, int Npad, int Nb,
                                  int Npad2, int Nb2, float* __restrict__ keh, float* __restrict__ hke,
-                                 __nv_bfloat16* __restrict__ umma, __nv_bfloat16* __restrict__ umma2) {
+                                 __nv_bfloat16* __restrict__ umma, __nv_bfloat16* __restrict__ umma2, __nv_bfloat16* __restrict__ hke16) {
     const int64_t n_keh = (int64_t)k * E * Hpad4;
     const int64_t n_hke = (int64_t)H * k * Epad4;
     const int64_t n_umma = (int64_t)k * Epad16 * Npad;
@@ -197,7 +197,9 @@ __global__ void conv_pack_kernel(const float* __restrict__ w, int E, int H, int 
             const int e = (int)(r % Epad4);
             const int j = (int)((r / Epad4) % k);
             const int h = (int)(r / ((int64_t)Epad4 * k));
-            hke[r] = (e < E) ? w[((int64_t)h * E + e) * k + j] : 0.f;
+            const float v = (e < E) ? w[((int64_t)h * E + e) * k + j] : 0.f;
+            hke[r] = v;
+            hke16[r] = __float2bfloat16_rn(v);
         } else if (q >= n_keh + n_hke + n_umma) {
             // CTA-pair layout: [pass][half][j][chunk c][row n < Nb2/2][e%8],  filter h = pass*Nb2 + half*Nb2/2 + n
             const int64_t r = q - n_keh - n_hke - n_umma;
@@ -339,7 +341,8 @@ extern "C" int rbr_conv_pack(const float* weight, int64_t emb, int64_t filters, 
     conv_pack_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(
         weight, (int)emb, (int)filters, (int)ksize, (int)p.Hpad4, (int)p.Epad4, (int)p.Epad16, (int)p.Npad, (int)(p.Nb > 0 ? p.Nb : 1),
         (int)npad2, (int)(p.Nb2 > 0 ? p.Nb2 : 2), reinterpret_cast<float*>(base + p.off_keh), reinterpret_cast<float*>(base + p.off_hke),
-        reinterpret_cast<__nv_bfloat16*>(base + p.off_umma), reinterpret_cast<__nv_bfloat16*>(base + p.off_umma2));
+        reinterpret_cast<__nv_bfloat16*>(base + p.off_umma), reinterpret_cast<__nv_bfloat16*>(base + p.off_umma2),
+        reinterpret_cast<__nv_bfloat16*>(base + p.off_hke16));
     RBR_LAUNCH_CHECK("conv_pack");
     return RBR_OK;
 }

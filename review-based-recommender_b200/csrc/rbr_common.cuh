@@ -70,6 +70,7 @@ struct PackLayout {
     int64_t P, Nb;      // tensor-core filter passes and filters per pass
     int64_t P2, Nb2;    // the same for the CTA-pair kernel (P2 == 0: unavailable)
     int64_t off_umma2;
+    int64_t off_hke16;  // bf16 copy of Whke [H][k][Epad4] (table-gradient kernel in bf16 mode)
     int64_t Hpad4;      // H rounded up to 4
     int64_t Epad4;      // E rounded up to 4
     int64_t Epad16;     // E rounded up to 16 (UMMA K granularity for bf16)
@@ -96,6 +97,8 @@ inline PackLayout pack_layout(int64_t E, int64_t H, int64_t k) {
     p.off_umma2 = round_up(b, 256);
     tc2_pass_split(E, H, k, &p.P2, &p.Nb2);
     b = p.off_umma2 + k * p.Epad16 * p.P2 * p.Nb2 * 2;
+    p.off_hke16 = round_up(b, 256);
+    b = p.off_hke16 + H * k * p.Epad4 * 2;
     p.total = round_up(b, 256);
     return p;
 }
