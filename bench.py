@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """bench.py — fwd+bwd samples/s of the review-encoder hot path on N B200s (one process per GPU).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--model deepconn|narre] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--model deepconn|narre|dual_att] [--mode train|infer]
+                    [--impl ours|reference]
 
 One "step" = optimizer.zero_grad() + forward + nn.MSELoss + backward (+ the gradient all-reduce when N > 1),
 i.e. trainer/train_deepconn_pp.py:161-165 of the reference, on BASELINE.json's configs[1]:
@@ -32,12 +33,23 @@ import torch  # noqa: E402
 CFG = {
     "deepconn": dict(B=4096, L=500, V=50000, E=300, H=100, K=32, U=20000, I=12000, ks=(3,)),
     "narre": dict(B=4096, R=10, T=60, V=50000, E=300, H=150, A=32, K=32, U=20000, I=12000, ks=(3,)),
+    # BASELINE.json configs[3]; dims from default_dual_att.json:17 and dual_att.py:20-21
+    "dual_att": dict(B=4096, L=500, V=50000, E=100, lw=5, lo=200, go=100, h1=500, h2=50),
+    # BASELINE.json configs[4]: inference scoring, vocab 200k (the fp32 table, 240 MB, does not fit L2), pairs sharded over ranks
+    "deepconn_infer": dict(B=4096, L=500, V=200000, E=300, H=100, K=32, U=20000, I=12000, ks=(3,)),
 }
-METRIC = {"deepconn": "DeepCoNN fwd+bwd samples/sec", "narre": "NARRE fwd+bwd samples/sec"}
+METRIC = {"deepconn": "DeepCoNN fwd+bwd samples/sec", "narre": "NARRE fwd+bwd samples/sec",
+          "dual_att": "D-ATT fwd+bwd samples/sec", "deepconn_infer": "DeepCoNN inference pairs/sec"}
 
 
 def workload_name(model):
     c = CFG[model]
+    if model == "dual_att":
+        return (f"D-ATT train step B={c['B']}/GPU doc={c['L']} vocab={c['V']} emb={c['E']} local {c['lo']}@k1 (window {c['lw']}) "
+                f"global 3x{c['go']}@k2,3,4 fc {c['h1']}-{c['h2']} (BASELINE.json configs[3])")
+    if model == "deepconn_infer":
+        return (f"DeepCoNN eval forward B={c['B']} pairs/step/GPU doc={c['L']} vocab={c['V']} emb={c['E']} filters={c['H']} k=3 "
+                f"(BASELINE.json configs[4]; pairs sharded over GPUs, no collective)")
     if model == "deepconn":
         return (f"DeepCoNN train step B={c['B']}/GPU doc={c['L']} vocab={c['V']} emb={c['E']} filters={c['H']} k=3 "
                 f"latent={c['K']} (BASELINE.json configs[1])")
@@ -62,13 +74,25 @@ def cpu_arm(model, sample_b, steps, warmup):
     from rbr_b200 import synth
     c = CFG[model]
     torch.set_num_threads(max(1, os.cpu_count() or 1))
-    if model == "deepconn":
+    if model in ("deepconn", "deepconn_infer"):
         params = synth.deepconn_params(c["U"], c["I"], c["V"], c["E"], c["H"], c["K"], c["ks"], seed=0)
         batch, ratings = synth.deepconn_batch(sample_b, c["L"], c["V"], c["U"], c["I"], seed=synth.SEED_BASE)
+    elif model == "dual_att":
+        params = synth.dual_att_params(c["V"], c["L"], c["lw"], c["lo"], c["go"], c["E"], c["h1"], c["h2"], seed=0)
+        batch, ratings = synth.dual_att_batch(sample_b, c["L"], c["V"], seed=synth.SEED_BASE)
     else:
         params = synth.narre_params(c["U"], c["I"], c["V"], c["E"], c["H"], c["A"], c["K"], c["ks"], seed=0)
         batch, ratings = synth.narre_batch(sample_b, c["R"], c["T"], c["V"], c["U"], c["I"], seed=synth.SEED_BASE)
-    sec = orc.time_fwd_bwd(model, params, batch, ratings, steps=steps, warmup=warmup)
+    if model == "deepconn_infer":
+        with torch.no_grad():
+            for _ in range(warmup):
+                orc.deepconn_forward(params, *batch)
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                orc.deepconn_forward(params, *batch)
+            sec = (time.perf_counter() - t0) / max(steps, 1)
+    else:
+        sec = orc.time_fwd_bwd(model, params, batch, ratings, steps=steps, warmup=warmup)
     return dict(value=sample_b / sec, unit="samples/s", cores=torch.get_num_threads(), kind="port",
                 sample=f"{sample_b} samples of the same workload per step, {steps} timed steps after {warmup} warm-up "
                        f"(oracle/rbr_oracle.py, torch CPU, {torch.get_num_threads()} threads of {os.cpu_count()} cores)"), sec
@@ -81,6 +105,8 @@ def run_reference_arm(args):
     sample_b = 128
     steps = max(1, min(args.steps, 5))
     warm = max(1, min(args.warmup, 2))
+    if args.mode == "infer":
+        args.model = "deepconn_infer"
     cb, sec = cpu_arm(args.model, sample_b, steps, warm)
     line = {
         "impl": "reference", "metric": METRIC[args.model], "value": cb["value"], "unit": "samples/s", "n_gpus": args.gpus,
@@ -95,7 +121,7 @@ def run_reference_arm(args):
 
 
 # ----------------------------------------------------------------------------------------------------
-# clocks sampler (NVML in a background thread, ~20 ms period, during the timed regions only)
+# clocks sampler (NVML in a background thread, ~50 ms period; samples kept from the timed regions only)
 # ----------------------------------------------------------------------------------------------------
 class ClockSampler:
     REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
@@ -124,13 +150,18 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.02)
+            time.sleep(0.05)
 
     def start(self):
-        if self.nv is not None:
+        if self.nv is not None and not os.environ.get("RBR_BENCH_NO_NVML"):
             self._stop.clear()
             self._thr = threading.Thread(target=self._loop, daemon=True)
             self._thr.start()
+
+    def mark(self):
+        """Forget what was sampled so far (the thread keeps running: its first NVML calls are slow and contend with kernel
+        launches for the driver lock, so it is started before the warm-up and only marked at the start of a timed region)."""
+        self.samples, self.reasons = [], set()
 
     def stop(self):
         if self._thr is not None:
@@ -148,16 +179,20 @@ def build(model_name, dev, precision):
     import rbr_b200
     from rbr_b200 import synth
     c = CFG[model_name]
-    if model_name == "deepconn":
+    if model_name in ("deepconn", "deepconn_infer"):
         params = synth.deepconn_params(c["U"], c["I"], c["V"], c["E"], c["H"], c["K"], c["ks"], seed=0)
         model = rbr_b200.DeepCoNNpp(c["U"], c["I"], c["V"], list(c["ks"]), c["E"], c["H"], c["K"], c["L"], None, 0.5,
                                     precision=precision)
+    elif model_name == "dual_att":
+        params = synth.dual_att_params(c["V"], c["L"], c["lw"], c["lo"], c["go"], c["E"], c["h1"], c["h2"], seed=0)
+        model = rbr_b200.DualAtt(c["V"], c["L"], c["lw"], c["lo"], c["go"], c["E"], c["h1"], c["h2"], 0.5, None, precision=precision)
     else:
         params = synth.narre_params(c["U"], c["I"], c["V"], c["E"], c["H"], c["A"], c["K"], c["ks"], seed=0)
         model = rbr_b200.NARRE(c["U"], c["I"], c["V"], list(c["ks"]), c["H"], c["E"], c["A"], c["K"], c["R"], c["T"], 0.5,
                                0, 0, 0, None, "CNN", precision=precision)
     model.load_state_dict(params)
-    return model.to(dev).train()
+    model = model.to(dev)
+    return model.eval() if model_name == "deepconn_infer" else model.train()
 
 
 def make_batches(model_name, n, rank):
@@ -166,8 +201,10 @@ def make_batches(model_name, n, rank):
     out = []
     for i in range(n):
         seed = synth.SEED_BASE + rank * 1000 + i
-        if model_name == "deepconn":
+        if model_name in ("deepconn", "deepconn_infer"):
             out.append(synth.deepconn_batch(c["B"], c["L"], c["V"], c["U"], c["I"], seed=seed))
+        elif model_name == "dual_att":
+            out.append(synth.dual_att_batch(c["B"], c["L"], c["V"], seed=seed))
         else:
             out.append(synth.narre_batch(c["B"], c["R"], c["T"], c["V"], c["U"], c["I"], seed=seed))
     return out
@@ -175,6 +212,10 @@ def make_batches(model_name, n, rank):
 
 def step(model, batch, ratings, loss_fn, world):
     from rbr_b200 import parallel
+    if not model.training:                # inference scoring (configs[4]): eval forward under no_grad, no collective
+        with torch.no_grad():
+            pred = model(*batch)
+        return pred.sum()
     model.zero_grad(set_to_none=True)
     model.invalidate_operand_cache()      # as after an optimizer step: re-stage the bf16 table shadow + packed weights
     out = model(*batch)
@@ -191,7 +232,9 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=10)
-    ap.add_argument("--model", default="deepconn", choices=["deepconn", "narre"])
+    ap.add_argument("--model", default="deepconn", choices=["deepconn", "narre", "dual_att"])
+    ap.add_argument("--mode", default="train", choices=["train", "infer"],
+                    help="infer = DeepCoNN eval forward at vocab 200k (BASELINE.json configs[4])")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -199,6 +242,8 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
+    if args.mode == "infer":
+        args.model = "deepconn_infer"
 
     import torch.distributed as dist
     import rbr_b200
@@ -230,18 +275,19 @@ def main():
     sampler = ClockSampler(local)
 
     # ------------------------------ device-resident timing (value) ------------------------------
+    sampler.start()
     for i in range(W):
         step(model, *dev_batches[i % NB], loss_fn, world)
     sync_all()
     l0 = lib.rbr_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sampler.start()
+    sampler.mark()
     e0.record()
     for i in range(K):
         loss = step(model, *dev_batches[i % NB], loss_fn, world)
     e1.record()
     sync_all()
-    sampler.stop()
+    value_clock_samples, value_reasons = list(sampler.samples), set(sampler.reasons)
     launches = lib.rbr_launch_count() - l0
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
     if world > 1:
@@ -286,12 +332,14 @@ def main():
 
     e2e_loop(W)
     sync_all()
-    sampler.start()
+    sampler.mark()
     t0 = time.perf_counter()
     e2e_loop(K)
     sync_all()
     t1 = time.perf_counter()
     sampler.stop()
+    sampler.samples = value_clock_samples + sampler.samples
+    sampler.reasons |= value_reasons
     et = torch.tensor([t1 - t0], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(et, op=dist.ReduceOp.MAX)
@@ -300,59 +348,89 @@ def main():
     # ------------------------------ dominant kernel: tcgen05 conv forward, timed alone ------------------------------
     roofline, extras = None, {}
     if rank == 0:
-        we = model.word_embeddings
-        conv = model.ngram.conv
-        table = we.embedding.weight.detach()
-        shadow = we.bf16_shadow()
-        packed = conv.packed(0)
-        w0, b0 = conv.list_of_conv1d[0].weight.detach(), conv.list_of_conv1d[0].bias.detach()
-        if args.model == "deepconn":
-            sides = [(dev_batches[i][0][0], dev_batches[i][0][2]) for i in range(NB)]
-        else:
-            sides = [(dev_batches[i][0][0].view(-1, c["T"]), dev_batches[i][0][2].view(-1, c["T"])) for i in range(NB)]
-        n_tok = sides[0][0].numel()
-        flops = 2.0 * n_tok * c["H"] * c["E"] * 3
-        reps = 20
-        for i in range(3):
-            ops.conv_act_maxpool(table, *sides[i % NB], w0, b0, 1, precision=args.precision, shadow=shadow, packed=packed)
-        torch.cuda.synchronize()
         k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        k0.record()
-        for i in range(reps):
-            ops.conv_act_maxpool(table, *sides[i % NB], w0, b0, 1, precision=args.precision, shadow=shadow, packed=packed)
-        k1.record()
-        torch.cuda.synchronize()
-        kms = k0.elapsed_time(k1) / reps
+
+        def time_kernel(fn, reps=20, warm=3):
+            """CUDA-event time of `fn(i)` (launches on torch's current stream, which is the stream the library uses)."""
+            for i in range(warm):
+                fn(i)
+            torch.cuda.synchronize()
+            k0.record()
+            for i in range(reps):
+                fn(i)
+            k1.record()
+            torch.cuda.synchronize()
+            return k0.elapsed_time(k1) / reps
+
+        we = model.word_embeddings
+        table = we.embedding.weight.detach()
+        shadow = we.bf16_shadow() if args.precision == "bf16" else None
+        if args.model == "dual_att":
+            conv_mod = model.u_local_atten.conv[0]                  # the largest conv of the encoder: E -> 200, k = 1, gated, tanh
+            w0, b0 = conv_mod.weight.detach(), conv_mod.bias.detach()
+            packed = ops.conv_pack(w0)
+            sides = [(dev_batches[i][0][0], None) for i in range(NB)]
+            kname, act, ksz, pad, n_per_step = "local-attention conv E->200 k=1 (gated tanh)", ops.ACT_TANH, 1, 0, 2
+        else:
+            conv = model.ngram.conv
+            packed = conv.packed(0)
+            w0, b0 = conv.list_of_conv1d[0].weight.detach(), conv.list_of_conv1d[0].bias.detach()
+            kname, act, ksz, pad, n_per_step = "gather+conv+bias+ReLU+max-over-time", ops.ACT_RELU, 3, 1, 2
+            if args.model == "narre":
+                sides = [(dev_batches[i][0][0].view(-1, c["T"]), dev_batches[i][0][2].view(-1, c["T"])) for i in range(NB)]
+            else:
+                sides = [(dev_batches[i][0][0], dev_batches[i][0][2]) for i in range(NB)]
+        n_tok = sides[0][0].numel()
+        hh = w0.shape[0]
+        flops = 2.0 * n_tok * hh * c["E"] * ksz
+        kms = time_kernel(lambda i: ops.conv_act_maxpool(table, *sides[i % NB], w0, b0, pad, act=act, precision=args.precision,
+                                                         shadow=shadow, packed=packed))
         achieved = flops / (kms * 1e-3) / 1e12
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "conv_tc_traffic.json")
         if os.path.exists(tpath):
             traffic = json.load(open(tpath)).get(args.model)
-        roofline = {"kernel": "conv_tc_kernel (gather+conv+bias+ReLU+max-over-time, tcgen05)" if args.precision == "bf16"
+        roofline = {"kernel": f"conv_tc2_kernel ({kname}; tcgen05 cta_group::2, TMA gather4 operands)" if args.precision == "bf16"
                     else "conv_fp32_kernel", "bound": "tensor", "achieved": achieved, "peak": peaks["tf"], "unit": "TFLOP/s",
                     "frac": achieved / peaks["tf"], "traffic": traffic, "peak_source": peaks["src"] + ", burst (kernel timed alone)",
-                    "ms_per_launch": kms, "algorithmic_flops_per_launch": flops, "launches_per_step": 2}
+                    "ms_per_launch": kms, "algorithmic_flops_per_launch": flops, "launches_per_step": n_per_step}
         if not args.no_extras:
-            # standalone fp32 gather (K1) against the HBM peak: tokens * (8 + 2*E*4) bytes
-            ids = sides[0][0]
-            g_bytes = n_tok * (8 + 2 * c["E"] * 4)
-            for _ in range(2):
-                out = ops.gather_rows(table, ids)
-            torch.cuda.synchronize()
-            k0.record()
-            for i in range(5):
-                out = ops.gather_rows(table, sides[i % NB][0])
-            k1.record()
-            torch.cuda.synchronize()
-            gms = k0.elapsed_time(k1) / 5
-            del out
-            extras["gather_fp32"] = {"bound": "hbm", "achieved": g_bytes / (gms * 1e-3) / 1e9, "peak": peaks["hbm"], "unit": "GB/s",
-                                     "frac": g_bytes / (gms * 1e-3) / 1e9 / peaks["hbm"], "ms_per_launch": gms}
+            def hbm(bytes_, ms):
+                gbs = bytes_ / (ms * 1e-3) / 1e9
+                return {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm"], "unit": "GB/s", "frac": gbs / peaks["hbm"],
+                        "ms_per_launch": ms, "algorithmic_bytes_per_launch": bytes_}
+            # K1 standalone fp32 gather: tokens * (8 + 2*E*4) bytes (SURVEY §8d)
+            outs = [None]
+            gms = time_kernel(lambda i: outs.__setitem__(0, ops.gather_rows(table, sides[i % NB][0])), reps=5, warm=2)
+            outs[0] = None
+            extras["gather_fp32"] = hbm(n_tok * (8 + 2 * c["E"] * 4), gms)
+            # K0 operand staging: fp32 table -> bf16 shadow (V*E*4 read + V*emb_pad*2 written)
+            if args.precision == "bf16":
+                sms = time_kernel(lambda i: ops.table_to_bf16(table), reps=10, warm=2)
+                extras["table_to_bf16"] = hbm(table.numel() * 4 + shadow.numel() * 2, sms)
+            if args.model in ("deepconn", "deepconn_infer", "narre"):
+                from rbr_b200.layers import fused_head
+                Bn, Hh, Kk = c["B"], c["H"], c["K"]
+                ut, it = torch.randn(Bn, Hh, device=dev), torch.randn(Bn, Hh, device=dev)
+                uid, iid = dev_batches[0][0][4], dev_batches[0][0][5]
+                with torch.no_grad():
+                    hms = time_kernel(lambda i: fused_head(model.user_feat, model.item_feat, model.fm, ut, it, uid, iid, False, None))
+                # K4 head: (2H + 2K + 4)*4 + 16 bytes per sample (SURVEY §8d)
+                extras["head_fwd"] = hbm(Bn * ((2 * Hh + 2 * Kk + 4) * 4 + 16), hms)
+            if args.model == "narre":
+                Bn, R, Hh, A = c["B"], c["R"], c["H"], c["A"]
+                feat = torch.randn(Bn, R, Hh, device=dev)
+                rid = dev_batches[0][0][6]
+                att = model.user_att
+                with torch.no_grad():
+                    ams = time_kernel(lambda i: att(feat, rid))
+                # K3 attention, one side: (R*H + R*A + H + R)*4 + R*8 bytes per sample (SURVEY §8d)
+                extras["narre_attention_fwd"] = hbm(Bn * ((R * Hh + R * A + Hh + R) * 4 + R * 8), ams)
 
     # ------------------------------ CPU baseline on this box's host cores (rank 0, N=1 only) ------------------------------
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu_baseline, _ = cpu_arm(args.model, 128, 5, 1)
+        cpu_baseline, _ = cpu_arm(args.model, 128, 5 if args.model != "dual_att" else 3, 1)
 
     if rank == 0:
         line = {
@@ -361,8 +439,10 @@ def main():
             "dtype": args.precision, "data": "synthetic",
             "config": {"workload": workload_name(args.model), "global_batch": world * c["B"], "parallelism": f"dp{world}",
                        "l2": f"inputs rotate over {NB} distinct batches ({NB * h2d_bytes / 1e6:.0f} MB of ids+masks) on top of "
-                             f"a 60 MB table, 30 MB bf16 shadow and 66 MB gradient buffer per step: larger than the 126 MB L2",
-                       "step": "zero_grad + forward + MSELoss + backward" + (" + gradient all-reduce" if world > 1 else "")},
+                             f"the {c['V'] * c['E'] * 4 / 1e6:.0f} MB table, its bf16 shadow and the dense gradient buffer touched every "
+                             f"step: larger than the 126 MB L2",
+                       "step": ("eval forward under no_grad (scores only)" if args.mode == "infer" else
+                                "zero_grad + forward + MSELoss + backward" + (" + gradient all-reduce" if world > 1 else ""))},
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                     "how": "pinned host buffers → H2D on a copy stream (prefetch depth 1) → nn.Module forward/backward → "
                            "loss read back to pinned host memory every step; wall clock, max over ranks"},
