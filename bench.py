@@ -210,6 +210,9 @@ def make_batches(model_name, n, rank):
     return out
 
 
+GRAD_COMPRESS = None       # --grad-allreduce bf16 sets "bf16" (optional gradient compression; default fp32 like the reference)
+
+
 def step(model, batch, ratings, loss_fn, world):
     from rbr_b200 import parallel
     if not model.training:                # inference scoring (configs[4]): eval forward under no_grad, no collective
@@ -223,7 +226,7 @@ def step(model, batch, ratings, loss_fn, world):
     loss = loss_fn(pred, ratings)
     loss.backward()
     if world > 1:
-        parallel.allreduce_gradients(model)
+        parallel.allreduce_gradients(model, compress=GRAD_COMPRESS)
     return loss
 
 
@@ -237,6 +240,13 @@ def main():
                     help="infer = DeepCoNN eval forward at vocab 200k (BASELINE.json configs[4])")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--grad-allreduce", default="fp32", choices=["fp32", "bf16"],
+                    help="wire dtype of the data-parallel gradient all-reduce (bf16 = optional compression, rounds the averaged gradient)")
+    ap.add_argument("--allreduce", default="nvls", choices=["nvls", "nccl"],
+                    help="nvls = the library's own multimem kernel through the NVSwitch on a symmetric-memory gradient arena "
+                         "(falls back to nccl when multicast is unavailable); nccl = one ncclAllReduce of the arena")
+    ap.add_argument("--overlap", default="off", choices=["off", "on"],
+                    help="start the word-table all-reduce inside backward, overlapping the weight-gradient kernels")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the NARRE / per-kernel extras")
     args = ap.parse_args()
@@ -262,6 +272,14 @@ def main():
 
     model = build(args.model, dev, args.precision)
     parallel.broadcast_parameters(model)
+    global GRAD_COMPRESS
+    GRAD_COMPRESS = "bf16" if args.grad_allreduce == "bf16" else None
+    ar_kind = "nccl"
+    if world > 1 and args.mode == "train" and args.overlap == "on":
+        parallel.enable_overlap(model)
+    elif world > 1 and args.mode == "train" and args.allreduce == "nvls" and args.grad_allreduce == "fp32":
+        ar_kind = ("nvls-multimem (own kernel), word-table slice overlapped with the weight-gradient kernels"
+                   if parallel.enable_nvls_allreduce(model, overlap=True) else "nccl (no NVLS multicast)")      # word-table all-reduce starts inside backward, overlapping the weight-gradient kernels
     NB = 4   # distinct input batches rotated through: 4 x 37 MB of ids+masks > L2 together with table/grad traffic
     host_batches = make_batches(args.model, NB, rank)
     dev_batches = [([t.to(dev) for t in b], r.to(dev)) for b, r in host_batches]
@@ -437,7 +455,7 @@ def main():
             "metric": METRIC[args.model], "value": value, "unit": "samples/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": args.precision, "data": "synthetic",
-            "config": {"workload": workload_name(args.model), "global_batch": world * c["B"], "parallelism": f"dp{world}",
+            "config": {"workload": workload_name(args.model), "global_batch": world * c["B"], "parallelism": f"dp{world}", "grad_allreduce": (f"{args.grad_allreduce} {ar_kind}" + (" overlapped" if args.overlap == "on" else "")) if world > 1 else None,
                        "l2": f"inputs rotate over {NB} distinct batches ({NB * h2d_bytes / 1e6:.0f} MB of ids+masks) on top of "
                              f"the {c['V'] * c['E'] * 4 / 1e6:.0f} MB table, its bf16 shadow and the dense gradient buffer touched every "
                              f"step: larger than the 126 MB L2",

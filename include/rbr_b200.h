@@ -106,6 +106,9 @@ int rbr_conv_act_maxpool_fwd(int precision, int activation, const void* table, c
  *   weight_grad[h,:,j] += g[n,h] * x[n, t*+j-pad, :],  bias_grad[h] += g[n,h],
  *   table_grad[ids[n, t*+j-pad], :] += g[n,h] * W[h,:,j]            (mask true, id != padding_idx)
  * with g = feat_grad * act'(feat), t* = argmax[n,h].
+ * The call may be split: weight_grad == bias_grad == NULL computes only the table (and gate) part, table_grad == NULL
+ * (with gate_grad == NULL) only the weight/bias part — data-parallel training finishes the table gradients of all
+ * document sides first so that their all-reduce overlaps the weight-gradient kernels (parallel.py).
  * gate / gate_grad: as in the forward; gate_grad (same shape as gate, +=) receives d loss / d gate =
  * sum_h g * (preact - bias) / gate, which is why a gated backward also needs `preact` and `bias`
  * (both may be NULL when gate_mode == 0).                                                             */
@@ -178,6 +181,17 @@ int rbr_datt_gate_bwd(const float* table, int64_t vocab, int64_t emb, const int6
                       const float* gate_global_grad, int64_t padding_idx, float* w_local_grad, float* b_local_grad,
                       float* w_global_grad, float* b_global_grad, float* table_grad, void* ws, int64_t ws_bytes,
                       void* stream);
+
+/* ---- K6: data-parallel gradient all-reduce through the NVSwitch (NVLS multimem) ------------------------------
+ * Replaces nn.DataParallel's gradient reduce_add (trainer/train_deepconn_pp.py:129-131) for one-process-per-GPU training:
+ * `multicast_ptr` is the NVLS multicast address of the flat gradient arena (symmetric memory, same offset on every GPU).
+ * Each rank calls this on its own stream; it reduces elements [rank, rank+1) * n/world across ALL GPUs inside the switch
+ * (multimem.ld_reduce, fp32 add), multiplies by `scale` (1/world for the mean) and broadcasts the result to every GPU
+ * (multimem.st).  The caller issues a cross-GPU barrier on the stream before (all gradients written) and after (all
+ * slices broadcast) the call.
+ * max_ctas <= 0 selects the default grid (32 CTAs: link-bound from 16 up, leaves the SMs to concurrent kernels).           */
+int rbr_multimem_allreduce_f32(void* multicast_ptr, int64_t n_floats, int rank, int world, float scale, int max_ctas,
+                               void* stream);
 
 #ifdef __cplusplus
 }

@@ -320,7 +320,10 @@ extern "C" int rbr_conv_act_maxpool_bwd(int precision, int activation, const voi
                                         int64_t feat_ld, int64_t padding_idx, float* weight_grad, float* bias_grad, float* table_grad, float* gate_grad, void* ws,
                                         int64_t ws_bytes, void* stream) {
     RBR_REQUIRE(table && ids && packed && feat && argmax && feat_grad, RBR_EINVAL, "conv_bwd: null pointer");
-    RBR_REQUIRE(weight_grad && bias_grad, RBR_EINVAL, "conv_bwd: null weight/bias grad");
+    RBR_REQUIRE((weight_grad != nullptr) == (bias_grad != nullptr), RBR_EINVAL, "conv_bwd: weight_grad and bias_grad go together");
+    RBR_REQUIRE(weight_grad || table_grad || gate_grad, RBR_EINVAL, "conv_bwd: nothing to compute");
+    const bool do_weight = weight_grad != nullptr;            // NULL weight/bias grads: only the table (+ gate) part
+    const bool do_entries = table_grad != nullptr || gate_grad != nullptr;
     RBR_REQUIRE(gate_mode >= 0 && gate_mode <= 2 && (gate_mode == 0) == (gate == nullptr), RBR_EINVAL, "conv_bwd: gate / gate_mode mismatch");
     RBR_REQUIRE(gate_mode == 0 || (preact && bias), RBR_EINVAL, "conv_bwd: a gated conv backward needs preact and bias");
     RBR_REQUIRE(gate_mode != 1 || ksize == 1, RBR_EUNSUPPORTED, "conv_bwd: per-token gate needs ksize == 1");
@@ -340,8 +343,8 @@ extern "C" int rbr_conv_act_maxpool_bwd(int precision, int activation, const voi
     const bool vec = (emb % 4 == 0) && emb <= 512 && (K == 1 || K == 2 || K == 3 || K == 4 || K == 5 || K == 7);
     const int nq = ((E >> 2) + 31) / 32;
 
-    RBR_CUDA(cudaMemsetAsync(w.dw_hke, 0, (size_t)H * K * epad4 * 4, s));
-    {
+    if (do_weight) RBR_CUDA(cudaMemsetAsync(w.dw_hke, 0, (size_t)H * K * epad4 * 4, s));
+    if (do_entries) {
         int blocks = (int)((ne + 255) / 256);
         if (blocks > 148 * 8) blocks = 148 * 8;
         conv_bwd_entries_kernel<<<blocks, 256, 0, s>>>(ids, mask, n_docs, L, H, K, (int)pad, vocab, padding_idx, feat, argmax,
@@ -350,7 +353,8 @@ extern "C" int rbr_conv_act_maxpool_bwd(int precision, int activation, const voi
         RBR_LAUNCH_CHECK("conv_bwd_entries_kernel");
     }
     // ---- weight + bias gradient
-    if (vec) {
+    if (!do_weight) {
+    } else if (vec) {
         const int dpw = 64;                                    // documents per warp
         const int warps_per_cta = 4;
         const int64_t chunks = (n_docs + dpw - 1) / dpw;
@@ -383,7 +387,7 @@ extern "C" int rbr_conv_act_maxpool_bwd(int precision, int activation, const voi
                                                            gate, gate_mode, w.dw_hke, epad4, bias_grad);
         RBR_LAUNCH_CHECK("conv_bwd_weight_scalar_kernel");
     }
-    {
+    if (do_weight) {
         const int64_t tot = (int64_t)H * E * K;
         int blocks = (int)((tot + 255) / 256);
         if (blocks > 148 * 4) blocks = 148 * 4;

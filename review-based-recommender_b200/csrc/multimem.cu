@@ -1,0 +1,69 @@
+// multimem.cu — data-parallel gradient all-reduce through the NVSwitch (NVLS): one kernel per GPU reduces ITS 1/world
+// slice of the flat gradient arena with multimem.ld_reduce (the switch adds the world's copies in fp32 and returns the
+// sum) and broadcasts the averaged slice to every GPU with multimem.st.  The arena lives in symmetric memory whose
+// multicast address is passed in (torch.distributed._symmetric_memory allocates and maps it; review-based-recommender_b200/
+// parallel.py); the cross-GPU barriers before and after the kernel are issued by the caller on the same stream.
+// Replaces, for the DP gradient exchange, ncclAllReduce + the 1/world scaling pass (the reference's nn.DataParallel
+// reduce_add, trainer/train_deepconn_pp.py:129-131): per-GPU link traffic is N bytes out + N bytes in instead of the
+// ring's 2 * (world-1)/world * N each way through the SMs.
+#include "rbr_common.cuh"
+
+namespace rbr {
+
+__device__ __forceinline__ float4 mm_ld_reduce(const float* p) {
+    float4 v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(p)
+                 : "memory");
+    return v;
+}
+__device__ __forceinline__ void mm_st(float* p, const float4& v, float scale) {
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x * scale), "f"(v.y * scale),
+                 "f"(v.z * scale), "f"(v.w * scale)
+                 : "memory");
+}
+
+// Each thread keeps MM_UNROLL independent 16-byte switch reductions in flight (the round trip through the NVSwitch is a few
+// microseconds; with one request per thread the kernel is latency-, not link-bound), then broadcasts them.
+constexpr int MM_UNROLL = 8;
+__global__ void __launch_bounds__(512) multimem_allreduce_kernel(float* __restrict__ mc, int64_t v4_begin, int64_t v4_end, float scale) {
+    const int64_t tile = (int64_t)blockDim.x * MM_UNROLL;
+    for (int64_t base = v4_begin + (int64_t)blockIdx.x * tile; base < v4_end; base += (int64_t)gridDim.x * tile) {
+        float4 v[MM_UNROLL];
+#pragma unroll
+        for (int u = 0; u < MM_UNROLL; ++u) {
+            const int64_t i = base + (int64_t)u * blockDim.x + threadIdx.x;
+            if (i < v4_end) v[u] = mm_ld_reduce(mc + 4 * i);
+        }
+#pragma unroll
+        for (int u = 0; u < MM_UNROLL; ++u) {
+            const int64_t i = base + (int64_t)u * blockDim.x + threadIdx.x;
+            if (i < v4_end) mm_st(mc + 4 * i, v[u], scale);
+        }
+    }
+}
+
+}  // namespace rbr
+
+using namespace rbr;
+
+extern "C" int rbr_multimem_allreduce_f32(void* multicast_ptr, int64_t n_floats, int rank, int world, float scale, int max_ctas,
+                                          void* stream) {
+    RBR_REQUIRE(multicast_ptr && n_floats >= 0 && world >= 1 && rank >= 0 && rank < world, RBR_EINVAL,
+                "rbr_multimem_allreduce_f32: bad arguments");
+    RBR_REQUIRE(n_floats % 4 == 0 && (uintptr_t)multicast_ptr % 16 == 0, RBR_EINVAL,
+                "rbr_multimem_allreduce_f32: buffer must be 16-byte aligned and a multiple of 4 floats");
+    const int64_t nv = n_floats / 4;
+    const int64_t per = (nv + world - 1) / world;
+    const int64_t b = per * rank, e = (b + per < nv) ? b + per : nv;
+    if (b >= e) return RBR_OK;
+    int64_t blocks = (e - b + 512 * MM_UNROLL - 1) / (512 * MM_UNROLL);
+    // The kernel is bound by the NVLink/NVSwitch rate (~0.4 TB/s per direction measured) from 16 CTAs up, so the default
+    // grid is small: it leaves the SMs to kernels running concurrently (the overlapped word-table reduction).
+    const int64_t cap = max_ctas > 0 ? max_ctas : 32;
+    if (blocks > cap) blocks = cap;
+    multimem_allreduce_kernel<<<(unsigned)blocks, 512, 0, as_stream(stream)>>>(reinterpret_cast<float*>(multicast_ptr), b, e, scale);
+    RBR_LAUNCH_CHECK("multimem_allreduce_kernel");
+    return RBR_OK;
+}

@@ -26,7 +26,7 @@ class DeepCoNNpp(nn.Module):
         self.last_arena = None          # flat gradient buffer of the most recent step (parallel.py all-reduces it)
 
     def _new_arena(self):
-        arena = ops.GradArena(list(self.named_parameters())) if torch.is_grad_enabled() else None
+        arena = ops.GradArena.for_module(self)
         self.last_arena = arena
         self.ngram._arena = arena
         return arena

@@ -87,7 +87,7 @@ class DualAtt(nn.Module):
 
     def forward(self, u_docs, i_docs):
         """u_docs, i_docs: [bz, doc_len] int64 → ratings [bz]."""
-        arena = ops.GradArena(list(self.named_parameters())) if torch.is_grad_enabled() else None
+        arena = ops.GradArena.for_module(self)
         self.last_arena = arena
         u_cat, i_cat = self.encode([u_docs, i_docs], ["u", "i"], arena)
         u_feat = self.fc(u_cat)                                                                   # dual_att.py:49-51

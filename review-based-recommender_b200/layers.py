@@ -111,6 +111,7 @@ class NgramFeat(nn.Module):
         self.dropout = nn.Dropout(p=dropout) if dropout else None       # created but never applied, as in the reference
         self.precision = precision or default_precision()
         self._arena = None
+        self.table_grad_hook = None     # called with the word-table gradient buffer once it is complete (parallel.py)
 
     @property
     def conv(self) -> MyConv1d:
@@ -134,6 +135,7 @@ class NgramFeat(nn.Module):
             "weight_params": [c.weight for c in convs],
             "bias_params": [c.bias for c in convs],
             "padding_idx": -1 if word_embeddings.padding_idx is None else word_embeddings.padding_idx,
+            "table_ready": self.table_grad_hook,
         }
         flat = []
         for ids, m in zip(sides, masks):

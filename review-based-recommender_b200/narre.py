@@ -31,7 +31,7 @@ class NARRE(nn.Module):
         self.last_arena = None
 
     def _new_arena(self):
-        arena = ops.GradArena(list(self.named_parameters())) if torch.is_grad_enabled() else None
+        arena = ops.GradArena.for_module(self)
         self.last_arena = arena
         self.ngram._arena = arena
         self.user_att._arena = arena

@@ -52,24 +52,187 @@ def _arena_covers(model: torch.nn.Module) -> bool:
     return True
 
 
-def allreduce_gradients(model: torch.nn.Module, group=None, average: bool = True) -> int:
-    """Sum (and average) parameter gradients across ranks.  Returns the number of collectives issued:
-    1 when every `.grad` lives in the step's flat arena (the fast path), else one flattened bucket."""
+class _EarlyTableReduce:
+    """State of the overlapped word-table all-reduce of one backward pass (see enable_overlap)."""
+
+    def __init__(self):
+        self.work = None
+        self.tensor: Optional[torch.Tensor] = None
+
+
+def enable_overlap(model: torch.nn.Module, group=None) -> None:
+    """Start the all-reduce of the word-embedding gradient (≈ 90 % of all gradient bytes) as soon as it is complete.
+
+    The encoder's backward (ops.EncodeDocsFn) finishes the table gradient of every document side first and then calls
+    this hook; the collective runs on NCCL's stream while the conv weight/bias-gradient kernels still execute, and
+    allreduce_gradients() later reduces only the remaining (small) gradients and waits for it."""
+    ngram = getattr(model, "ngram", None)
+    if ngram is None or not hasattr(ngram, "table_grad_hook"):
+        return
+    state = _EarlyTableReduce()
+    model._rbr_early_table = state
+
+    def hook(g_table: torch.Tensor):
+        if dist.is_initialized() and dist.get_world_size(group) > 1:
+            state.tensor = g_table
+            state.work = dist.all_reduce(g_table, op=dist.ReduceOp.AVG if dist.get_backend(group) == "nccl" else dist.ReduceOp.SUM,
+                                         group=group, async_op=True)
+
+    ngram.table_grad_hook = hook
+
+
+class _NvlsState:
+    def __init__(self, hdl, mc, n, rank, world, device, overlap):
+        self.hdl, self.mc, self.n, self.rank, self.world = hdl, mc, n, rank, world
+        self.overlap = overlap
+        self.side = torch.cuda.Stream(device=device, priority=-1) if overlap else None
+        self.ev_ready = torch.cuda.Event() if overlap else None
+        self.ev_done = torch.cuda.Event() if overlap else None
+        self.early: Optional[tuple] = None          # (lo, hi) float range already being reduced on the side stream
+
+
+def enable_nvls_allreduce(model: torch.nn.Module, group=None, overlap: bool = True) -> bool:
+    """Put the model's flat gradient arena in symmetric memory (torch.distributed._symmetric_memory) and let
+    allreduce_gradients() reduce it with the library's own NVLS kernel (rbr_multimem_allreduce_f32: multimem.ld_reduce /
+    multimem.st through the NVSwitch, 1/world folded in) instead of ncclAllReduce.  Collective call (every rank, after
+    init and before the first training step).  Returns False — and leaves the NCCL path in place — when the GPUs have
+    no NVLS multicast support.
+
+    overlap=True: the word-embedding gradient (≈ 90 % of the bytes) is reduced on a side stream from inside backward,
+    as soon as the table gradients of all document sides are complete (ops.EncodeDocsFn runs them first), concurrently
+    with the conv weight-gradient kernels: the reduction kernel is link-bound with 32 CTAs, so it takes few SMs."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1 or dist.get_backend(group) != "nccl":
+        return False
+    from .ops import GradArena
+    was = torch.is_grad_enabled()
+    torch.set_grad_enabled(True)
+    try:
+        layout = GradArena.for_module(model)
+    finally:
+        torch.set_grad_enabled(was)
+    if layout is None or layout.total == 0:
+        return False
+    try:
+        import torch.distributed._symmetric_memory as symm_mem
+        pg = group if group is not None else dist.group.WORLD
+        dev = next(model.parameters()).device
+        n = (layout.total + 1023) // 1024 * 1024
+        buf = symm_mem.empty(n, dtype=torch.float32, device=dev)
+        hdl = symm_mem.rendezvous(buf, pg)
+        mc = int(getattr(hdl, "multicast_ptr", 0) or 0)
+        ok = torch.tensor([1 if mc else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if int(ok.item()) == 0:
+            return False
+    except Exception:
+        return False
+    ngram = getattr(model, "ngram", None)
+    overlap = bool(overlap and ngram is not None and hasattr(ngram, "table_grad_hook"))
+    st = _NvlsState(hdl, mc, n, dist.get_rank(group), dist.get_world_size(group), dev, overlap)
+    model.__dict__["_rbr_arena_buffer"] = buf
+    model.__dict__["_rbr_nvls"] = st
+    if overlap:
+        from ._lib import lib
+
+        def hook(g_table: torch.Tensor):
+            lo = (g_table.data_ptr() - buf.data_ptr()) // 4
+            cnt = g_table.numel() // 4 * 4
+            if lo < 0 or lo + cnt > n or lo % 4 or cnt == 0:
+                return
+            main = torch.cuda.current_stream()
+            st.ev_ready.record(main)
+            with torch.cuda.stream(st.side):
+                st.side.wait_event(st.ev_ready)
+                hdl.barrier(channel=2)          # every rank's table gradient is complete
+                lib.check(lib.rbr_multimem_allreduce_f32(mc + 4 * lo, cnt, st.rank, st.world, 1.0 / st.world, 0,
+                                                         st.side.cuda_stream), "rbr_multimem_allreduce_f32")
+                hdl.barrier(channel=3)
+                st.ev_done.record(st.side)
+            st.early = (lo, lo + cnt)
+
+        ngram.table_grad_hook = hook
+    return True
+
+
+def _nvls_allreduce(model: torch.nn.Module, flat: torch.Tensor, average: bool) -> bool:
+    st = model.__dict__.get("_rbr_nvls")
+    buf = model.__dict__.get("_rbr_arena_buffer")
+    if st is None or buf is None or flat.data_ptr() != buf.data_ptr():
+        return False
+    from ._lib import lib
+    main = torch.cuda.current_stream()
+    scale = (1.0 / st.world) if average else 1.0
+    ranges = [(0, st.n)]
+    if st.early is not None:
+        lo, hi = st.early
+        ranges = [r for r in ((0, lo), (hi, st.n)) if r[1] > r[0]]
+    st.hdl.barrier(channel=0)                   # every rank has finished writing its gradients (stream-ordered, device side)
+    for lo, hi in ranges:
+        lib.check(lib.rbr_multimem_allreduce_f32(st.mc + 4 * lo, hi - lo, st.rank, st.world, scale, 0, main.cuda_stream),
+                  "rbr_multimem_allreduce_f32")
+    st.hdl.barrier(channel=1)                   # every slice has been broadcast before anyone reads the result
+    if st.early is not None:
+        main.wait_event(st.ev_done)             # the overlapped word-table reduction
+        st.early = None
+    return True
+
+
+def allreduce_gradients(model: torch.nn.Module, group=None, average: bool = True, compress: Optional[str] = None) -> int:
+    """Sum (and average) parameter gradients across ranks.  Returns the number of collectives issued after backward:
+    1 when every `.grad` lives in the step's flat arena (the fast path), else one flattened bucket.  With
+    enable_overlap(model) the word-table gradient was already started from inside backward and is excluded here."""
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
         return 0
     world = dist.get_world_size(group)
+    nccl = dist.get_backend(group) == "nccl"
+    op = dist.ReduceOp.AVG if (average and nccl) else dist.ReduceOp.SUM       # NCCL averages in the collective itself
+    post_scale = average and not nccl
+    early = getattr(model, "_rbr_early_table", None)
+    if compress not in (None, "bf16"):
+        raise ValueError("compress must be None or 'bf16'")
     if _arena_covers(model):
         flat = model.last_arena.flat
-        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
-        if average:
-            flat.mul_(1.0 / world)
-        return 1
-    grads = [p.grad for p in model.parameters() if p.requires_grad and p.grad is not None]
+        if (early is None or early.work is None) and compress is None and _nvls_allreduce(model, flat, average):
+            return 1
+        if compress == "bf16" and nccl and (early is None or early.work is None):
+            # optional gradient compression: halves the bytes on the wire; the averaged gradient is rounded to bf16
+            # (relative error 2^-9 per element) — off by default, the reference's DataParallel reduces in fp32
+            half = flat.to(torch.bfloat16)
+            dist.all_reduce(half, op=op, group=group)
+            flat.copy_(half)
+            return 1
+        pieces = [flat]
+        if early is not None and early.work is not None and early.tensor is not None:
+            lo = (early.tensor.data_ptr() - flat.data_ptr()) // 4
+            hi = lo + early.tensor.numel()
+            pieces = [t for t in (flat[:lo], flat[hi:]) if t.numel() > 0]
+        n = 0
+        for t in pieces:
+            dist.all_reduce(t, op=op, group=group)
+            if post_scale:
+                t.mul_(1.0 / world)
+            n += 1
+        if early is not None and early.work is not None:
+            early.work.wait()
+            if average and not nccl:
+                early.tensor.mul_(1.0 / world)
+            early.work, early.tensor = None, None
+        return n
+    if early is not None and early.work is not None:          # mixed case: finish the early one, then the bucket below re-reduces nothing twice
+        early.work.wait()
+        done = early.tensor
+        if average and not nccl:
+            done.mul_(1.0 / world)
+        early.work, early.tensor = None, None
+    else:
+        done = None
+    grads = [p.grad for p in model.parameters() if p.requires_grad and p.grad is not None
+             and not (done is not None and p.grad.data_ptr() == done.data_ptr())]
     if not grads:
         return 0
     flat = torch.cat([g.reshape(-1) for g in grads])
-    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
-    if average:
+    dist.all_reduce(flat, op=op, group=group)
+    if post_scale:
         flat.mul_(1.0 / world)
     off = 0
     for g in grads:

@@ -115,6 +115,20 @@ ref = torch.nn.Linear(6, 3); ref.load_state_dict(model.state_dict())
 torch.nn.functional.mse_loss(ref(x), y).backward()
 assert torch.allclose(model.weight.grad, ref.weight.grad, atol=1e-6), (model.weight.grad, ref.weight.grad)
 assert torch.allclose(model.bias.grad, ref.bias.grad, atol=1e-6)
+# overlapped path: the (large) first gradient is reduced from a hook fired inside backward, the rest afterwards
+import types
+model.ngram = types.SimpleNamespace(table_grad_hook=None)
+parallel.enable_overlap(model)
+arena2 = GradArena(list(model.named_parameters()))
+model.weight.grad = arena2.view(model.weight); model.weight.grad.copy_(gw)
+model.bias.grad = arena2.view(model.bias); model.bias.grad.copy_(gb)
+model.last_arena = arena2
+model.ngram.table_grad_hook(model.weight.grad)            # what ops.EncodeDocsFn.backward does once the table gradient is complete
+n = parallel.allreduce_gradients(model)
+assert n == 1                                             # only the remainder is reduced after backward
+assert torch.allclose(model.weight.grad, ref.weight.grad, atol=1e-6)
+assert torch.allclose(model.bias.grad, ref.bias.grad, atol=1e-6)
+del model.ngram, model._rbr_early_table
 # slow path: grads not in the arena
 model.last_arena = None
 model.weight.grad = gw.clone(); model.bias.grad = gb.clone()

@@ -214,3 +214,20 @@ def test_oob_ids_are_counted_not_fatal():
     out = ops.gather_rows(table, ids)
     assert float(out[0, 2].abs().max()) == 0.0 and float(out[0, 3].abs().max()) == 0.0
     assert lib.rbr_consume_oob_count(None) == 2
+
+
+def test_two_pass_backward_with_table_hook_matches_single_pass():
+    """Data-parallel overlap splits the encoder backward (table gradients of all sides first, hook, then weight
+    gradients): same gradients as the single pass, and the hook sees the complete table gradient."""
+    g = Golden("deepconn_small")
+    seen = {}
+    grads = []
+    for use_hook in (False, True):
+        model = build_model(g, "fp32")
+        if use_hook:
+            model.ngram.table_grad_hook = lambda t: seen.setdefault("table", t.detach().clone())
+        _, _, gr = run_step(model, g.batch, g.ratings)
+        grads.append(gr)
+    for k in grads[0]:
+        assert rel_err(grads[1][k], grads[0][k]) < 1e-6, k
+    assert rel_err(seen["table"].cpu(), g.grads["word_embeddings.embedding.weight"]) < FP32_GRAD_TOL
