@@ -113,6 +113,12 @@ int rbr_conv_act_maxpool_fwd(int precision, int activation, const void* table, c
  * sum_h g * (preact - bias) / gate, which is why a gated backward also needs `preact` and `bias`
  * (both may be NULL when gate_mode == 0).                                                             */
 int64_t rbr_conv_bwd_workspace_bytes(int64_t n_docs, int64_t filters, int64_t ksize, int64_t emb, int64_t vocab);
+/* Backward formulation for SHORT documents (doc_len <= 128, filters <= 160, no gate; NARRE's 60-token reviews): one
+ * per-document kernel (embedding dim sliced, weight slice in shared memory, dW slice in registers, dX per document in shared
+ * memory) instead of entries + token sort + weight + table kernels.  0 = never (default: it is instruction-bound and
+ * currently 2x slower than the generic kernels, see conv_bwd.cu), 1 = when the batch has >= 64 documents, 2 = whenever
+ * the shape allows.  Returns the previous mode.  Both formulations compute the same gradients (tests run both).          */
+int rbr_set_conv_bwd_short(int mode);
 int rbr_conv_act_maxpool_bwd(int precision, int activation, const void* table, const void* shadow_bf16,
                              int64_t vocab, int64_t emb, const int64_t* ids, const uint8_t* mask,
                              const float* gate, int gate_mode, int64_t n_docs, int64_t doc_len,

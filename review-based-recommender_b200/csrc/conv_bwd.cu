@@ -12,10 +12,20 @@
 // The table gradient is a warp-segmented scatter-add: entries are counting-sorted by token id
 // (token_sort.cuh) and each warp reduces a chunk of same-token entries in registers before one vector
 // atomic per (chunk, token) — no [N,L,E] gradient tensor ever exists.
+#include <stdlib.h>
+
 #include "rbr_common.cuh"
 #include "token_sort.cuh"
 
 namespace rbr {
+
+// conv_bwd_short.cu: per-document formulation for short documents (weight + bias + table gradient in one kernel)
+bool conv_bwd_short_ok(int E, int H, int K, int L, int gate_mode, int64_t vocab);
+int conv_bwd_short_dispatch(bool bf16, const float* table, const __nv_bfloat16* shadow, int emb_pad, int64_t vocab, int E,
+                            const int64_t* ids, const uint8_t* mask, int64_t n_docs, int L, int H, int K, int pad,
+                            int64_t padding_idx, const float* feat, const int32_t* argmax, const float* feat_grad, int feat_ld,
+                            int act, const float* whke, int epad4, int do_weight, int do_table, float* dw_hke, float* bias_grad,
+                            float* table_grad, cudaStream_t s);
 
 // ---- entries: key (token id or -1) and coefficient per (doc, filter, tap) ------------------------------
 __global__ void __launch_bounds__(256) conv_bwd_entries_kernel(
@@ -293,6 +303,18 @@ static ConvBwdWs conv_bwd_ws(void* base, int64_t n_docs, int64_t H, int64_t K, i
     return w;
 }
 
+// 0 = generic kernels only (default), 1 = per-document kernel for short documents when the batch has >= 64 documents,
+// 2 = per-document kernel whenever the shape allows.  Initial value from RBR_BWD_SHORT.  Round-1 measurement (NARRE side,
+// 40 960 docs x 60, H=150): per-document kernel 4.0 ms vs 2.0 ms for entries + sort + weight + table — it removes the L2
+// traffic (6.5 GB → 0.26 GB) but executes 2.1 G warp instructions (2 FMAs per ~6 issued with 64-wide slices), so it stays off.
+static int g_bwd_short = -1;
+extern "C" int rbr_set_conv_bwd_short(int mode) {
+    RBR_REQUIRE(mode >= 0 && mode <= 2, RBR_EINVAL, "rbr_set_conv_bwd_short: mode must be 0, 1 or 2");
+    const int prev = g_bwd_short < 0 ? 0 : g_bwd_short;
+    g_bwd_short = mode;
+    return prev;
+}
+
 extern "C" int64_t rbr_conv_bwd_workspace_bytes(int64_t n_docs, int64_t filters, int64_t ksize, int64_t emb, int64_t vocab) {
     return conv_bwd_ws(nullptr, n_docs, filters, ksize, emb, vocab).total;
 }
@@ -344,6 +366,28 @@ extern "C" int rbr_conv_act_maxpool_bwd(int precision, int activation, const voi
     const int nq = ((E >> 2) + 31) / 32;
 
     if (do_weight) RBR_CUDA(cudaMemsetAsync(w.dw_hke, 0, (size_t)H * K * epad4 * 4, s));
+    // short documents (NARRE's 60-token reviews): the per-document kernel does weight, bias and table gradient in one pass
+    if (g_bwd_short < 0) {
+        const char* e_ = getenv("RBR_BWD_SHORT");
+        g_bwd_short = (e_ && e_[0] >= '0' && e_[0] <= '2') ? e_[0] - '0' : 0;
+    }
+    if (g_bwd_short != 0 && vec && !gate_grad && conv_bwd_short_ok(E, H, K, L, gate_mode, vocab) && (n_docs >= 64 || g_bwd_short == 2) &&
+        (!table_grad || (uintptr_t)table_grad % 16 == 0)) {
+        const int rc = conv_bwd_short_dispatch(precision == RBR_PREC_BF16, reinterpret_cast<const float*>(table),
+                                               reinterpret_cast<const __nv_bfloat16*>(shadow_bf16), (int)rbr_emb_pad(emb), vocab, E, ids,
+                                               mask, n_docs, L, H, K, (int)pad, padding_idx, feat, argmax, feat_grad, (int)feat_ld,
+                                               activation, whke, epad4, do_weight ? 1 : 0, table_grad ? 1 : 0, w.dw_hke, bias_grad,
+                                               table_grad, s);
+        if (rc != RBR_OK) return rc;
+        if (do_weight) {
+            const int64_t tot = (int64_t)H * E * K;
+            int blocks = (int)((tot + 255) / 256);
+            if (blocks > 148 * 4) blocks = 148 * 4;
+            conv_bwd_unpack_kernel<<<blocks, 256, 0, s>>>(w.dw_hke, H, E, K, epad4, weight_grad);
+            RBR_LAUNCH_CHECK("conv_bwd_unpack_kernel");
+        }
+        return RBR_OK;
+    }
     if (do_entries) {
         int blocks = (int)((ne + 255) / 256);
         if (blocks > 148 * 8) blocks = 148 * 8;
