@@ -33,7 +33,6 @@ constexpr int T2_M = 128;                  // positions per CTA tile (UMMA M = 2
 // Warp roles: [0, EW) epilogue, [EW, EW+4) TMA producers (TMA issue is serialised per warp), EW+4 = TMEM owner + MMA issuer.
 constexpr int T2_PROD_WARPS = 4;
 constexpr int t2_threads(int ew) { return (ew + T2_PROD_WARPS + 1) * 32; }
-constexpr int T2_MAX_SLOTS = 6;            // documents packed into one tile (short-document mode)
 constexpr int T2_MIN_STAGES = 3;
 
 struct Tc2Plan {
@@ -49,7 +48,7 @@ struct Tc2Plan {
     int nst;          // ring stages
     int w_bytes;      // resident weights per CTA = K * C * NL * 16
     int mode_b, D, tpu;
-    int S;            // mode B: tile rows between consecutive documents (Lext, or Lext rounded up to 32 when that packs as many)
+    int S;            // mode B: tile rows between consecutive documents = Lext rounded up to 32 (one document per epilogue warp row block)
     int64_t n_units;
     int tmem_cols, acc_stride;
     int off_ring, off_w, off_bias, off_keys, off_bars, off_slot, smem_bytes;   // offsets from the 1024-aligned base
@@ -157,7 +156,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const Tc2Args a) {
         fence_barrier_init();
     }
     for (int i = threadIdx.x; i < p.Nb; i += blockDim.x) bias_s[i] = (h0 + i < p.H) ? a.bias[h0 + i] : 0.f;
-    for (int i = threadIdx.x; i < 2 * p.D * p.Nb; i += blockDim.x) keys_s[i] = 0ull;
+    for (int i = threadIdx.x; i < 2 * 4 * p.Nb; i += blockDim.x) keys_s[i] = 0ull;
     if (warp == T2_MMA_WARP) tmem_alloc2(smem_u32((const void*)tmem_slot), (uint32_t)p.tmem_cols);
     if (warp == T2_PROD_WARP0 && lane == 0) tma_prefetch_desc(&tmap);
     tc_fence_before();
@@ -317,18 +316,19 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const Tc2Args a) {
             const int64_t unit = ci + (g / p.tpu) * ctas_per_pass;
             const int tt = (int)(g % p.tpu);
             const int buf = (int)(g & 1);
-            // pooled keys are double buffered by unit parity: ONE named barrier per unit (the buffer is next written two units later,
-            // i.e. after the following unit's barrier, which every thread passes only once it has finalised this unit)
-            unsigned long long* keys_u = keys_s + ((g / p.tpu) & 1) * (p.D * p.Nb);
-            int slot, t;
-            if (p.mode_b) { slot = m / p.S; t = m - slot * p.S; } else { slot = 0; t = tt * T2_M + m; }
+            // Pooled keys (value, ~position) live in shared memory per TMEM lane quadrant: entry [quad][column] is owned by exactly
+            // one warp (quad = warp & 3, column chunk by share), so the running max over the tiles of a document is a plain
+            // read-modify-write — no atomics (a 64-bit shared atomicMax is a CAS loop, and four quadrants contended for every
+            // column).  Double buffered by unit parity: ONE named barrier per unit (the buffer is next written two units
+            // later, i.e. after the following unit's barrier, which every thread passes only once it has finalised this unit).
+            unsigned long long* keys_u = keys_s + ((g / p.tpu) & 1) * (4 * p.Nb);
+            // mode B packs documents on 32-row (warp) boundaries: a warp's rows all belong to one document slot
+            const int slot = p.mode_b ? (quad * 32) / p.S : 0;
+            const int t = p.mode_b ? m - slot * p.S : tt * T2_M + m;
             const int64_t my_doc = p.mode_b ? unit * p.D + slot : unit;
             const bool valid = (t < p.Lout) && (slot < p.D) && (unit < p.n_units) && (my_doc < a.n_docs);
             float row_gate = 1.f;
             if (a.gate_mode == 1 && valid) row_gate = a.gate[my_doc * p.L + t];
-            const int slot_lo = p.mode_b ? (quad * 32) / p.S : 0;
-            int slot_hi = p.mode_b ? (quad * 32 + 31) / p.S : 0;
-            if (slot_hi >= p.D) slot_hi = p.D - 1;
 
             mbar_wait(bar_accf + 8 * buf, (uint32_t)((g >> 1) & 1));
             tc_fence_after();
@@ -347,17 +347,17 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const Tc2Args a) {
 #pragma unroll
                     for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * row_gate);
                 }
-                for (int sl = slot_lo; sl <= slot_hi && !(p.dbg & 2); ++sl) {
-                    const bool mine = valid && slot == sl;
+                if (!(p.dbg & 2)) {
                     uint32_t keep_v = 0, keep_b = 0;
-                    if (__all_sync(0xffffffffu, mine)) tc_colmax<true>(v, true, lane, keep_v, keep_b);
-                    else tc_colmax<false>(v, mine, lane, keep_v, keep_b);
+                    if (__all_sync(0xffffffffu, valid)) tc_colmax<true>(v, true, lane, keep_v, keep_b);
+                    else tc_colmax<false>(v, valid, lane, keep_v, keep_b);
                     if (lane < 16 && keep_b) {
-                        const int first = __ffs(keep_b) - 1;
-                        const int tf = p.mode_b ? (quad * 32 + first - sl * p.S) : (tt * T2_M + quad * 32 + first);
+                        const int first = __ffs(keep_b) - 1;              // first (smallest-position) row attaining the max
+                        const int tf = p.mode_b ? (quad * 32 + first - slot * p.S) : (tt * T2_M + quad * 32 + first);
                         const unsigned long long key =
                             ((unsigned long long)f2ord(keep_v) << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)tf);
-                        atomicMax(keys_u + sl * p.Nb + c0 + lane, key);
+                        unsigned long long* kp = keys_u + quad * p.Nb + c0 + lane;
+                        if (key > *kp) *kp = key;
                     }
                 }
             }
@@ -368,11 +368,16 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const Tc2Args a) {
             }
             if (tt == p.tpu - 1) {
                 asm volatile("bar.sync 1, %0;" ::"n"(T2_EPI_THREADS) : "memory");
+                const int qps = p.mode_b ? p.S / 32 : 4;      // quadrants per document slot
                 for (int o = threadIdx.x; o < p.D * p.Nb; o += T2_EPI_THREADS) {
                     const int sl = o / p.Nb, c = o - sl * p.Nb;
                     const int64_t doc = p.mode_b ? unit * p.D + sl : unit;
-                    const unsigned long long key = keys_u[o];
-                    keys_u[o] = 0ull;
+                    unsigned long long key = 0ull;
+                    for (int q = sl * qps; q < sl * qps + qps && q < 4; ++q) {
+                        const unsigned long long k2 = keys_u[q * p.Nb + c];
+                        keys_u[q * p.Nb + c] = 0ull;
+                        key = k2 > key ? k2 : key;
+                    }
                     if (unit < p.n_units && doc < a.n_docs && h0 + c < p.H) {
                         const float raw_v = __uint_as_float(ord2f((uint32_t)(key >> 32)));
                         const int tbest = (int)(0xFFFFFFFFu - (uint32_t)key);
@@ -410,17 +415,12 @@ static bool tc2_make_plan(int E, int H, int K, int L, int pad, int act, int64_t 
     p.stage_tx = p.groups * 512;
     p.stage_bytes = t2_stage_bytes(K);
     p.w_bytes = K * p.C * p.NL * 16;
-    p.S = p.Lext;
-    if (p.Lext * 2 <= T2_M + K - 1) {
+    // short documents: several per tile, each starting on a 32-row (epilogue-warp) boundary
+    p.S = (int)round_up(p.Lext, 32);
+    if (p.S + p.Lext <= T2_M + K - 1) {
         p.mode_b = 1;
-        p.D = (T2_M + K - 1) / p.Lext;
-        int dmax = 4096 / (p.Nb * 8);
-        if (dmax > T2_MAX_SLOTS) dmax = T2_MAX_SLOTS;
-        if (dmax < 1) dmax = 1;
-        if (p.D > dmax) p.D = dmax;
-        // documents aligned to 32-row (epilogue-warp) boundaries when that packs as many per tile: no warp straddles two docs
-        const int s32 = (int)round_up(p.Lext, 32);
-        if ((T2_M + K - 1 - p.Lext) / s32 + 1 >= p.D) p.S = s32;
+        p.D = (T2_M + K - 1 - p.Lext) / p.S + 1;
+        if (p.D > 4) p.D = 4;
         p.tpu = 1;
         p.n_units = (n_docs + p.D - 1) / p.D;
     } else {
@@ -433,7 +433,7 @@ static bool tc2_make_plan(int E, int H, int K, int L, int pad, int act, int64_t 
         for (int j = 0; j < 8; ++j) p.boff[ks * 8 + j] = (uint32_t)(ks * 2 * p.NL + j * p.C * p.NL);   // K-step = 2 chunk columns, tap = C
     p.acc_stride = p.Nb <= 128 ? 128 : 256;
     p.tmem_cols = 2 * p.acc_stride;
-    const int tail = p.Nb * 4 + 8 + 2 * p.D * p.Nb * 8 + 8 * (2 * 16 + 5) + 16;
+    const int tail = p.Nb * 4 + 8 + 2 * 4 * p.Nb * 8 + 8 * (2 * 16 + 5) + 16;
     int nst = (T2_SMEM_MAX - 1024 - p.w_bytes - tail - 256) / p.stage_bytes;
     if (nst > 16) nst = 16;
     if (nst < T2_MIN_STAGES) return false;
@@ -444,7 +444,7 @@ static bool tc2_make_plan(int E, int H, int K, int L, int pad, int act, int64_t 
     off = (off + 15) / 16 * 16;
     p.off_bias = off; off += p.Nb * 4;
     off = (off + 7) / 8 * 8;
-    p.off_keys = off; off += 2 * p.D * p.Nb * 8;
+    p.off_keys = off; off += 2 * 4 * p.Nb * 8;
     p.off_bars = off; off += 8 * (2 * nst + 5);
     p.off_slot = off; off += 16;
     p.smem_bytes = off + 1024;                   // slack for the manual 1024-byte alignment of the base

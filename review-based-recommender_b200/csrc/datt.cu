@@ -60,7 +60,7 @@ __global__ void datt_transpose_kernel(const float* __restrict__ w, int E, int Ep
 }
 
 // one CTA per document: warp w takes tokens w, w+8, ...; lane c owns elements 4c..4c+3 of the row
-template <bool V4>
+template <bool V4, int WIN>
 __global__ void __launch_bounds__(DA_WARPS * 32) datt_gate_fwd_kernel(
     const float* __restrict__ table, int64_t vocab, int E, const int64_t* __restrict__ ids, int L, const float* __restrict__ waT,
     const float* __restrict__ b_local, int win, const float* __restrict__ wgT, const float* __restrict__ b_global,
@@ -76,6 +76,10 @@ __global__ void __launch_bounds__(DA_WARPS * 32) datt_gate_fwd_kernel(
     for (int i = threadIdx.x; i < win * Ep; i += blockDim.x) wa_s[i] = waT[i];
     __syncthreads();
     float gacc = 0.f;
+    // The `win` window dot products of a token are reduced TOGETHER: a transposed butterfly (8 values → 4 → 2 → 1 per lane
+    // over the xor-16/8/4 steps, then two plain steps) needs 9 shuffles instead of 5 per value; afterwards the lane whose
+    // bits (4,3,2) spell j holds d_j.  (The kernel was issue-bound: 242 warp instructions per token, mostly reductions.)
+    const int my_j = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
     for (int t = wib; t < L; t += DA_WARPS) {
         const int64_t id = ids[n * L + t];
         float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -83,11 +87,30 @@ __global__ void __launch_bounds__(DA_WARPS * 32) datt_gate_fwd_kernel(
         if (!ok && lane == 0) note_oob();
         if (ok) x = ld_row4<V4>(table + id * E, E, lane);
         if (lane < e4) gacc += dot4(x, __ldg(reinterpret_cast<const float4*>(wgT + (int64_t)t * Ep) + lane));
-        for (int j = 0; j < win; ++j) {
-            float d = (lane < e4) ? dot4(x, *reinterpret_cast<const float4*>(wa_s + j * Ep + lane * 4)) : 0.f;
-            d = warp_sum(d);
-            if (lane == 0) dloc[j * L + t] = d;
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            v[j] = (j < WIN && lane < e4) ? dot4(x, *reinterpret_cast<const float4*>(wa_s + j * Ep + lane * 4)) : 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {                                  // xor 16: 8 → 4 values
+            const bool up = lane & 16;
+            const float keep = up ? v[i + 4] : v[i], send = up ? v[i] : v[i + 4];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
         }
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {                                  // xor 8: 4 → 2
+            const bool up = lane & 8;
+            const float keep = up ? v[i + 2] : v[i], send = up ? v[i] : v[i + 2];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+        }
+        {                                                              // xor 4: 2 → 1
+            const bool up = lane & 4;
+            const float keep = up ? v[1] : v[0], send = up ? v[0] : v[1];
+            v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+        }
+        v[0] += __shfl_xor_sync(0xffffffffu, v[0], 2);
+        v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+        if ((lane & 3) == 0 && my_j < WIN) dloc[my_j * L + t] = v[0];
     }
     gacc = warp_sum(gacc);
     if (lane == 0) gpart[wib] = gacc;
@@ -320,7 +343,12 @@ extern "C" int rbr_datt_gate_fwd(const float* table, int64_t vocab, int64_t emb,
     RBR_LAUNCH_CHECK("datt_transpose(global)");
     const size_t smem = ((size_t)((win * L + 3) & ~3) + (size_t)win * Ep + DA_WARPS) * 4;
     RBR_REQUIRE(smem <= 200 * 1024, RBR_EUNSUPPORTED, "rbr_datt_gate_fwd: doc_len too large for shared memory");
-    auto kern = (E % 4 == 0) ? datt_gate_fwd_kernel<true> : datt_gate_fwd_kernel<false>;
+    void (*kern)(const float*, int64_t, int, const int64_t*, int, const float*, const float*, int, const float*, const float*, float*,
+                 float*) = nullptr;
+#define RBR_GF(W_) case W_: kern = (E % 4 == 0) ? datt_gate_fwd_kernel<true, W_> : datt_gate_fwd_kernel<false, W_>; break;
+    switch (win) { RBR_GF(1) RBR_GF(3) RBR_GF(5) RBR_GF(7) }
+#undef RBR_GF
+    RBR_REQUIRE(kern != nullptr, RBR_EUNSUPPORTED, "rbr_datt_gate_fwd: window must be 1, 3, 5 or 7");
     RBR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<(unsigned)n_docs, DA_WARPS * 32, smem, s>>>(table, vocab, E, ids, L, w.waT, b_local, win, w.wgT, b_global, gate_local,
                                                        gate_global);

@@ -9,7 +9,7 @@ prec = sys.argv[1] if len(sys.argv) > 1 else "bf16"
 n_docs = int(sys.argv[2]) if len(sys.argv) > 2 else 4096
 L = int(sys.argv[3]) if len(sys.argv) > 3 else 500
 H = int(sys.argv[4]) if len(sys.argv) > 4 else 100
-V, E = 50000, 300
+V, E = 50000, int(os.environ.get("RBR_PROF_E", "300"))
 k = int(sys.argv[5]) if len(sys.argv) > 5 else 3
 p = synth.deepconn_params(10, 10, V, E, H, 32, (k,), seed=0)
 table = p["word_embeddings.embedding.weight"].cuda()
