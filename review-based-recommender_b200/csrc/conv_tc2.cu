@@ -29,7 +29,8 @@ constexpr int T2_SMEM_MAX = 232448;        // 227 KB opt-in dynamic shared memor
 constexpr int T2_M = 128;                  // positions per CTA tile (UMMA M = 256 over the pair)
 // Epilogue warps EW (template parameter of the kernel): 8 or 16 = 2 or 4 per TMEM lane quadrant, each reducing a share of
 // the 16-column chunks.  The max-reduction is a chain of fixed-latency warp ops: 16 warps hide it when there is a lot of it
-// per tile (many filter chunks, or short documents = per-tile finalisation), 8 leave more issue slots to the MMA warp.
+// per tile relative to the MMA/gather work (many filter chunks, short documents = per-tile finalisation, or a narrow
+// embedding = few K blocks per tile), 8 leave more issue slots to the MMA warp.
 // Warp roles: [0, EW) epilogue, [EW, EW+4) TMA producers (TMA issue is serialised per warp), EW+4 = TMEM owner + MMA issuer.
 constexpr int T2_PROD_WARPS = 4;
 constexpr int t2_threads(int ew) { return (ew + T2_PROD_WARPS + 1) * 32; }
@@ -532,7 +533,7 @@ int conv_tc2_dispatch(const __nv_bfloat16* shadow, int64_t vocab, int E, const i
     a.vocab = vocab; a.ids = ids; a.mask = mask; a.n_docs = n_docs; a.wpack = umma_w2; a.bias = bias;
     a.feat = feat; a.argmax = argmax; a.preact = preact; a.gate = gate; a.gate_mode = gate_mode; a.feat_ld = feat_ld;
     static const char* ew_env = getenv("RBR_TC2_EPI_WARPS");                    // timing experiments: force 8 or 16
-    const bool wide = ew_env ? atoi(ew_env) == 16 : (a.p.mode_b || a.p.Nb / 16 >= 9);
+    const bool wide = ew_env ? atoi(ew_env) == 16 : (a.p.mode_b || a.p.Nb / 16 >= 9 || a.p.nkb <= 2);
 #define RBR_T2(KT_) return wide ? tc2_launch<KT_, 16>(tm, a, s) : tc2_launch<KT_, 8>(tm, a, s)
     switch (K) {
         case 1: RBR_T2(1);
