@@ -536,9 +536,12 @@ int conv_tc2_dispatch(const __nv_bfloat16* shadow, int64_t vocab, int E, const i
     cuuint64_t gstr[1] = {(cuuint64_t)emb_pad * 2};
     cuuint32_t box[2] = {64, 1};
     cuuint32_t estr[2] = {1, 1};
+    static const char* promo_env = getenv("RBR_TMA_PROMO");           // tuning knob: 0 none, 1 64B, 2 128B, 3 256B (default)
+    const int promo = promo_env ? atoi(promo_env) : 3;
+    const CUtensorMapL2promotion l2p = promo == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : promo == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+                                       : promo == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
     const CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(shadow), gdim, gstr, box, estr,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, l2p, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     RBR_REQUIRE(r == CUDA_SUCCESS, RBR_ECUDA, "conv_fwd[bf16]: cuTensorMapEncodeTiled failed (%d)", (int)r);
     a.vocab = vocab; a.ids = ids; a.mask = mask; a.n_docs = n_docs; a.wpack = umma_w2; a.bias = bias;
     a.feat = feat; a.argmax = argmax; a.preact = preact; a.gate = gate; a.gate_mode = gate_mode; a.feat_ld = feat_ld;

@@ -40,6 +40,15 @@ SHAPES = [
     (40, 10, 60, 24, 20, 3),
     (6, 300, 200, 100, 200, 5),
     (300, 500, 2000, 300, 100, 3),
+    # edge shapes: one document, documents shorter than the kernel's tile and than a warp, one filter, filters split into
+    # passes (H=300), tiny / odd embedding widths, k=7 halo, odd number of documents for the CTA pair
+    (1, 500, 300, 300, 100, 3),
+    (1, 3, 20, 8, 1, 3),
+    (3, 1, 20, 8, 5, 1),
+    (65, 17, 90, 40, 33, 3),
+    (11, 200, 400, 300, 300, 3),
+    (9, 260, 300, 72, 48, 7),
+    (130, 31, 500, 100, 200, 5),
 ]
 
 
