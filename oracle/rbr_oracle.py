@@ -94,7 +94,7 @@ def conv1d_same(x: Tensor, weight: Tensor, bias: Tensor) -> Tensor:
     h, e2, k = weight.shape
     assert e == e2 and k % 2 == 1          # layers.py:39 asserts odd kernel sizes
     p = (k - 1) // 2
-    xp = torch.zeros(n, l + 2 * p, e, dtype=x.dtype)
+    xp = torch.zeros(n, l + 2 * p, e, dtype=x.dtype, device=x.device)
     xp[:, p:p + l] = x
     y = bias.view(1, 1, h).expand(n, l, h).clone()
     for j in range(k):
@@ -109,7 +109,7 @@ def conv1d_valid(x: Tensor, weight: Tensor, bias: Tensor, pad: int = 0) -> Tenso
     """
     n, l, e = x.shape
     h, _, k = weight.shape
-    xp = torch.zeros(n, l + 2 * pad, e, dtype=x.dtype)
+    xp = torch.zeros(n, l + 2 * pad, e, dtype=x.dtype, device=x.device)
     xp[:, pad:pad + l] = x
     lout = l + 2 * pad - k + 1
     y = bias.view(1, 1, h).expand(n, lout, h).clone()
