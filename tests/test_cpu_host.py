@@ -168,3 +168,26 @@ def test_bench_reference_arm_contract():
     out2 = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
                           env=dict(env, RANK="1", WORLD_SIZE="2"), capture_output=True, text=True, timeout=120)
     assert out2.returncode == 0 and out2.stdout.strip() == ""
+
+
+def test_grad_arena_layout_is_cached_per_module_and_tracks_requires_grad():
+    from rbr_b200.ops import GradArena
+    m = torch.nn.Sequential(torch.nn.Linear(5, 3), torch.nn.Linear(3, 2))
+    a1, a2 = GradArena.for_module(m), GradArena.for_module(m)
+    assert a1 is not a2 and a1.slots is a2.slots            # fresh arena per step, shared layout
+    assert a1.total == 64 * 4                                # four parameters, 256-byte (64-float) aligned slots
+    v = a1.view(m[0].weight)
+    assert v.shape == m[0].weight.shape and float(v.abs().sum()) == 0.0
+    v.add_(1.0)
+    assert float(a1.flat.sum()) == 15.0 and a2.flat is None  # lazily allocated, independent buffers
+    m[1].bias.requires_grad_(False)
+    a3 = GradArena.for_module(m)
+    assert a3.slots is not a1.slots and a3.view(m[1].bias) is None and a3.total == 64 * 3
+    with torch.no_grad():
+        assert GradArena.for_module(m) is None
+    # a persistent external buffer (the NVLS symmetric-memory arena) is re-zeroed, not re-allocated
+    buf = torch.ones(1024)
+    m.__dict__["_rbr_arena_buffer"] = buf
+    a4 = GradArena.for_module(m)
+    w = a4.view(m[0].weight)
+    assert w.data_ptr() == buf.data_ptr() and float(buf[:a4.total].sum()) == 0.0 and float(buf[a4.total:].sum()) == 1024 - a4.total
