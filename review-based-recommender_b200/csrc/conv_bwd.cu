@@ -274,7 +274,8 @@ __global__ void conv_bwd_unpack_kernel(const float* __restrict__ dw_hke, int H, 
         const int j = (int)(q % K);
         const int e = (int)((q / K) % E);
         const int h = (int)(q / ((int64_t)K * E));
-        wgrad[q] += dw_hke[((int64_t)h * K + j) * epad4 + e];
+        const float v = dw_hke[((int64_t)h * K + j) * epad4 + e];
+        if (v != 0.f) atomicAdd(wgrad + q, v);          // the document sides may run concurrently on two streams
     }
 }
 

@@ -32,6 +32,17 @@ def _stream(refresh: bool = False) -> int:
     return _STREAM_CACHE[0]
 
 
+_SIDE_STREAMS: Dict[str, list] = {}
+
+
+def _side_streams(device, n: int) -> list:
+    """n persistent auxiliary streams on `device` (created once)."""
+    pool = _SIDE_STREAMS.setdefault(str(device), [])
+    while len(pool) < n:
+        pool.append(torch.cuda.Stream(device=device))
+    return pool[:n]
+
+
 def _p(t: Optional[torch.Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 
@@ -278,27 +289,41 @@ class EncodeDocsFn(torch.autograd.Function):
         # still runs), then the weight part.  A single pass when there is no hook.
         hook = cfg.get("table_ready") if need_table else None
         passes = ((True, False), (False, True)) if hook is not None else ((True, True),)
+        # The document sides are independent (they only meet in += accumulations, all atomic): side s > 0 runs on its own
+        # stream, so the small kernels of one side (single-CTA scan, sort) overlap the other side's work.
+        main = torch.cuda.current_stream()
+        live = [s for s in range(ns) if feat_grads[s] is not None]
+        side_streams = _side_streams(table.device, max(0, len(live) - 1))
+        fgs = {s: feat_grads[s].contiguous() for s in live}
         for do_table, do_weight in passes:
-            for s in range(ns):
-                if feat_grads[s] is None:
-                    continue
-                fg = feat_grads[s].contiguous()
-                ids, mask = ids_l[s], mask_l[s]
-                doc_len = ids.shape[-1]
-                n_docs = ids.numel() // doc_len
-                col = 0
-                for i in range(n_conv):
-                    h, _, k = ctx.weights[i].shape
-                    gt = g_table if do_table else None
-                    if gt is not None or do_weight:
-                        ws_bytes = lib.rbr_conv_bwd_workspace_bytes(n_docs, h, k, emb, vocab)
-                        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=table.device)
-                        lib.check(lib.rbr_conv_act_maxpool_bwd(
-                            prec, cfg["act"], _p(table), _p(ctx.shadow), vocab, emb, _p(ids), _p(mask), None, 0, n_docs, doc_len,
-                            _p(ctx.packed[i]), h, k, cfg["pads"][i], feats[s].data_ptr() + 4 * col, argmaxes[s].data_ptr() + 4 * col,
-                            fg.data_ptr() + 4 * col, None, None, h_total, cfg["padding_idx"], _p(g_w[i]) if do_weight else None,
-                            _p(g_b[i]) if do_weight else None, _p(gt), None, _p(ws), ws_bytes, _stream()), "rbr_conv_act_maxpool_bwd")
-                    col += h
+            ev_fork = main.record_event() if len(live) > 1 else None
+            for rank_s, s in enumerate(live):
+                stream_s = main if rank_s == 0 else side_streams[rank_s - 1]
+                if rank_s > 0:
+                    stream_s.wait_event(ev_fork)
+                with torch.cuda.stream(stream_s):
+                    sh = _stream(refresh=True)
+                    fg = fgs[s]
+                    ids, mask = ids_l[s], mask_l[s]
+                    doc_len = ids.shape[-1]
+                    n_docs = ids.numel() // doc_len
+                    col = 0
+                    for i in range(n_conv):
+                        h, _, k = ctx.weights[i].shape
+                        gt = g_table if do_table else None
+                        if gt is not None or do_weight:
+                            ws_bytes = lib.rbr_conv_bwd_workspace_bytes(n_docs, h, k, emb, vocab)
+                            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=table.device)
+                            lib.check(lib.rbr_conv_act_maxpool_bwd(
+                                prec, cfg["act"], _p(table), _p(ctx.shadow), vocab, emb, _p(ids), _p(mask), None, 0, n_docs, doc_len,
+                                _p(ctx.packed[i]), h, k, cfg["pads"][i], feats[s].data_ptr() + 4 * col,
+                                argmaxes[s].data_ptr() + 4 * col, fg.data_ptr() + 4 * col, None, None, h_total, cfg["padding_idx"],
+                                _p(g_w[i]) if do_weight else None, _p(g_b[i]) if do_weight else None, _p(gt), None, _p(ws),
+                                ws_bytes, sh), "rbr_conv_act_maxpool_bwd")
+                        col += h
+            for rank_s in range(1, len(live)):
+                main.wait_event(side_streams[rank_s - 1].record_event())
+            _stream(refresh=True)
             if hook is not None and do_table and not do_weight:
                 hook(g_table)
         return (g_table, None, *g_w, *g_b, *([None] * (2 * ns)))
@@ -484,15 +509,39 @@ class DattEncodeFn(torch.autograd.Function):
         need_table = ctx.needs_input_grad[0]
         g_table = _grad_buf(arena, cfg["table_param"], need_table)
         ret = []
+        # the user and item sides only meet in the (atomic) table gradient: the second side runs on its own stream
+        main = torch.cuda.current_stream()
+        side_streams = _side_streams(dev, max(0, ctx.n_sides - 1))
+        ev_fork = main.record_event() if ctx.n_sides > 1 else None
+        all_grads = [[_grad_buf(arena, p, True) for p in cfg["params"][s]] for s in range(ctx.n_sides)]
+        fgs = [None if feat_grads[s] is None else feat_grads[s].contiguous() for s in range(ctx.n_sides)]
         for s in range(ctx.n_sides):
             ids, gate_l, gate_g, feat, amax, pre = ctx.saved_tensors[6 * s:6 * s + 6]
             prm, packed = ctx.side_ctx[s]
-            grads = [_grad_buf(arena, p, True) for p in cfg["params"][s]]
+            grads = all_grads[s]
             ret += [None, *grads]
-            if feat_grads[s] is None:
+            if fgs[s] is None:
                 continue
             n_docs, doc_len = ids.shape
-            fg = feat_grads[s].contiguous()
+            fg = fgs[s]
+            stream_s = main if s == 0 else side_streams[s - 1]
+            if s > 0:
+                stream_s.wait_event(ev_fork)
+            with torch.cuda.stream(stream_s):
+                _stream(refresh=True)
+                DattEncodeFn._side_backward(cfg, table, ctx.shadow, prec, arena, ids, gate_l, gate_g, feat, amax, pre, prm, packed,
+                                            grads, fg, g_table, vocab, emb, dev)
+        for s in range(1, ctx.n_sides):
+            if fgs[s] is not None:
+                main.wait_event(side_streams[s - 1].record_event())
+        _stream(refresh=True)
+        return (g_table, None, *ret)
+
+    @staticmethod
+    def _side_backward(cfg, table, shadow, prec, arena, ids, gate_l, gate_g, feat, amax, pre, prm, packed, grads, fg, g_table, vocab,
+                       emb, dev):
+        if True:
+            n_docs, doc_len = ids.shape
             la_w, la_b, lc_w, lc_b, ga_w, ga_b = prm[:6]
             convs = [(lc_w, lc_b, gate_l, 1, 2, 3)] + [(prm[6 + 2 * i], prm[7 + 2 * i], gate_g, 2, 6 + 2 * i, 7 + 2 * i)
                                                        for i in range(3)]
@@ -505,7 +554,7 @@ class DattEncodeFn(torch.autograd.Function):
                 ws_bytes = lib.rbr_conv_bwd_workspace_bytes(n_docs, h, k, emb, vocab)
                 ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
                 lib.check(lib.rbr_conv_act_maxpool_bwd(
-                    prec, ACT_TANH, _p(table), _p(ctx.shadow), vocab, emb, _p(ids), None, _p(gate), mode, n_docs, doc_len, _p(pk),
+                    prec, ACT_TANH, _p(table), _p(shadow), vocab, emb, _p(ids), None, _p(gate), mode, n_docs, doc_len, _p(pk),
                     h, k, 0, feat.data_ptr() + 4 * col, amax.data_ptr() + 4 * col, fg.data_ptr() + 4 * col,
                     pre.data_ptr() + 4 * col, _p(b), h_total, cfg["padding_idx"], _p(grads[wi]), _p(grads[bi]), _p(g_table),
                     _p(d_gate_l if mode == 1 else d_gate_g), _p(ws), ws_bytes, _stream()), "rbr_conv_act_maxpool_bwd")
@@ -517,4 +566,3 @@ class DattEncodeFn(torch.autograd.Function):
                                             _p(gate_g), _p(d_gate_l), _p(d_gate_g), cfg["padding_idx"], _p(grads[0]), _p(grads[1]),
                                             _p(grads[4]), _p(grads[5]), _p(g_table), _p(ws), ws_bytes, _stream()),
                       "rbr_datt_gate_bwd")
-        return (g_table, None, *ret)
