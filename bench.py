@@ -324,29 +324,20 @@ def main():
     # scheduling jitter (observed: 3.5 ms/step on a noisy VM).  Replay keeps the timed region device-bound.  The FM /
     # attention dropout seed is a host value and is therefore fixed per graph (the mask differs between the 4 graphs).
     graphs, graph_note = None, "eager"
-    if args.graphs == "auto" and world == 1:
+    if args.graphs == "auto" and world == 1 and args.mode == "train":
         try:
-            side = torch.cuda.Stream(device=dev)
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):
-                for i in range(3):
-                    step(model, *dev_batches[i % NB], loss_fn, world)
-            torch.cuda.current_stream().wait_stream(side)
-            torch.cuda.synchronize()
+            from rbr_b200.graphs import GraphedTrainStep
             graphs, pool, per_step = [], None, 0
             for i in range(NB):
-                g = torch.cuda.CUDAGraph()
-                model.zero_grad(set_to_none=True)
                 c0 = lib.rbr_launch_count()
-                with torch.cuda.graph(g, pool=pool):
-                    g_loss = step(model, *dev_batches[i], loss_fn, world)
-                per_step = lib.rbr_launch_count() - c0
-                pool = g.pool()
-                graphs.append((g, g_loss))
-            for g, _ in graphs:
-                g.replay()
+                gs = GraphedTrainStep(model, loss_fn, *dev_batches[i], warmup=1, pool=pool)
+                per_step = (lib.rbr_launch_count() - c0) // 2          # one warm-up + one captured execution
+                pool = gs.pool
+                graphs.append(gs)
+            for gs in graphs:
+                gs.replay()
             torch.cuda.synchronize()
-            graph_note = f"CUDA-graph replay of the step ({NB} graphs, one per rotating batch)"
+            graph_note = f"CUDA-graph replay of the step (rbr_b200.graphs.GraphedTrainStep, {NB} graphs, one per rotating batch)"
         except Exception as e:
             graphs, graph_note = None, f"eager (graph capture failed: {type(e).__name__}: {str(e)[:100]})"
             torch.cuda.synchronize()
@@ -356,8 +347,7 @@ def main():
     e0.record()
     if graphs is not None:
         for i in range(K):
-            graphs[i % NB][0].replay()
-        loss = graphs[(K - 1) % NB][1]
+            loss = graphs[i % NB].replay()
     else:
         for i in range(K):
             loss = step(model, *dev_batches[i % NB], loss_fn, world)
@@ -386,7 +376,7 @@ def main():
             ev.record(copy_stream)
         return d, ev
 
-    def e2e_loop(n):
+    def e2e_loop_eager(n):
         nxt = upload(0)
         last = None
         for i in range(n):
@@ -405,6 +395,51 @@ def main():
             last = done
         if last is not None:
             last.synchronize()
+
+    # graphed public API (rbr_b200.graphs.GraphedTrainStep): two step objects ping-pong, so that the H2D of step i+1 into one
+    # object's static input buffers overlaps the replay of step i on the other
+    e2e_steps, e2e_note = None, "nn.Module forward/backward (eager)"
+    if graphs is not None:
+        try:
+            from rbr_b200.graphs import GraphedTrainStep
+            e2e_steps = [GraphedTrainStep(model, loss_fn, *dev_batches[j], warmup=1, pool=graphs[0].pool) for j in range(2)]
+            e2e_note = "rbr_b200.graphs.GraphedTrainStep (CUDA-graph replay; H2D straight into the graph's static input buffers)"
+        except Exception:
+            e2e_steps = None
+    free_ev = [None, None]          # replay of the object finished → its input buffers may be overwritten
+
+    def e2e_loop_graphed(n):
+        main = torch.cuda.current_stream()
+
+        def load(i):
+            o = e2e_steps[i & 1]
+            if free_ev[i & 1] is not None:
+                copy_stream.wait_event(free_ev[i & 1])
+            b, r = pinned[i % NB]
+            o.load(b, r, stream=copy_stream)
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+            return ev
+        nxt = load(0)
+        last = None
+        for i in range(n):
+            ev = nxt
+            if i + 1 < n:
+                nxt = load(i + 1)
+            main.wait_event(ev)
+            loss = e2e_steps[i & 1].replay()
+            loss_host[i & 1].copy_(loss.detach(), non_blocking=True)
+            done = torch.cuda.Event()
+            done.record()
+            free_ev[i & 1] = done
+            if last is not None:
+                last.synchronize()
+            last = done
+        if last is not None:
+            last.synchronize()
+
+    def e2e_loop(n):
+        return e2e_loop_graphed(n) if e2e_steps is not None else e2e_loop_eager(n)
 
     e2e_loop(W)
     sync_all()
@@ -554,7 +589,7 @@ def main():
                        "step": ("eval forward under no_grad (scores only)" if args.mode == "infer" else
                                 "zero_grad + forward + MSELoss + backward" + (" + gradient all-reduce" if world > 1 else ""))},
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
-                    "how": "pinned host buffers → H2D on a copy stream (prefetch depth 1) → nn.Module forward/backward → "
+                    "how": "pinned host buffers → H2D on a copy stream (prefetch depth 1) → " + e2e_note + " → "
                            "loss read back to pinned host memory every step; wall clock, max over ranks"},
             "gpu_launches": int(launches), "gpu_launches_per_step": launches / K,
             "clocks": sampler.summary(), "roofline": roofline, "cpu_baseline": cpu_baseline, "final_loss": final_loss,

@@ -150,7 +150,9 @@ int rbr_narre_attn_bwd(const float* feat, const int64_t* other_id, int64_t batch
  *   u_text/i_text [B,H]; u_id/i_id [B] int64; W [H,K], b [K], ebd [users|items, K]; fm_h [K];
  *   user_bias [users], item_bias [items]; g_bias [1].
  *   drop_p in [0,1): FM dropout (0 = eval); the keep-mask is a counter hash of (drop_seed, sample, k) —
- *   it cannot bit-match torch's Philox stream, parity tests run with drop_p = 0.
+ *   it cannot bit-match torch's Philox stream, parity tests run with drop_p = 0.  drop_seed_dev (optional DEVICE pointer) is
+ *   added to drop_seed inside the kernel: a step counter living on the device, so that a CUDA-graph replay of the step draws
+ *   a new mask every time (graphs.py); the backward must be given the same pair.
  *   pred [B];  u_lat/i_lat [B,K] saved for the backward.
  *   ratings may be NULL; otherwise loss_sum[0] += sum (pred-rating)^2 and
  *   pred_grad[b] = 2*(pred-rating)*grad_scale  (grad_scale = 1/B for MSELoss 'mean').                 */
@@ -158,13 +160,13 @@ int rbr_head_fwd(const float* u_text, const float* i_text, const int64_t* u_id, 
                  int64_t hidden, int64_t latent, const float* Wu, const float* bu, const float* ebd_u,
                  const float* Wi, const float* bi, const float* ebd_i, const float* fm_h, const float* user_bias,
                  const float* item_bias, const float* g_bias, int64_t users, int64_t items, float drop_p,
-                 uint64_t drop_seed, float* pred, float* u_lat, float* i_lat, const float* ratings,
-                 float grad_scale, float* loss_sum, float* pred_grad, void* stream);
+                 uint64_t drop_seed, const uint64_t* drop_seed_dev, float* pred, float* u_lat, float* i_lat,
+                 const float* ratings, float grad_scale, float* loss_sum, float* pred_grad, void* stream);
 /* pred_grad [B] → u_text_grad/i_text_grad [B,H] (written) and parameter grads (+=).                    */
 int rbr_head_bwd(const float* u_text, const float* i_text, const int64_t* u_id, const int64_t* i_id, int64_t batch,
                  int64_t hidden, int64_t latent, const float* Wu, const float* Wi, const float* fm_h,
-                 const float* u_lat, const float* i_lat, float drop_p, uint64_t drop_seed, int64_t padding_idx,
-                 int64_t users, int64_t items, const float* pred_grad, float* u_text_grad, float* i_text_grad, float* Wu_grad, float* bu_grad,
+                 const float* u_lat, const float* i_lat, float drop_p, uint64_t drop_seed, const uint64_t* drop_seed_dev,
+                 int64_t padding_idx, int64_t users, int64_t items, const float* pred_grad, float* u_text_grad, float* i_text_grad, float* Wu_grad, float* bu_grad,
                  float* ebd_u_grad, float* Wi_grad, float* bi_grad, float* ebd_i_grad, float* fm_h_grad,
                  float* user_bias_grad, float* item_bias_grad, float* g_bias_grad, void* stream);
 

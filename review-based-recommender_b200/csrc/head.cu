@@ -28,8 +28,9 @@ __global__ void __launch_bounds__(HD_WARPS * 32) head_fwd_kernel(
     const float* __restrict__ ebd_u, const float* __restrict__ Wi, const float* __restrict__ bi, const float* __restrict__ ebd_i,
     const float* __restrict__ fm_h, const float* __restrict__ user_bias, const float* __restrict__ item_bias,
     const float* __restrict__ g_bias, int64_t users, int64_t items, float drop_p, uint64_t drop_seed,
-    float* __restrict__ pred, float* __restrict__ u_lat, float* __restrict__ i_lat, const float* __restrict__ ratings,
-    float grad_scale, float* __restrict__ loss_sum, float* __restrict__ pred_grad) {
+    const uint64_t* __restrict__ drop_seed_dev, float* __restrict__ pred, float* __restrict__ u_lat, float* __restrict__ i_lat,
+    const float* __restrict__ ratings, float grad_scale, float* __restrict__ loss_sum, float* __restrict__ pred_grad) {
+    if (drop_seed_dev) drop_seed += *drop_seed_dev;          // device-resident step counter (CUDA-graph replay varies the mask)
     extern __shared__ __align__(16) float smem[];
     float* Wu_s = smem;
     float* Wi_s = smem + H * (K + 1);
@@ -86,11 +87,12 @@ __global__ void __launch_bounds__(HD_WARPS * 32) head_bwd_kernel(
     const float* __restrict__ u_text, const float* __restrict__ i_text, const int64_t* __restrict__ u_id,
     const int64_t* __restrict__ i_id, int64_t B, int H, int K, const float* __restrict__ Wu, const float* __restrict__ Wi,
     const float* __restrict__ fm_h, const float* __restrict__ u_lat, const float* __restrict__ i_lat, float drop_p,
-    uint64_t drop_seed, int64_t padding_idx, int64_t users, int64_t items, const float* __restrict__ pred_grad,
+    uint64_t drop_seed, const uint64_t* __restrict__ drop_seed_dev, int64_t padding_idx, int64_t users, int64_t items, const float* __restrict__ pred_grad,
     float* __restrict__ u_text_grad, float* __restrict__ i_text_grad, float* __restrict__ Wu_grad, float* __restrict__ bu_grad,
     float* __restrict__ ebd_u_grad, float* __restrict__ Wi_grad, float* __restrict__ bi_grad, float* __restrict__ ebd_i_grad,
     float* __restrict__ fm_h_grad, float* __restrict__ user_bias_grad, float* __restrict__ item_bias_grad,
     float* __restrict__ g_bias_grad) {
+    if (drop_seed_dev) drop_seed += *drop_seed_dev;
     extern __shared__ __align__(16) float smem[];
     const int KS = K + 1;
     float* Wu_s = smem;                          // [H][K+1]
@@ -200,8 +202,8 @@ extern "C" int rbr_head_fwd(const float* u_text, const float* i_text, const int6
                             int64_t hidden, int64_t latent, const float* Wu, const float* bu, const float* ebd_u,
                             const float* Wi, const float* bi, const float* ebd_i, const float* fm_h, const float* user_bias,
                             const float* item_bias, const float* g_bias, int64_t users, int64_t items, float drop_p,
-                            uint64_t drop_seed, float* pred, float* u_lat, float* i_lat, const float* ratings,
-                            float grad_scale, float* loss_sum, float* pred_grad, void* stream) {
+                            uint64_t drop_seed, const uint64_t* drop_seed_dev, float* pred, float* u_lat, float* i_lat,
+                            const float* ratings, float grad_scale, float* loss_sum, float* pred_grad, void* stream) {
     RBR_REQUIRE(u_text && i_text && u_id && i_id && Wu && bu && ebd_u && Wi && bi && ebd_i && fm_h && user_bias && item_bias &&
                     g_bias && pred && u_lat && i_lat,
                 RBR_EINVAL, "rbr_head_fwd: null pointer");
@@ -217,15 +219,15 @@ extern "C" int rbr_head_fwd(const float* u_text, const float* i_text, const int6
     if (blocks > 148 * 2) blocks = 148 * 2;
     head_fwd_kernel<<<(unsigned)blocks, HD_WARPS * 32, smem, as_stream(stream)>>>(
         u_text, i_text, u_id, i_id, batch, H, K, Wu, bu, ebd_u, Wi, bi, ebd_i, fm_h, user_bias, item_bias, g_bias, users, items,
-        drop_p, drop_seed, pred, u_lat, i_lat, ratings, grad_scale, loss_sum, pred_grad);
+        drop_p, drop_seed, drop_seed_dev, pred, u_lat, i_lat, ratings, grad_scale, loss_sum, pred_grad);
     RBR_LAUNCH_CHECK("head_fwd_kernel");
     return RBR_OK;
 }
 
 extern "C" int rbr_head_bwd(const float* u_text, const float* i_text, const int64_t* u_id, const int64_t* i_id, int64_t batch,
                             int64_t hidden, int64_t latent, const float* Wu, const float* Wi, const float* fm_h,
-                            const float* u_lat, const float* i_lat, float drop_p, uint64_t drop_seed, int64_t padding_idx,
-                            int64_t users, int64_t items, const float* pred_grad, float* u_text_grad, float* i_text_grad, float* Wu_grad, float* bu_grad,
+                            const float* u_lat, const float* i_lat, float drop_p, uint64_t drop_seed,
+                            const uint64_t* drop_seed_dev, int64_t padding_idx, int64_t users, int64_t items, const float* pred_grad, float* u_text_grad, float* i_text_grad, float* Wu_grad, float* bu_grad,
                             float* ebd_u_grad, float* Wi_grad, float* bi_grad, float* ebd_i_grad, float* fm_h_grad,
                             float* user_bias_grad, float* item_bias_grad, float* g_bias_grad, void* stream) {
     RBR_REQUIRE(u_text && i_text && u_id && i_id && Wu && Wi && fm_h && u_lat && i_lat && pred_grad && u_text_grad &&
@@ -242,7 +244,7 @@ extern "C" int rbr_head_bwd(const float* u_text, const float* i_text, const int6
     int64_t blocks = (batch + HD_BS - 1) / HD_BS;
     if (blocks > 148 * 2) blocks = 148 * 2;
     head_bwd_kernel<<<(unsigned)blocks, HD_WARPS * 32, smem, as_stream(stream)>>>(
-        u_text, i_text, u_id, i_id, batch, H, K, Wu, Wi, fm_h, u_lat, i_lat, drop_p, drop_seed, padding_idx,
+        u_text, i_text, u_id, i_id, batch, H, K, Wu, Wi, fm_h, u_lat, i_lat, drop_p, drop_seed, drop_seed_dev, padding_idx,
         users, items, pred_grad, u_text_grad, i_text_grad, Wu_grad, bu_grad, ebd_u_grad, Wi_grad, bi_grad,
         ebd_i_grad, fm_h_grad, user_bias_grad, item_bias_grad, g_bias_grad);
     RBR_LAUNCH_CHECK("head_bwd_kernel");

@@ -212,10 +212,13 @@ class FM(nn.Module):
 def fused_head(user_feat: LastFeat, item_feat: LastFeat, fm: FM, u_text, i_text, u_id, i_id, training: bool, arena):
     """K4: LastFeat(user) + LastFeat(item) + FM in one kernel (reference deepconn.py:48-51)."""
     p = fm.dropout.p if training else 0.0
-    seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if p > 0 else 0
+    # dropout mask seed: a fresh host value per call, or — inside a captured CUDA graph (graphs.GraphedTrainStep) — a fixed
+    # base plus a step counter that lives on the device and is bumped at the start of every replay
+    seed_dev = fm.__dict__.get("_rbr_seed_dev") if p > 0 else None
+    seed = 0 if p <= 0 else (0x5EED if seed_dev is not None else int(torch.randint(0, 2 ** 62, (1,)).item()))
     params = [user_feat.W, user_feat.b, user_feat.ebd.weight, item_feat.W, item_feat.b, item_feat.ebd.weight, fm.h,
               fm.user_bias.weight, fm.item_bias.weight, fm.g_bias]
-    return ops.HeadFn.apply(u_text, i_text, u_id, i_id, *params, p, seed, fm.padding_idx, arena, params)
+    return ops.HeadFn.apply(u_text, i_text, u_id, i_id, *params, p, seed, fm.padding_idx, arena, params, seed_dev)
 
 
 class LinearAttention(nn.Module):

@@ -376,7 +376,7 @@ class HeadFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, u_text, i_text, u_id, i_id, Wu, bu, ebd_u, Wi, bi, ebd_i, fm_h, user_bias, item_bias, g_bias, drop_p,
-                drop_seed, padding_idx, arena, params):
+                drop_seed, padding_idx, arena, params, seed_dev=None):
         _stream(refresh=True)
         u_text = _req(u_text, torch.float32, "u_text")
         i_text = _req(i_text, torch.float32, "i_text")
@@ -389,10 +389,10 @@ class HeadFn(torch.autograd.Function):
         u_lat = torch.empty(B, K, dtype=torch.float32, device=u_text.device)
         i_lat = torch.empty(B, K, dtype=torch.float32, device=u_text.device)
         lib.check(lib.rbr_head_fwd(_p(u_text), _p(i_text), _p(u_id), _p(i_id), B, H, K, *[_p(t) for t in fl], ebd_u.shape[0],
-                                   ebd_i.shape[0], float(drop_p), int(drop_seed), _p(pred), _p(u_lat), _p(i_lat), None, 0.0,
-                                   None, None, _stream()), "rbr_head_fwd")
+                                   ebd_i.shape[0], float(drop_p), int(drop_seed), _p(seed_dev), _p(pred), _p(u_lat), _p(i_lat), None,
+                                   0.0, None, None, _stream()), "rbr_head_fwd")
         ctx.save_for_backward(u_text, i_text, u_id, i_id, fl[0], fl[3], fl[6], u_lat, i_lat)
-        ctx.drop, ctx.padding_idx, ctx.arena, ctx.params = (float(drop_p), int(drop_seed)), padding_idx, arena, params
+        ctx.drop, ctx.padding_idx, ctx.arena, ctx.params = (float(drop_p), int(drop_seed), seed_dev), padding_idx, arena, params
         ctx.sizes = (ebd_u.shape[0], ebd_i.shape[0])
         return pred
 
@@ -407,10 +407,10 @@ class HeadFn(torch.autograd.Function):
         # params order: Wu, bu, ebd_u, Wi, bi, ebd_i, fm_h, user_bias, item_bias, g_bias
         grads = [_grad_buf(ctx.arena, p, True) for p in ctx.params]
         lib.check(lib.rbr_head_bwd(_p(u_text), _p(i_text), _p(u_id), _p(i_id), B, H, K, _p(Wu), _p(Wi), _p(fm_h), _p(u_lat),
-                                   _p(i_lat), ctx.drop[0], ctx.drop[1], -1 if ctx.padding_idx is None else ctx.padding_idx,
+                                   _p(i_lat), ctx.drop[0], ctx.drop[1], _p(ctx.drop[2]), -1 if ctx.padding_idx is None else ctx.padding_idx,
                                    ctx.sizes[0], ctx.sizes[1], _p(g_pred), _p(g_ut), _p(g_it), *[_p(g) for g in grads],
                                    _stream()), "rbr_head_bwd")
-        return (g_ut, g_it, None, None, *grads, None, None, None, None, None)
+        return (g_ut, g_it, None, None, *grads, None, None, None, None, None, None)
 
 
 # ---------------------------------------------------------------------------------------------------

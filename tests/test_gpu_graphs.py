@@ -1,0 +1,60 @@
+"""GPU tests of rbr_b200.graphs.GraphedTrainStep: a captured-and-replayed training step gives the same loss and gradients
+as the eager nn.Module path on every batch fed to it, and the FM dropout mask still changes from replay to replay."""
+import pytest
+import torch
+
+import rbr_b200
+from conftest import rel_err
+from rbr_b200 import synth
+from rbr_b200.graphs import GraphedTrainStep
+
+pytestmark = pytest.mark.gpu
+
+
+def _model(dropout, precision="fp32"):
+    U, I, V, E, H, K, L = 40, 30, 600, 64, 24, 16, 96
+    params = synth.deepconn_params(U, I, V, E, H, K, (3,), seed=3)
+    model = rbr_b200.DeepCoNNpp(U, I, V, [3], E, H, K, L, None, dropout, precision=precision)
+    model.load_state_dict(params)
+    return model.cuda().train(), (U, I, V, L)
+
+
+def _eager(model, batch, ratings):
+    model.zero_grad(set_to_none=True)
+    loss = torch.nn.MSELoss()(model(*batch), ratings)
+    loss.backward()
+    return float(loss), {k: p.grad.detach().clone() for k, p in model.named_parameters()}
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_graphed_step_matches_eager_on_every_batch(precision):
+    model, (U, I, V, L) = _model(0.0, precision)
+    batches = []
+    for seed in (5, 6, 7):
+        b, r = synth.deepconn_batch(32, L, V, U, I, seed=seed)
+        batches.append(([t.cuda() for t in b], r.cuda()))
+    ref = [_eager(model, b, r) for b, r in batches]
+    step = GraphedTrainStep(model, torch.nn.MSELoss(), *batches[0])
+    for (b, r), (ref_loss, ref_grads) in zip(batches, ref):
+        # inputs from pinned HOST memory for one of them: H2D straight into the graph's static buffers
+        src = [t.cpu().pin_memory() for t in b] if ref_loss == ref[1][0] else b
+        loss = step(src, r)
+        torch.cuda.synchronize()
+        assert abs(float(loss) - ref_loss) <= 1e-6 * max(1.0, abs(ref_loss))
+        for k, p in model.named_parameters():
+            assert rel_err(p.grad.cpu(), ref_grads[k].cpu()) < 1e-6, k
+
+
+def test_graphed_step_dropout_mask_changes_between_replays():
+    model, (U, I, V, L) = _model(0.5)
+    b, r = synth.deepconn_batch(64, L, V, U, I, seed=9)
+    b, r = [t.cuda() for t in b], r.cuda()
+    step = GraphedTrainStep(model, torch.nn.MSELoss(), b, r)
+    losses = []
+    for _ in range(4):
+        losses.append(float(step.replay()))
+    assert len({round(x, 6) for x in losses}) > 1, losses          # same inputs, different FM dropout masks
+    model.eval()
+    with torch.no_grad():
+        p1, p2 = model(*b), model(*b)
+    assert torch.equal(p1, p2)
