@@ -248,8 +248,9 @@ def main():
     ap.add_argument("--overlap", default="off", choices=["off", "on"],
                     help="start the word-table all-reduce inside backward, overlapping the weight-gradient kernels")
     ap.add_argument("--graphs", default="auto", choices=["auto", "off"],
-                    help="auto: at N=1 the device-timed loop replays CUDA graphs of the step (one per rotating batch), so host "
-                         "scheduling jitter cannot make it CPU-bound; e2e always goes through the eager public API")
+                    help="auto: the timed loops replay CUDA graphs of the step (rbr_b200.graphs.GraphedTrainStep, one per rotating "
+                         "batch; at N>1 the gradient exchange is captured with it), so host scheduling jitter cannot make them "
+                         "CPU-bound; off: eager nn.Module calls")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--library-baseline", action="store_true",
                     help="also time the oracle's plain-PyTorch formulation of the same step on this GPU (ATen/cuDNN library kernels, "
@@ -324,13 +325,15 @@ def main():
     # scheduling jitter (observed: 3.5 ms/step on a noisy VM).  Replay keeps the timed region device-bound.  The FM /
     # attention dropout seed is a host value and is therefore fixed per graph (the mask differs between the 4 graphs).
     graphs, graph_note = None, "eager"
-    if args.graphs == "auto" and world == 1 and args.mode == "train":
+    use_graphs = args.graphs == "auto" and args.mode == "train" and (world == 1 or os.environ.get("RBR_BENCH_DP_GRAPHS", "1") == "1")
+    post_bwd = (lambda: parallel.allreduce_gradients(model, compress=GRAD_COMPRESS)) if world > 1 else None
+    if use_graphs:
         try:
             from rbr_b200.graphs import GraphedTrainStep
             graphs, pool, per_step = [], None, 0
             for i in range(NB):
                 c0 = lib.rbr_launch_count()
-                gs = GraphedTrainStep(model, loss_fn, *dev_batches[i], warmup=1, pool=pool)
+                gs = GraphedTrainStep(model, loss_fn, *dev_batches[i], warmup=1, pool=pool, post_backward=post_bwd)
                 per_step = (lib.rbr_launch_count() - c0) // 2          # one warm-up + one captured execution
                 pool = gs.pool
                 graphs.append(gs)
@@ -339,6 +342,8 @@ def main():
             torch.cuda.synchronize()
             graph_note = f"CUDA-graph replay of the step (rbr_b200.graphs.GraphedTrainStep, {NB} graphs, one per rotating batch)"
         except Exception as e:
+            if world > 1:
+                raise                                # ranks must not diverge (one eager, one graphed) inside collectives
             graphs, graph_note = None, f"eager (graph capture failed: {type(e).__name__}: {str(e)[:100]})"
             torch.cuda.synchronize()
     l0 = lib.rbr_launch_count()
@@ -402,7 +407,8 @@ def main():
     if graphs is not None:
         try:
             from rbr_b200.graphs import GraphedTrainStep
-            e2e_steps = [GraphedTrainStep(model, loss_fn, *dev_batches[j], warmup=1, pool=graphs[0].pool) for j in range(2)]
+            e2e_steps = [GraphedTrainStep(model, loss_fn, *dev_batches[j], warmup=1, pool=graphs[0].pool, post_backward=post_bwd)
+                         for j in range(2)]
             e2e_note = "rbr_b200.graphs.GraphedTrainStep (CUDA-graph replay; H2D straight into the graph's static input buffers)"
         except Exception:
             e2e_steps = None

@@ -14,7 +14,9 @@ the graph-safe Philox offset).
         torch.nn.utils.clip_grad_norm_(model.parameters(), 5.0); optimizer.step()
 
 Shapes are fixed at capture (the reference pads every batch to the same [bz, doc_len]; a ragged last batch needs its own
-step object or the eager path).  Data-parallel training keeps the eager path (parallel.py).
+step object or the eager path).  Data-parallel: pass `post_backward=lambda: parallel.allreduce_gradients(model)` — the
+gradient exchange (NVLS kernel and its device-side barriers, or ncclAllReduce) is captured with the step; every rank must
+construct and replay its step object in lockstep.
 """
 from __future__ import annotations
 
@@ -26,11 +28,12 @@ import torch
 class GraphedTrainStep:
     def __init__(self, model: torch.nn.Module, loss_fn: Callable, example_batch: Sequence[torch.Tensor],
                  example_ratings: torch.Tensor, restage_operands: bool = True, warmup: int = 3,
-                 pool=None, device: Optional[torch.device] = None):
+                 pool=None, device: Optional[torch.device] = None, post_backward: Optional[Callable[[], None]] = None):
         dev = device or next(model.parameters()).device
         if dev.type != "cuda":
             raise RuntimeError("GraphedTrainStep needs the model on a CUDA device")
         self.model, self.loss_fn, self.restage = model, loss_fn, restage_operands
+        self.post_backward = post_backward      # e.g. lambda: parallel.allreduce_gradients(model) — captured with the step
         self.static_batch = [torch.empty(t.shape, dtype=t.dtype, device=dev) for t in example_batch]
         self.static_ratings = torch.empty(example_ratings.shape, dtype=example_ratings.dtype, device=dev)
         fm = getattr(model, "fm", None)
@@ -64,6 +67,8 @@ class GraphedTrainStep:
         pred = out[0] if isinstance(out, tuple) else out
         loss = self.loss_fn(pred, self.static_ratings)
         loss.backward()
+        if self.post_backward is not None:
+            self.post_backward()
         return loss
 
     def load(self, batch: Sequence[torch.Tensor], ratings: torch.Tensor, stream: Optional[torch.cuda.Stream] = None) -> None:
