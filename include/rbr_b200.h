@@ -92,6 +92,11 @@ int rbr_conv_pack(const float* weight, int64_t emb, int64_t filters, int64_t ksi
  * falling back to the single-CTA cp.async kernel for shapes outside it), 1 = single-CTA kernel only, 2 = CTA-pair kernel
  * only.  Returns the previous setting.  Both kernels compute the same function (tests run every case on both).          */
 int rbr_set_conv_tc_variant(int variant);
+/* Tiling plan of the CTA-pair kernel for a shape (host-only, launches nothing; used by the CPU tests of the tiling logic):
+ * out[0..15] = {available, passes, filters/pass, filters/CTA, 64-wide K blocks, K steps, gather4 groups per stage, stage bytes,
+ * ring stages, resident weight bytes per CTA, short-document mode, documents per tile, document row stride, tiles per document,
+ * shared-memory bytes, TMEM columns}.                                                                                         */
+int rbr_conv_tc2_plan(int64_t emb, int64_t filters, int64_t ksize, int64_t doc_len, int64_t pad, int64_t n_docs, int64_t* out);
 int rbr_conv_act_maxpool_fwd(int precision, int activation, const void* table, const void* shadow_bf16,
                              int64_t vocab, int64_t emb, const int64_t* ids, const uint8_t* mask,
                              const float* gate, int gate_mode, int64_t n_docs, int64_t doc_len,

@@ -561,4 +561,18 @@ int conv_tc2_dispatch(const __nv_bfloat16* shadow, int64_t vocab, int E, const i
 
 }  // namespace rbr
 
+// Host-side plan of the CTA-pair kernel for a shape, without launching anything (tests of the tiling logic run on CPU).
+// out[0..15] = {available, P, Nb, NL, nkb, ksteps, groups, stage_bytes, nst, w_bytes, mode_b, D, S, tpu, smem_bytes, tmem_cols}
+extern "C" int rbr_conv_tc2_plan(int64_t emb, int64_t filters, int64_t ksize, int64_t doc_len, int64_t pad, int64_t n_docs,
+                                 int64_t* out) {
+    RBR_REQUIRE(out, RBR_EINVAL, "rbr_conv_tc2_plan: null pointer");
+    rbr::Tc2Plan p{};
+    const bool ok = emb > 0 && filters > 0 && ksize > 0 && doc_len > 0 && pad >= 0 &&
+                    rbr::tc2_make_plan((int)emb, (int)filters, (int)ksize, (int)doc_len, (int)pad, 0, n_docs, &p);
+    const int64_t v[16] = {ok ? 1 : 0, p.P, p.Nb, p.NL, p.nkb, p.ksteps, p.groups, p.stage_bytes, p.nst, p.w_bytes, p.mode_b, p.D, p.S,
+                           p.tpu, p.smem_bytes, p.tmem_cols};
+    for (int i = 0; i < 16; ++i) out[i] = v[i];
+    return RBR_OK;
+}
+
 RBR_DEFINE_OOB_ACCESSOR(conv_tc2)

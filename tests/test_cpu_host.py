@@ -191,3 +191,39 @@ def test_grad_arena_layout_is_cached_per_module_and_tracks_requires_grad():
     a4 = GradArena.for_module(m)
     w = a4.view(m[0].weight)
     assert w.data_ptr() == buf.data_ptr() and float(buf[:a4.total].sum()) == 0.0 and float(buf[a4.total:].sum()) == 1024 - a4.total
+
+
+def test_conv_tc2_plan_invariants():
+    """Tiling logic of the CTA-pair conv kernel (host code, no GPU): shared memory / TMEM budgets, UMMA shape rules, ring depth,
+    short-document packing."""
+    import ctypes
+    from rbr_b200._lib import lib
+    out = (ctypes.c_int64 * 16)()
+    shapes = [(300, 100, 3, 500, 1), (300, 150, 3, 60, 1), (300, 100, 3, 60, 1), (100, 200, 1, 500, 0), (100, 100, 2, 500, 0),
+              (100, 100, 4, 500, 0), (300, 300, 3, 200, 1), (16, 16, 1, 40, 0), (8, 1, 3, 3, 1), (72, 48, 7, 260, 3),
+              (100, 200, 5, 31, 2), (40, 33, 3, 17, 1), (300, 100, 5, 500, 2), (512, 256, 3, 128, 1), (300, 100, 3, 10, 1)]
+    n_ok = 0
+    for E, H, K, L, pad in shapes:
+        assert lib.rbr_conv_tc2_plan(E, H, K, L, pad, 1000, ctypes.cast(out, ctypes.c_void_p)) == 0
+        ok, P, Nb, NL, nkb, ksteps, groups, stage_bytes, nst, w_bytes, mode_b, D, S, tpu, smem, tmem = list(out)
+        if not ok:
+            continue
+        n_ok += 1
+        Lext, Lout = L + 2 * pad, L + 2 * pad - K + 1
+        assert P >= 1 and P * Nb >= H and Nb % 16 == 0 and 16 <= Nb <= 256 and NL * 2 == Nb          # UMMA N rules, M = 256
+        assert nkb * 64 >= E and ksteps * 16 >= E and ksteps <= nkb * 4
+        assert groups * 4 >= 128 + K - 1 and stage_bytes % 1024 == 0 and stage_bytes >= groups * 512   # swizzle-atom aligned stages
+        assert nst >= 3 and smem <= 232448 and w_bytes == K * ((E + 15) // 16 * 2) * NL * 16
+        assert tmem in (256, 512) and tmem >= 2 * Nb
+        if mode_b:
+            assert S % 32 == 0 and S >= Lext and 1 <= D <= 4 and tpu == 1
+            assert (D - 1) * S + Lext <= 128 + K - 1                                                   # all documents' rows are staged
+            assert (D - 1) * S + Lout <= 128                                                           # and their outputs are TMEM lanes
+        else:
+            assert D == 1 and tpu == (Lout + 127) // 128
+    assert n_ok >= 12
+    # the benchmark shapes take one pass each (A operand gathered once)
+    lib.rbr_conv_tc2_plan(300, 100, 3, 500, 1, 4096, ctypes.cast(out, ctypes.c_void_p))
+    assert out[0] == 1 and out[1] == 1 and out[2] == 112 and out[8] >= 6
+    lib.rbr_conv_tc2_plan(300, 150, 3, 60, 1, 40960, ctypes.cast(out, ctypes.c_void_p))
+    assert out[0] == 1 and out[1] == 1 and out[2] == 160 and out[10] == 1 and out[11] == 2 and out[12] == 64
