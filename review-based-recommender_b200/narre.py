@@ -58,7 +58,18 @@ class NARRE(nn.Module):
         u_feat, i_feat = self.ngram.encode(self.word_embeddings, [u_docs, i_docs], [u_m, i_m])
         u_feat = u_feat.view(bz, self.doc_num, self.hiddem_dim)
         i_feat = i_feat.view(bz, self.doc_num, self.hiddem_dim)
-        u_feat, u_att_scores = self.user_att(u_feat, reuid)            # narre.py:184
-        i_feat, i_att_scores = self.item_att(i_feat, reiid)            # narre.py:185
+        # the user-side and item-side attentions are independent, latency-bound kernels (one warp per sample): the item side
+        # runs on an auxiliary stream, forward and (because autograd replays each node on its forward stream) backward
+        if u_feat.is_cuda:
+            main = torch.cuda.current_stream()
+            aux = ops._side_streams(u_feat.device, 1)[0]
+            aux.wait_stream(main)
+            with torch.cuda.stream(aux):
+                i_feat, i_att_scores = self.item_att(i_feat, reiid)    # narre.py:185
+            u_feat, u_att_scores = self.user_att(u_feat, reuid)        # narre.py:184
+            main.wait_stream(aux)
+        else:
+            u_feat, u_att_scores = self.user_att(u_feat, reuid)
+            i_feat, i_att_scores = self.item_att(i_feat, reiid)
         pred = fused_head(self.user_feat, self.item_feat, self.fm, u_feat, i_feat, u_id, i_id, self.training, arena)
         return pred.view(-1), u_att_scores, i_att_scores
