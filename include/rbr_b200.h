@@ -41,6 +41,15 @@ extern "C" {
 #define RBR_ACT_RELU 0 /* NgramFeat: nn.ReLU  (models/deepconn/layers.py:108)                       */
 #define RBR_ACT_TANH 1 /* D-ATT:     nn.Tanh  (models/dual_att/layers.py:39,69,73,77)               */
 
+/* `flags` of the conv entry points (per call; the library keeps no process-wide switches) */
+#define RBR_CONV_TC_SINGLE_CTA 1 /* bf16 forward: only the single-CTA cp.async tensor-core kernel (A/B timing, tests)        */
+#define RBR_CONV_TC_PAIR_ONLY 2  /* bf16 forward: only the CTA-pair TMA kernel; RBR_EUNSUPPORTED when the shape is outside it */
+#define RBR_CONV_BWD_DENSE_TC 4  /* backward: force the dense tensor-core formulation (short documents) where the shape allows;
+                                    default = chosen by shape                                                                  */
+#define RBR_CONV_BWD_SPARSE 8    /* backward: force the arg-max-sparse CUDA-core formulation                                   */
+#define RBR_IDS_I32 16           /* `ids` points to int32 token ids (staged input pipeline) instead of int64     */
+#define RBR_MASK_FROM_IDS 32     /* mask == NULL means mask = (ids != 0) — utils.py:30-42's get_mask — instead of "all true"   */
+
 int rbr_version(void);
 const char* rbr_last_error(void);
 /* Number of out-of-range token/id values seen by any kernel since the last call (they are treated as
@@ -86,23 +95,22 @@ int rbr_conv_pack(const float* weight, int64_t emb, int64_t filters, int64_t ksi
  *   gate  optional fp32 multiplier applied to every (unmasked) token row before the conv:
  *         gate_mode 0 = none, 1 = per token [n_docs, doc_len], 2 = per doc [n_docs]  (D-ATT gates)
  *   feat  [n_docs, feat_ld] fp32, columns [0, filters) written;  argmax [n_docs, feat_ld] int32 with
- *         the FIRST position attaining the max (nn.MaxPool1d tie rule);  preact (optional, same shape):
- *         the pooled value before the activation (needed by the backward of a gated conv).            */
-/* Tensor-core (RBR_PREC_BF16) kernel selection: 0 = best available (default: the CTA-pair cta_group::2 / TMA-gather kernel,
- * falling back to the single-CTA cp.async kernel for shapes outside it), 1 = single-CTA kernel only, 2 = CTA-pair kernel
- * only.  Returns the previous setting.  Both kernels compute the same function (tests run every case on both).          */
-int rbr_set_conv_tc_variant(int variant);
+ *         the FIRST position attaining the max (nn.MaxPool1d tie rule);  pool_raw (optional, same shape):
+ *         the pooled value before bias and activation, gate included (gate * conv_nobias(x) at the arg-max;
+ *         needed by the backward of a gated conv).
+ *   ids   int64 (torch.LongTensor) or, with RBR_IDS_I32 in `flags`, int32; RBR_MASK_FROM_IDS: see above.
+ *   RBR_PREC_BF16 shapes outside both tensor-core kernels fall back to the fp32 kernel when `table` is given. */
 /* Tiling plan of the CTA-pair kernel for a shape (host-only, launches nothing; used by the CPU tests of the tiling logic):
  * out[0..15] = {available, passes, filters/pass, filters/CTA, 64-wide K blocks, K steps, gather4 groups per stage, stage bytes,
  * ring stages, resident weight bytes per CTA, short-document mode, documents per tile, document row stride, tiles per document,
  * shared-memory bytes, TMEM columns}.                                                                                         */
 int rbr_conv_tc2_plan(int64_t emb, int64_t filters, int64_t ksize, int64_t doc_len, int64_t pad, int64_t n_docs, int64_t* out);
 int rbr_conv_act_maxpool_fwd(int precision, int activation, const void* table, const void* shadow_bf16,
-                             int64_t vocab, int64_t emb, const int64_t* ids, const uint8_t* mask,
+                             int64_t vocab, int64_t emb, const void* ids, const uint8_t* mask,
                              const float* gate, int gate_mode, int64_t n_docs, int64_t doc_len,
                              const void* packed, const float* bias, int64_t filters, int64_t ksize,
-                             int64_t pad, float* feat, int32_t* argmax, float* preact, int64_t feat_ld,
-                             void* stream);
+                             int64_t pad, float* feat, int32_t* argmax, float* pool_raw, int64_t feat_ld,
+                             int flags, void* stream);
 
 /* ---- K2b: arg-max-sparse backward of K2 ------------------------------------------------------------
  * Replaces aten::convolution_backward + max_pool1d backward + relu backward + masked_fill backward +
@@ -115,23 +123,17 @@ int rbr_conv_act_maxpool_fwd(int precision, int activation, const void* table, c
  * (with gate_grad == NULL) only the weight/bias part — data-parallel training finishes the table gradients of all
  * document sides first so that their all-reduce overlaps the weight-gradient kernels (parallel.py).
  * gate / gate_grad: as in the forward; gate_grad (same shape as gate, +=) receives d loss / d gate =
- * sum_h g * (preact - bias) / gate, which is why a gated backward also needs `preact` and `bias`
- * (both may be NULL when gate_mode == 0).                                                             */
+ * sum_h g * conv_nobias(x) = sum_h g * pool_raw / gate (0 where the gate saturated to exactly 0: no cancellation, no
+ * inf/NaN), which is why a gated backward also needs the forward's `pool_raw` (NULL when gate_mode == 0). */
 int64_t rbr_conv_bwd_workspace_bytes(int64_t n_docs, int64_t filters, int64_t ksize, int64_t emb, int64_t vocab);
-/* Backward formulation for SHORT documents (doc_len <= 128, filters <= 160, no gate; NARRE's 60-token reviews): one
- * per-document kernel (embedding dim sliced, weight slice in shared memory, dW slice in registers, dX per document in shared
- * memory) instead of entries + token sort + weight + table kernels.  0 = never (default: it is instruction-bound and
- * currently 2x slower than the generic kernels, see conv_bwd.cu), 1 = when the batch has >= 64 documents, 2 = whenever
- * the shape allows.  Returns the previous mode.  Both formulations compute the same gradients (tests run both).          */
-int rbr_set_conv_bwd_short(int mode);
 int rbr_conv_act_maxpool_bwd(int precision, int activation, const void* table, const void* shadow_bf16,
-                             int64_t vocab, int64_t emb, const int64_t* ids, const uint8_t* mask,
+                             int64_t vocab, int64_t emb, const void* ids, const uint8_t* mask,
                              const float* gate, int gate_mode, int64_t n_docs, int64_t doc_len,
                              const void* packed, int64_t filters, int64_t ksize, int64_t pad,
                              const float* feat, const int32_t* argmax, const float* feat_grad,
-                             const float* preact, const float* bias, int64_t feat_ld,
+                             const float* pool_raw, int64_t feat_ld,
                              int64_t padding_idx, float* weight_grad, float* bias_grad, float* table_grad,
-                             float* gate_grad, void* ws, int64_t ws_bytes, void* stream);
+                             float* gate_grad, void* ws, int64_t ws_bytes, int flags, void* stream);
 
 /* ---- K3: fused NARRE review-level attention --------------------------------------------------------
  * Replaces LinearAttention.forward, models/narre/narre.py:40-64 (dropout excluded: applied by the caller).
@@ -159,19 +161,26 @@ int rbr_narre_attn_bwd(const float* feat, const int64_t* other_id, int64_t batch
  *   added to drop_seed inside the kernel: a step counter living on the device, so that a CUDA-graph replay of the step draws
  *   a new mask every time (graphs.py); the backward must be given the same pair.
  *   pred [B];  u_lat/i_lat [B,K] saved for the backward.
- *   ratings may be NULL; otherwise loss_sum[0] += sum (pred-rating)^2 and
- *   pred_grad[b] = 2*(pred-rating)*grad_scale  (grad_scale = 1/B for MSELoss 'mean').                 */
+ *   ratings may be NULL; otherwise loss_sum[0] += grad_scale * sum (pred-rating)^2 (the caller zero-fills it) and
+ *   pred_grad[b] = 2*(pred-rating)*grad_scale  (grad_scale = 1/B for MSELoss 'mean': loss_sum is then the loss). */
 int rbr_head_fwd(const float* u_text, const float* i_text, const int64_t* u_id, const int64_t* i_id, int64_t batch,
                  int64_t hidden, int64_t latent, const float* Wu, const float* bu, const float* ebd_u,
                  const float* Wi, const float* bi, const float* ebd_i, const float* fm_h, const float* user_bias,
                  const float* item_bias, const float* g_bias, int64_t users, int64_t items, float drop_p,
                  uint64_t drop_seed, const uint64_t* drop_seed_dev, float* pred, float* u_lat, float* i_lat,
                  const float* ratings, float grad_scale, float* loss_sum, float* pred_grad, void* stream);
-/* pred_grad [B] → u_text_grad/i_text_grad [B,H] (written) and parameter grads (+=).                    */
+/* pred_grad [B] → u_text_grad/i_text_grad [B,H] (written) and parameter grads (+=).  Each of the four id tables has its
+ * own padding row (nn.Embedding(padding_idx=...) of LastFeat.ebd ×2, FM.user_bias, FM.item_bias; < 0: none), which gets
+ * no gradient.
+ * rbr_head_dropout_mask (test/debug aid): writes the keep-scale the kernels apply, keep[b,k] in {0, 1/(1-p)}, for the same
+ * (drop_p, drop_seed, drop_seed_dev) triple.                                                            */
+int rbr_head_dropout_mask(int64_t batch, int64_t latent, float drop_p, uint64_t drop_seed, const uint64_t* drop_seed_dev,
+                          float* keep, void* stream);
 int rbr_head_bwd(const float* u_text, const float* i_text, const int64_t* u_id, const int64_t* i_id, int64_t batch,
                  int64_t hidden, int64_t latent, const float* Wu, const float* Wi, const float* fm_h,
                  const float* u_lat, const float* i_lat, float drop_p, uint64_t drop_seed, const uint64_t* drop_seed_dev,
-                 int64_t padding_idx, int64_t users, int64_t items, const float* pred_grad, float* u_text_grad, float* i_text_grad, float* Wu_grad, float* bu_grad,
+                 int64_t ebd_u_padding_idx, int64_t ebd_i_padding_idx, int64_t user_bias_padding_idx,
+                 int64_t item_bias_padding_idx, int64_t users, int64_t items, const float* pred_grad, float* u_text_grad, float* i_text_grad, float* Wu_grad, float* bu_grad,
                  float* ebd_u_grad, float* Wi_grad, float* bi_grad, float* ebd_i_grad, float* fm_h_grad,
                  float* user_bias_grad, float* item_bias_grad, float* g_bias_grad, void* stream);
 

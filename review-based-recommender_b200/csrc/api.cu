@@ -25,15 +25,15 @@ int cuda_fail(cudaError_t e, const char* what) {
     return RBR_ECUDA;
 }
 
-int conv_fp32_dispatch(const float* table, int64_t vocab, int E, const int64_t* ids, const uint8_t* mask, const float* gate,
+int conv_fp32_dispatch(const float* table, int64_t vocab, int E, IdView ids, const uint8_t* mask, const float* gate,
                        int gate_mode, int64_t n_docs, int L, const float* keh, int Hpad4, const float* bias, int H, int K,
                        int pad, int act, float* feat, int32_t* argmax, float* preact, int feat_ld, cudaStream_t s);
-int conv_tc_dispatch(const __nv_bfloat16* shadow, int64_t vocab, int E, const int64_t* ids, const uint8_t* mask,
+int conv_tc_dispatch(const __nv_bfloat16* shadow, int64_t vocab, int E, IdView ids, const uint8_t* mask,
                      const float* gate, int gate_mode, int64_t n_docs, int L, const __nv_bfloat16* umma_w, const void* zero_row,
                      const float* bias, int H, int K, int pad, int act, float* feat, int32_t* argmax, float* preact, int feat_ld,
                      cudaStream_t s);
 
-int conv_tc2_dispatch(const __nv_bfloat16* shadow, int64_t vocab, int E, const int64_t* ids, const uint8_t* mask,
+int conv_tc2_dispatch(const __nv_bfloat16* shadow, int64_t vocab, int E, IdView ids, const uint8_t* mask,
                       const float* gate, int gate_mode, int64_t n_docs, int L, const __nv_bfloat16* umma_w2, const float* bias,
                       int H, int K, int pad, int act, float* feat, int32_t* argmax, float* preact, int feat_ld, cudaStream_t s);
 
@@ -48,24 +48,6 @@ int oob_consume_datt(cudaStream_t, unsigned int*);
 }  // namespace rbr
 
 using namespace rbr;
-
-// which tensor-core conv variant rbr_conv_act_maxpool_fwd uses: 0 = best available (CTA-pair/TMA first), 1 = single-CTA
-// cp.async variant only, 2 = CTA-pair variant only (error when the shape is outside it).  Initial value from the
-// environment variable RBR_CONV_TC_VARIANT; rbr_set_conv_tc_variant() changes it at run time (tests, A/B timing).
-static int g_conv_tc_variant = -1;
-static int conv_tc_variant() {
-    if (g_conv_tc_variant < 0) {
-        const char* e = getenv("RBR_CONV_TC_VARIANT");
-        g_conv_tc_variant = (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 0;
-    }
-    return g_conv_tc_variant;
-}
-extern "C" int rbr_set_conv_tc_variant(int variant) {
-    RBR_REQUIRE(variant >= 0 && variant <= 2, RBR_EINVAL, "rbr_set_conv_tc_variant: variant must be 0, 1 or 2");
-    const int prev = conv_tc_variant();
-    g_conv_tc_variant = variant;
-    return prev;
-}
 
 extern "C" int rbr_version(void) { return 100; }   // 0.1.0
 
@@ -87,11 +69,12 @@ extern "C" int rbr_consume_oob_count(void* stream) {
 }
 
 extern "C" int rbr_conv_act_maxpool_fwd(int precision, int activation, const void* table, const void* shadow_bf16,
-                                        int64_t vocab, int64_t emb, const int64_t* ids, const uint8_t* mask, const float* gate,
+                                        int64_t vocab, int64_t emb, const void* ids_raw, const uint8_t* mask, const float* gate,
                                         int gate_mode, int64_t n_docs, int64_t doc_len, const void* packed, const float* bias,
                                         int64_t filters, int64_t ksize, int64_t pad, float* feat, int32_t* argmax,
-                                        float* preact, int64_t feat_ld, void* stream) {
-    RBR_REQUIRE(ids && packed && bias && feat && argmax, RBR_EINVAL, "conv_fwd: null pointer");
+                                        float* preact, int64_t feat_ld, int flags, void* stream) {
+    const IdView ids = id_view(ids_raw, flags);
+    RBR_REQUIRE(ids_raw && packed && bias && feat && argmax, RBR_EINVAL, "conv_fwd: null pointer");
     RBR_REQUIRE(n_docs >= 0 && doc_len > 0 && filters > 0 && ksize > 0 && emb > 0 && vocab > 0 && pad >= 0, RBR_EINVAL,
                 "conv_fwd: bad sizes");
     RBR_REQUIRE(feat_ld >= filters, RBR_EINVAL, "conv_fwd: feat_ld < filters");
@@ -111,20 +94,34 @@ extern "C" int rbr_conv_act_maxpool_fwd(int precision, int activation, const voi
     }
     if (precision == RBR_PREC_BF16) {
         RBR_REQUIRE(shadow_bf16, RBR_EINVAL, "conv_fwd: bf16 precision needs the bf16 shadow table");
-        // CTA-pair / TMA-gather variant first; RBR_CONV_TC_VARIANT=1 pins the single-CTA cp.async variant (A/B timing)
-        const int variant = conv_tc_variant();
-        if (variant != 1 && pl.P2 > 0) {
+        // CTA-pair / TMA-gather kernel first, then the single-CTA cp.async kernel, then (shapes outside both) the fp32 kernel
+        const bool single_only = (flags & RBR_CONV_TC_SINGLE_CTA) != 0, pair_only = (flags & RBR_CONV_TC_PAIR_ONLY) != 0;
+        RBR_REQUIRE(!(single_only && pair_only), RBR_EINVAL, "conv_fwd: RBR_CONV_TC_SINGLE_CTA and RBR_CONV_TC_PAIR_ONLY exclude each other");
+        if (!single_only && pl.P2 > 0) {
             const int rc2 = conv_tc2_dispatch(reinterpret_cast<const __nv_bfloat16*>(shadow_bf16), vocab, (int)emb, ids, mask, gate,
                                               gate_mode, n_docs, (int)doc_len,
                                               reinterpret_cast<const __nv_bfloat16*>(pk + pl.off_umma2), bias, (int)filters,
                                               (int)ksize, (int)pad, activation, feat, argmax, preact, (int)feat_ld, s);
             if (rc2 != RBR_EUNSUPPORTED) return rc2;
-            RBR_REQUIRE(variant != 2, RBR_EUNSUPPORTED, "conv_fwd[bf16]: shape outside the CTA-pair variant");
         }
-        RBR_REQUIRE(variant != 2, RBR_EUNSUPPORTED, "conv_fwd[bf16]: shape outside the CTA-pair variant");
-        return conv_tc_dispatch(reinterpret_cast<const __nv_bfloat16*>(shadow_bf16), vocab, (int)emb, ids, mask, gate, gate_mode,
-                                n_docs, (int)doc_len, reinterpret_cast<const __nv_bfloat16*>(pk + pl.off_umma), pk + pl.off_zero,
-                                bias, (int)filters, (int)ksize, (int)pad, activation, feat, argmax, preact, (int)feat_ld, s);
+        RBR_REQUIRE(!pair_only, RBR_EUNSUPPORTED, "conv_fwd[bf16]: shape outside the CTA-pair variant");
+        if (pl.P > 0) {
+            const int rc1 = conv_tc_dispatch(reinterpret_cast<const __nv_bfloat16*>(shadow_bf16), vocab, (int)emb, ids, mask, gate,
+                                             gate_mode, n_docs, (int)doc_len, reinterpret_cast<const __nv_bfloat16*>(pk + pl.off_umma),
+                                             pk + pl.off_zero, bias, (int)filters, (int)ksize, (int)pad, activation, feat, argmax,
+                                             preact, (int)feat_ld, s);
+            if (rc1 != RBR_EUNSUPPORTED) return rc1;
+        }
+        RBR_REQUIRE(!single_only && table, RBR_EUNSUPPORTED, "conv_fwd[bf16]: shape outside the tensor-core kernels (%s)", rbr_last_error());
+        static bool warned = false;
+        if (!warned) {
+            warned = true;
+            fprintf(stderr, "rbr_b200: conv shape (emb %lld, filters %lld, k %lld, doc_len %lld) is outside the tensor-core kernels; "
+                            "using the fp32 kernel for it\n", (long long)emb, (long long)filters, (long long)ksize, (long long)doc_len);
+        }
+        return conv_fp32_dispatch(reinterpret_cast<const float*>(table), vocab, (int)emb, ids, mask, gate, gate_mode, n_docs,
+                                  (int)doc_len, reinterpret_cast<const float*>(pk + pl.off_keh), (int)pl.Hpad4, bias,
+                                  (int)filters, (int)ksize, (int)pad, activation, feat, argmax, preact, (int)feat_ld, s);
     }
     set_error("conv_fwd: unknown precision %d", precision);
     return RBR_EINVAL;

@@ -19,20 +19,12 @@
 
 namespace rbr {
 
-// conv_bwd_short.cu: per-document formulation for short documents (weight + bias + table gradient in one kernel)
-bool conv_bwd_short_ok(int E, int H, int K, int L, int gate_mode, int64_t vocab);
-int conv_bwd_short_dispatch(bool bf16, const float* table, const __nv_bfloat16* shadow, int emb_pad, int64_t vocab, int E,
-                            const int64_t* ids, const uint8_t* mask, int64_t n_docs, int L, int H, int K, int pad,
-                            int64_t padding_idx, const float* feat, const int32_t* argmax, const float* feat_grad, int feat_ld,
-                            int act, const float* whke, int epad4, int do_weight, int do_table, float* dw_hke, float* bias_grad,
-                            float* table_grad, cudaStream_t s);
-
 // ---- entries: key (token id or -1) and coefficient per (doc, filter, tap) ------------------------------
 __global__ void __launch_bounds__(256) conv_bwd_entries_kernel(
-    const int64_t* __restrict__ ids, const uint8_t* __restrict__ mask, int64_t n_docs, int L, int H, int K, int pad,
+    const IdView ids, const uint8_t* __restrict__ mask, int64_t n_docs, int L, int H, int K, int pad,
     int64_t vocab, int64_t padding_idx, const float* __restrict__ feat, const int32_t* __restrict__ argmax,
     const float* __restrict__ feat_grad, int feat_ld, int act, const float* __restrict__ gate, int gate_mode,
-    const float* __restrict__ preact, const float* __restrict__ bias, float* __restrict__ gate_grad,
+    const float* __restrict__ pool_raw, float* __restrict__ gate_grad,
     int32_t* __restrict__ keys, float* __restrict__ coef) {
     const int64_t total = n_docs * H * K;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -46,16 +38,18 @@ __global__ void __launch_bounds__(256) conv_bwd_entries_kernel(
         const int ts = argmax[n * feat_ld + h];
         const int t = ts + j - pad;
         if (gate_mode) {
-            // y = gate * conv_nobias(x) + bias  →  d/d gate = g * (preact - bias) / gate;  d/d x, d/d W scale by gate
+            // y = gate * conv_nobias(x) + bias, pool_raw = gate * conv_nobias(x)  →  d/d gate = g * pool_raw / gate (no
+            // cancellation; a gate that saturated to exactly 0 contributes 0: its own derivative gate*(1-gate) is 0 downstream);
+            // d/d x and d/d W scale by the gate
             const int64_t gi = gate_mode == 1 ? n * L + ts : n;
             const float gv = gate[gi];
-            if (j == 0 && gate_grad && g != 0.f) atomicAdd(gate_grad + gi, g * (preact[n * feat_ld + h] - bias[h]) / gv);
+            if (j == 0 && gate_grad && g != 0.f && gv != 0.f) atomicAdd(gate_grad + gi, g * (pool_raw[n * feat_ld + h] / gv));
             g *= gv;
         }
         int32_t key = -1;
-        if (g != 0.f && t >= 0 && t < L && (!mask || mask[n * L + t])) {
-            const int64_t id = ids[n * L + t];
-            if (id >= 0 && id < vocab && id != padding_idx) key = (int32_t)id;
+        if (g != 0.f && t >= 0 && t < L) {
+            const int64_t id = ld_id(ids, n * L + t);
+            if (ld_mask(ids, mask, n * L + t, id) && id >= 0 && id < vocab && id != padding_idx) key = (int32_t)id;
         }
         keys[q] = key;
         coef[q] = g;
@@ -142,7 +136,7 @@ __global__ void __launch_bounds__(256) conv_bwd_table_kernel(const int32_t* __re
 template <int K, int NQ, bool BF16>
 __global__ void __launch_bounds__(128) conv_bwd_weight_kernel(
     const float* __restrict__ table, const __nv_bfloat16* __restrict__ shadow, int emb_pad16, int64_t vocab, int E,
-    const int64_t* __restrict__ ids, const uint8_t* __restrict__ mask, int64_t n_docs, int L, int H, int pad,
+    const IdView ids, const uint8_t* __restrict__ mask, int64_t n_docs, int L, int H, int pad,
     const float* __restrict__ feat, const int32_t* __restrict__ argmax, const float* __restrict__ feat_grad, int feat_ld,
     int act, const float* __restrict__ gate, int gate_mode, int docs_per_warp, float* __restrict__ dw_hke /* [H][K][Epad4] */,
     int epad4, float* __restrict__ bias_grad) {
@@ -180,9 +174,9 @@ __global__ void __launch_bounds__(128) conv_bwd_weight_kernel(
         for (int j = 0; j < K; ++j) {
             id_l[j] = -1;
             const int t = ts_l + j;
-            if (g_l != 0.f && t >= 0 && t < L && (!mask || mask[n * L + t])) {
-                const int64_t id = __ldg(ids + n * L + t);
-                if (id >= 0 && id < vocab) id_l[j] = id;
+            if (g_l != 0.f && t >= 0 && t < L) {
+                const int64_t id = ld_id(ids, n * L + t);
+                if (ld_mask(ids, mask, n * L + t, id) && id >= 0 && id < vocab) id_l[j] = id;
             }
         }
         const int cnt = (int)min((int64_t)32, n1 - nb);
@@ -229,7 +223,7 @@ __global__ void __launch_bounds__(128) conv_bwd_weight_kernel(
 
 // generic (any E, any K) scalar variant of the weight gradient, used when E % 4 != 0 or K is large
 __global__ void __launch_bounds__(128) conv_bwd_weight_scalar_kernel(
-    const float* __restrict__ table, int64_t vocab, int E, const int64_t* __restrict__ ids,
+    const float* __restrict__ table, int64_t vocab, int E, const IdView ids,
     const uint8_t* __restrict__ mask, int64_t n_docs, int L, int H, int K, int pad, const float* __restrict__ feat,
     const int32_t* __restrict__ argmax, const float* __restrict__ feat_grad, int feat_ld, int act,
     const float* __restrict__ gate, int gate_mode, float* __restrict__ dw_hke, int epad4, float* __restrict__ bias_grad) {
@@ -245,8 +239,8 @@ __global__ void __launch_bounds__(128) conv_bwd_weight_scalar_kernel(
     for (int j = 0; j < K; ++j) {
         const int t = ts + j;
         if (t < 0 || t >= L) continue;
-        if (mask && !mask[n * L + t]) continue;
-        const int64_t id = ids[n * L + t];
+        const int64_t id = ld_id(ids, n * L + t);
+        if (!ld_mask(ids, mask, n * L + t, id)) continue;
         if (id < 0 || id >= vocab) continue;
         for (int e = threadIdx.x; e < E; e += blockDim.x)
             atomicAdd(dw_hke + ((int64_t)h * K + j) * epad4 + e, g * table[id * E + e]);
@@ -304,25 +298,13 @@ static ConvBwdWs conv_bwd_ws(void* base, int64_t n_docs, int64_t H, int64_t K, i
     return w;
 }
 
-// 0 = generic kernels only (default), 1 = per-document kernel for short documents when the batch has >= 64 documents,
-// 2 = per-document kernel whenever the shape allows.  Initial value from RBR_BWD_SHORT.  Round-1 measurement (NARRE side,
-// 40 960 docs x 60, H=150): per-document kernel 4.0 ms vs 2.0 ms for entries + sort + weight + table — it removes the L2
-// traffic (6.5 GB → 0.26 GB) but executes 2.1 G warp instructions (2 FMAs per ~6 issued with 64-wide slices), so it stays off.
-static int g_bwd_short = -1;
-extern "C" int rbr_set_conv_bwd_short(int mode) {
-    RBR_REQUIRE(mode >= 0 && mode <= 2, RBR_EINVAL, "rbr_set_conv_bwd_short: mode must be 0, 1 or 2");
-    const int prev = g_bwd_short < 0 ? 0 : g_bwd_short;
-    g_bwd_short = mode;
-    return prev;
-}
-
 extern "C" int64_t rbr_conv_bwd_workspace_bytes(int64_t n_docs, int64_t filters, int64_t ksize, int64_t emb, int64_t vocab) {
     return conv_bwd_ws(nullptr, n_docs, filters, ksize, emb, vocab).total;
 }
 
 template <int K, bool BF16>
 static int launch_weight(int nq, dim3 grid, cudaStream_t s, const float* table, const __nv_bfloat16* shadow, int emb_pad16,
-                         int64_t vocab, int E, const int64_t* ids, const uint8_t* mask, int64_t n_docs, int L, int H, int pad,
+                         int64_t vocab, int E, IdView ids, const uint8_t* mask, int64_t n_docs, int L, int H, int pad,
                          const float* feat, const int32_t* argmax, const float* feat_grad, int feat_ld, int act,
                          const float* gate, int gate_mode, int dpw, float* dw_hke, int epad4, float* bias_grad) {
 #define RBR_W(NQ)                                                                                                     \
@@ -336,19 +318,20 @@ static int launch_weight(int nq, dim3 grid, cudaStream_t s, const float* table, 
 }
 
 extern "C" int rbr_conv_act_maxpool_bwd(int precision, int activation, const void* table, const void* shadow_bf16,
-                                        int64_t vocab, int64_t emb, const int64_t* ids, const uint8_t* mask,
+                                        int64_t vocab, int64_t emb, const void* ids_raw, const uint8_t* mask,
                                         const float* gate, int gate_mode, int64_t n_docs, int64_t doc_len,
                                         const void* packed, int64_t filters, int64_t ksize, int64_t pad, const float* feat,
-                                        const int32_t* argmax, const float* feat_grad, const float* preact, const float* bias,
+                                        const int32_t* argmax, const float* feat_grad, const float* pool_raw,
                                         int64_t feat_ld, int64_t padding_idx, float* weight_grad, float* bias_grad, float* table_grad, float* gate_grad, void* ws,
-                                        int64_t ws_bytes, void* stream) {
-    RBR_REQUIRE(table && ids && packed && feat && argmax && feat_grad, RBR_EINVAL, "conv_bwd: null pointer");
+                                        int64_t ws_bytes, int flags, void* stream) {
+    RBR_REQUIRE(table && ids_raw && packed && feat && argmax && feat_grad, RBR_EINVAL, "conv_bwd: null pointer");
+    const IdView ids = id_view(ids_raw, flags);
     RBR_REQUIRE((weight_grad != nullptr) == (bias_grad != nullptr), RBR_EINVAL, "conv_bwd: weight_grad and bias_grad go together");
     RBR_REQUIRE(weight_grad || table_grad || gate_grad, RBR_EINVAL, "conv_bwd: nothing to compute");
     const bool do_weight = weight_grad != nullptr;            // NULL weight/bias grads: only the table (+ gate) part
     const bool do_entries = table_grad != nullptr || gate_grad != nullptr;
     RBR_REQUIRE(gate_mode >= 0 && gate_mode <= 2 && (gate_mode == 0) == (gate == nullptr), RBR_EINVAL, "conv_bwd: gate / gate_mode mismatch");
-    RBR_REQUIRE(gate_mode == 0 || (preact && bias), RBR_EINVAL, "conv_bwd: a gated conv backward needs preact and bias");
+    RBR_REQUIRE(gate_mode == 0 || !gate_grad || pool_raw, RBR_EINVAL, "conv_bwd: the gate gradient of a gated conv needs pool_raw");
     RBR_REQUIRE(gate_mode != 1 || ksize == 1, RBR_EUNSUPPORTED, "conv_bwd: per-token gate needs ksize == 1");
     RBR_REQUIRE(precision == RBR_PREC_FP32 || shadow_bf16, RBR_EINVAL, "conv_bwd: bf16 precision needs the shadow table");
     RBR_REQUIRE(n_docs >= 0 && doc_len > 0 && filters > 0 && ksize > 0 && emb > 0, RBR_EINVAL, "conv_bwd: bad sizes");
@@ -367,33 +350,11 @@ extern "C" int rbr_conv_act_maxpool_bwd(int precision, int activation, const voi
     const int nq = ((E >> 2) + 31) / 32;
 
     if (do_weight) RBR_CUDA(cudaMemsetAsync(w.dw_hke, 0, (size_t)H * K * epad4 * 4, s));
-    // short documents (NARRE's 60-token reviews): the per-document kernel does weight, bias and table gradient in one pass
-    if (g_bwd_short < 0) {
-        const char* e_ = getenv("RBR_BWD_SHORT");
-        g_bwd_short = (e_ && e_[0] >= '0' && e_[0] <= '2') ? e_[0] - '0' : 0;
-    }
-    if (g_bwd_short != 0 && vec && !gate_grad && conv_bwd_short_ok(E, H, K, L, gate_mode, vocab) && (n_docs >= 64 || g_bwd_short == 2) &&
-        (!table_grad || (uintptr_t)table_grad % 16 == 0)) {
-        const int rc = conv_bwd_short_dispatch(precision == RBR_PREC_BF16, reinterpret_cast<const float*>(table),
-                                               reinterpret_cast<const __nv_bfloat16*>(shadow_bf16), (int)rbr_emb_pad(emb), vocab, E, ids,
-                                               mask, n_docs, L, H, K, (int)pad, padding_idx, feat, argmax, feat_grad, (int)feat_ld,
-                                               activation, whke, epad4, do_weight ? 1 : 0, table_grad ? 1 : 0, w.dw_hke, bias_grad,
-                                               table_grad, s);
-        if (rc != RBR_OK) return rc;
-        if (do_weight) {
-            const int64_t tot = (int64_t)H * E * K;
-            int blocks = (int)((tot + 255) / 256);
-            if (blocks > 148 * 4) blocks = 148 * 4;
-            conv_bwd_unpack_kernel<<<blocks, 256, 0, s>>>(w.dw_hke, H, E, K, epad4, weight_grad);
-            RBR_LAUNCH_CHECK("conv_bwd_unpack_kernel");
-        }
-        return RBR_OK;
-    }
     if (do_entries) {
         int blocks = (int)((ne + 255) / 256);
         if (blocks > 148 * 8) blocks = 148 * 8;
         conv_bwd_entries_kernel<<<blocks, 256, 0, s>>>(ids, mask, n_docs, L, H, K, (int)pad, vocab, padding_idx, feat, argmax,
-                                                       feat_grad, (int)feat_ld, activation, gate, gate_mode, preact, bias, gate_grad,
+                                                       feat_grad, (int)feat_ld, activation, gate, gate_mode, pool_raw, gate_grad,
                                                        w.keys, w.coef);
         RBR_LAUNCH_CHECK("conv_bwd_entries_kernel");
     }

@@ -29,7 +29,7 @@ __host__ __device__ constexpr int cf_xs_stride(int tm, int k) {
 
 template <int TM, int K>
 __global__ void __launch_bounds__(32 * (TM / 8)) conv_fp32_kernel(
-    const float* __restrict__ table, int64_t vocab, int E, const int64_t* __restrict__ ids,
+    const float* __restrict__ table, int64_t vocab, int E, const IdView ids,
     const uint8_t* __restrict__ mask, const float* __restrict__ gate, int gate_mode, int L,
     const float* __restrict__ keh, int Hpad4, const float* __restrict__ bias, int H, int pad, int Lout, int act,
     float* __restrict__ feat, int32_t* __restrict__ argmax, float* __restrict__ preact, int feat_ld, int TX) {
@@ -48,20 +48,12 @@ __global__ void __launch_bounds__(32 * (TM / 8)) conv_fp32_kernel(
     const int tx = tid % TX, ty = tid / TX;
     const int64_t doc = blockIdx.x;
     const int hb0 = blockIdx.y * 256;
-    const int64_t* doc_ids = ids + doc * L;
-    const uint8_t* doc_mask = mask ? mask + doc * L : nullptr;
     const bool vec = (E % 4 == 0);
 
     float best_v[8];
     int best_t[8];
 #pragma unroll
     for (int c = 0; c < 8; ++c) { best_v[c] = -INFINITY; best_t[c] = 0; }
-    float bcol[8];
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-        const int h = hb0 + tx * 8 + c;
-        bcol[c] = (active && h < H) ? bias[h] : 0.f;
-    }
     const float doc_gate = (gate_mode == 2) ? gate[doc] : 1.f;
 
     for (int t0 = 0; t0 < Lout; t0 += TM) {
@@ -69,9 +61,11 @@ __global__ void __launch_bounds__(32 * (TM / 8)) conv_fp32_kernel(
         for (int r = tid; r < XROWS; r += blockDim.x) {
             const int t = t0 - pad + r;
             int64_t src = -1;
-            if (t >= 0 && t < L && (!doc_mask || doc_mask[t])) {
-                const int64_t id = doc_ids[t];
-                if (id >= 0 && id < vocab) src = id; else note_oob();
+            if (t >= 0 && t < L) {
+                const int64_t id = ld_id(ids, doc * L + t);
+                if (ld_mask(ids, mask, doc * L + t, id)) {
+                    if (id >= 0 && id < vocab) src = id; else note_oob();
+                }
             }
             row_src[r] = src;
         }
@@ -148,8 +142,9 @@ __global__ void __launch_bounds__(32 * (TM / 8)) conv_fp32_kernel(
                     if (gate_mode == 1) g = gate[doc * L + t];
 #pragma unroll
                     for (int c = 0; c < 8; ++c) {
-                        const float v = fmaf(acc[i][c], g, bcol[c]);
-                        if (v > best_v[c]) { best_v[c] = v; best_t[c] = t; }
+                        const float v = acc[i][c] * g;                        // gate * conv_nobias(x); the bias is added after the max
+                        // `!(v <= best)`: a NaN wins and stays (torch's max_pool1d propagates NaN), ties keep the earlier position
+                        if (!(v <= best_v[c]) && !(best_v[c] != best_v[c])) { best_v[c] = v; best_t[c] = t; }
                     }
                 }
             }
@@ -175,16 +170,17 @@ __global__ void __launch_bounds__(32 * (TM / 8)) conv_fp32_kernel(
         for (int y = 1; y < TY; ++y) {
             const float v = red_v[y * HB + c];
             const int t = red_t[y * HB + c];
-            if (v > bv || (v == bv && t < bt)) { bv = v; bt = t; }
+            const bool v_nan = v != v, b_nan = bv != bv;
+            if ((v_nan && (!b_nan || t < bt)) || (!v_nan && !b_nan && (v > bv || (v == bv && t < bt)))) { bv = v; bt = t; }
         }
-        feat[doc * feat_ld + h] = act_apply(act, bv);
-        if (preact) preact[doc * feat_ld + h] = bv;
+        feat[doc * feat_ld + h] = act_apply(act, bv + bias[h]);
+        if (preact) preact[doc * feat_ld + h] = bv;                      // pool_raw: no bias
         argmax[doc * feat_ld + h] = bt;
     }
 }
 
 template <int TM, int K>
-static int launch_conv_fp32(const float* table, int64_t vocab, int E, const int64_t* ids, const uint8_t* mask,
+static int launch_conv_fp32(const float* table, int64_t vocab, int E, IdView ids, const uint8_t* mask,
                             const float* gate, int gate_mode, int64_t n_docs, int L, const float* keh, int Hpad4,
                             const float* bias, int H, int pad, int Lout, int act, float* feat, int32_t* argmax, float* preact,
                             int feat_ld, cudaStream_t s) {
@@ -211,7 +207,7 @@ static int launch_conv_fp32(const float* table, int64_t vocab, int E, const int6
     return RBR_OK;
 }
 
-int conv_fp32_dispatch(const float* table, int64_t vocab, int E, const int64_t* ids, const uint8_t* mask,
+int conv_fp32_dispatch(const float* table, int64_t vocab, int E, IdView ids, const uint8_t* mask,
                        const float* gate, int gate_mode, int64_t n_docs, int L, const float* keh, int Hpad4,
                        const float* bias, int H, int K, int pad, int act, float* feat, int32_t* argmax, float* preact, int feat_ld,
                        cudaStream_t s) {

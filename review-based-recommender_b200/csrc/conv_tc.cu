@@ -93,7 +93,7 @@ void tc_pass_split(int64_t E, int64_t H, int64_t K, int64_t* P, int64_t* Nb) {
 struct TcArgs {
     const __nv_bfloat16* shadow;
     int64_t vocab;
-    const int64_t* ids;
+    IdView ids;
     const uint8_t* mask;
     int64_t n_docs;
     const __nv_bfloat16* wpack;      // [P][K][C][Nb][8]
@@ -101,7 +101,7 @@ struct TcArgs {
     const float* bias;
     float* feat;
     int32_t* argmax;
-    float* preact;                   // optional: pooled value before the activation
+    float* preact;                   // optional pool_raw: pooled gate * conv_nobias(x), before bias and activation
     const float* gate;               // optional multiplicative gate (D-ATT): mode 1 per token (k == 1), mode 2 per doc
     int gate_mode;
     int feat_ld;
@@ -266,8 +266,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcArgs a) 
                 int64_t doc;
                 int t;
                 if (tc_row_source(p, unit, tt, my_r0 + ROWSTEP * i, a.n_docs, &doc, &t)) {
-                    id_next[i] = a.ids[doc * p.L + t];
-                    ok_next[i] = a.mask ? a.mask[doc * p.L + t] : (uint8_t)1;
+                    id_next[i] = ld_id(a.ids, doc * p.L + t);
+                    ok_next[i] = ld_mask(a.ids, a.mask, doc * p.L + t, id_next[i]) ? (uint8_t)1 : (uint8_t)0;
                 }
             }
         };
@@ -372,9 +372,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcArgs a) 
                     if (doc < a.n_docs && h0 + c < p.H) {
                         const float raw = __uint_as_float(ord2f((uint32_t)(key >> 32)));
                         const int tbest = (int)(0xFFFFFFFFu - (uint32_t)key);
-                        const float pre = (a.gate_mode == 2 ? raw * a.gate[doc] : raw) + bias_s[c];   // per-doc gate > 0: monotone
-                        a.feat[doc * a.feat_ld + h0 + c] = act_apply(p.act, pre);
-                        if (a.preact) a.preact[doc * a.feat_ld + h0 + c] = pre;
+                        const float gated = a.gate_mode == 2 ? raw * a.gate[doc] : raw;                 // per-doc gate > 0: monotone
+                        a.feat[doc * a.feat_ld + h0 + c] = act_apply(p.act, gated + bias_s[c]);
+                        if (a.preact) a.preact[doc * a.feat_ld + h0 + c] = gated;                       // pool_raw: no bias
                         a.argmax[doc * a.feat_ld + h0 + c] = tbest;
                     }
                 }
@@ -451,7 +451,7 @@ static bool tc_make_plan(int E, int H, int K, int L, int pad, int act, int64_t n
     return true;
 }
 
-int conv_tc_dispatch(const __nv_bfloat16* shadow, int64_t vocab, int E, const int64_t* ids, const uint8_t* mask,
+int conv_tc_dispatch(const __nv_bfloat16* shadow, int64_t vocab, int E, IdView ids, const uint8_t* mask,
                      const float* gate, int gate_mode, int64_t n_docs, int L, const __nv_bfloat16* umma_w, const void* zero_row,
                      const float* bias, int H, int K, int pad, int act, float* feat, int32_t* argmax, float* preact, int feat_ld,
                      cudaStream_t s) {

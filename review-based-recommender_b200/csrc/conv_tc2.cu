@@ -80,7 +80,7 @@ void tc2_pass_split(int64_t E, int64_t H, int64_t K, int64_t* P, int64_t* Nb) {
 
 struct Tc2Args {
     int64_t vocab;
-    const int64_t* ids;
+    IdView ids;
     const uint8_t* mask;
     int64_t n_docs;
     const __nv_bfloat16* wpack;      // [P][2][K][C][NL][8]
@@ -248,8 +248,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const Tc2Args a) {
                 int64_t doc;
                 int t;
                 if (t2_row_source(p, unit, tt, r, a.n_docs, &doc, &t)) {
-                    id_next[i] = a.ids[doc * p.L + t];
-                    ok_next[i] = a.mask ? a.mask[doc * p.L + t] : (uint8_t)1;
+                    id_next[i] = ld_id(a.ids, doc * p.L + t);
+                    ok_next[i] = ld_mask(a.ids, a.mask, doc * p.L + t, id_next[i]) ? (uint8_t)1 : (uint8_t)0;
                 }
             }
         };
@@ -392,9 +392,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const Tc2Args a) {
                     if (unit < p.n_units && doc < a.n_docs && h0 + c < p.H) {
                         const float raw_v = __uint_as_float(ord2f((uint32_t)(key >> 32)));
                         const int tbest = (int)(0xFFFFFFFFu - (uint32_t)key);
-                        const float pre = (a.gate_mode == 2 ? raw_v * a.gate[doc] : raw_v) + bias_s[c];   // per-doc gate > 0: monotone
-                        a.feat[doc * a.feat_ld + h0 + c] = act_apply(p.act, pre);
-                        if (a.preact) a.preact[doc * a.feat_ld + h0 + c] = pre;
+                        const float gated = a.gate_mode == 2 ? raw_v * a.gate[doc] : raw_v;                 // per-doc gate > 0: monotone
+                        a.feat[doc * a.feat_ld + h0 + c] = act_apply(p.act, gated + bias_s[c]);
+                        if (a.preact) a.preact[doc * a.feat_ld + h0 + c] = gated;                           // pool_raw: no bias
                         a.argmax[doc * a.feat_ld + h0 + c] = tbest;
                     }
                 }
@@ -518,7 +518,7 @@ static int tc2_launch(const CUtensorMap& tm, const Tc2Args& a, cudaStream_t s) {
 }
 
 // returns RBR_EUNSUPPORTED (without setting an error message the caller must surface) when the shape is outside this variant
-int conv_tc2_dispatch(const __nv_bfloat16* shadow, int64_t vocab, int E, const int64_t* ids, const uint8_t* mask,
+int conv_tc2_dispatch(const __nv_bfloat16* shadow, int64_t vocab, int E, IdView ids, const uint8_t* mask,
                       const float* gate, int gate_mode, int64_t n_docs, int L, const __nv_bfloat16* umma_w2, const float* bias,
                       int H, int K, int pad, int act, float* feat, int32_t* argmax, float* preact, int feat_ld, cudaStream_t s) {
     Tc2Args a{};

@@ -80,14 +80,15 @@ __global__ void __launch_bounds__(HD_WARPS * 32) head_fwd_kernel(
         }
         __syncwarp();
     }
-    if (ratings && loss_sum && lane == 0 && loss_acc != 0.f) atomicAdd(loss_sum, loss_acc);
+    if (ratings && loss_sum && lane == 0 && loss_acc != 0.f) atomicAdd(loss_sum, loss_acc * grad_scale);
 }
 
 __global__ void __launch_bounds__(HD_WARPS * 32) head_bwd_kernel(
     const float* __restrict__ u_text, const float* __restrict__ i_text, const int64_t* __restrict__ u_id,
     const int64_t* __restrict__ i_id, int64_t B, int H, int K, const float* __restrict__ Wu, const float* __restrict__ Wi,
     const float* __restrict__ fm_h, const float* __restrict__ u_lat, const float* __restrict__ i_lat, float drop_p,
-    uint64_t drop_seed, const uint64_t* __restrict__ drop_seed_dev, int64_t padding_idx, int64_t users, int64_t items, const float* __restrict__ pred_grad,
+    uint64_t drop_seed, const uint64_t* __restrict__ drop_seed_dev, int64_t pad_eu, int64_t pad_ei, int64_t pad_bu, int64_t pad_bi,
+    int64_t users, int64_t items, const float* __restrict__ pred_grad,
     float* __restrict__ u_text_grad, float* __restrict__ i_text_grad, float* __restrict__ Wu_grad, float* __restrict__ bu_grad,
     float* __restrict__ ebd_u_grad, float* __restrict__ Wi_grad, float* __restrict__ bi_grad, float* __restrict__ ebd_i_grad,
     float* __restrict__ fm_h_grad, float* __restrict__ user_bias_grad, float* __restrict__ item_bias_grad,
@@ -122,8 +123,9 @@ __global__ void __launch_bounds__(HD_WARPS * 32) head_bwd_kernel(
                 for (int h = lane; h < H; h += 32) { xu_s[s * H + h] = u_text[b * H + h]; xi_s[s * H + h] = i_text[b * H + h]; }
                 const float gp = pred_grad[b];
                 const int64_t uid = u_id[b], iid = i_id[b];
-                const bool u_row = uid >= 0 && uid < users && uid != padding_idx;
-                const bool i_row = iid >= 0 && iid < items && iid != padding_idx;
+                const bool u_ok = uid >= 0 && uid < users, i_ok = iid >= 0 && iid < items;
+                const bool u_row = u_ok && uid != pad_eu, i_row = i_ok && iid != pad_ei;        // LastFeat.ebd padding rows
+                const bool ub_row = u_ok && uid != pad_bu, ib_row = i_ok && iid != pad_bi;      // FM.user_bias / item_bias padding rows
 #pragma unroll
                 for (int q = 0; q < HD_KQ; ++q) {
                     const int kk = lane + 32 * q;
@@ -143,8 +145,8 @@ __global__ void __launch_bounds__(HD_WARPS * 32) head_bwd_kernel(
                 }
                 if (lane == 0) {
                     dgb += gp;
-                    if (u_row) atomicAdd(user_bias_grad + uid, gp);
-                    if (i_row) atomicAdd(item_bias_grad + iid, gp);
+                    if (ub_row) atomicAdd(user_bias_grad + uid, gp);
+                    if (ib_row) atomicAdd(item_bias_grad + iid, gp);
                 }
             } else {
                 for (int h = lane; h < H; h += 32) { xu_s[s * H + h] = 0.f; xi_s[s * H + h] = 0.f; }
@@ -194,9 +196,30 @@ __global__ void __launch_bounds__(HD_WARPS * 32) head_bwd_kernel(
     if (lane == 0 && dgb != 0.f) atomicAdd(g_bias_grad, dgb);
 }
 
+// test / debug aid: the keep-scale both kernels apply, keep[b,k] in {0, 1/(1-p)}
+__global__ void head_dropout_mask_kernel(int64_t B, int K, float drop_p, uint64_t drop_seed, const uint64_t* __restrict__ drop_seed_dev,
+                                         float* __restrict__ keep) {
+    if (drop_seed_dev) drop_seed += *drop_seed_dev;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < B * K; q += stride)
+        keep[q] = keep_scale(drop_p, drop_seed, q / K, K, (int)(q % K));
+}
+
 }  // namespace rbr
 
 using namespace rbr;
+
+extern "C" int rbr_head_dropout_mask(int64_t batch, int64_t latent, float drop_p, uint64_t drop_seed, const uint64_t* drop_seed_dev,
+                                     float* keep, void* stream) {
+    RBR_REQUIRE(keep && batch >= 0 && latent > 0, RBR_EINVAL, "rbr_head_dropout_mask: bad arguments");
+    RBR_REQUIRE(drop_p >= 0.f && drop_p < 1.f, RBR_EINVAL, "rbr_head_dropout_mask: dropout p must be in [0,1)");
+    if (batch == 0) return RBR_OK;
+    int64_t blocks = (batch * latent + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    head_dropout_mask_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(batch, (int)latent, drop_p, drop_seed, drop_seed_dev, keep);
+    RBR_LAUNCH_CHECK("head_dropout_mask_kernel");
+    return RBR_OK;
+}
 
 extern "C" int rbr_head_fwd(const float* u_text, const float* i_text, const int64_t* u_id, const int64_t* i_id, int64_t batch,
                             int64_t hidden, int64_t latent, const float* Wu, const float* bu, const float* ebd_u,
@@ -227,7 +250,8 @@ extern "C" int rbr_head_fwd(const float* u_text, const float* i_text, const int6
 extern "C" int rbr_head_bwd(const float* u_text, const float* i_text, const int64_t* u_id, const int64_t* i_id, int64_t batch,
                             int64_t hidden, int64_t latent, const float* Wu, const float* Wi, const float* fm_h,
                             const float* u_lat, const float* i_lat, float drop_p, uint64_t drop_seed,
-                            const uint64_t* drop_seed_dev, int64_t padding_idx, int64_t users, int64_t items, const float* pred_grad, float* u_text_grad, float* i_text_grad, float* Wu_grad, float* bu_grad,
+                            const uint64_t* drop_seed_dev, int64_t ebd_u_padding_idx, int64_t ebd_i_padding_idx,
+                            int64_t user_bias_padding_idx, int64_t item_bias_padding_idx, int64_t users, int64_t items, const float* pred_grad, float* u_text_grad, float* i_text_grad, float* Wu_grad, float* bu_grad,
                             float* ebd_u_grad, float* Wi_grad, float* bi_grad, float* ebd_i_grad, float* fm_h_grad,
                             float* user_bias_grad, float* item_bias_grad, float* g_bias_grad, void* stream) {
     RBR_REQUIRE(u_text && i_text && u_id && i_id && Wu && Wi && fm_h && u_lat && i_lat && pred_grad && u_text_grad &&
@@ -244,8 +268,8 @@ extern "C" int rbr_head_bwd(const float* u_text, const float* i_text, const int6
     int64_t blocks = (batch + HD_BS - 1) / HD_BS;
     if (blocks > 148 * 2) blocks = 148 * 2;
     head_bwd_kernel<<<(unsigned)blocks, HD_WARPS * 32, smem, as_stream(stream)>>>(
-        u_text, i_text, u_id, i_id, batch, H, K, Wu, Wi, fm_h, u_lat, i_lat, drop_p, drop_seed, drop_seed_dev, padding_idx,
-        users, items, pred_grad, u_text_grad, i_text_grad, Wu_grad, bu_grad, ebd_u_grad, Wi_grad, bi_grad,
+        u_text, i_text, u_id, i_id, batch, H, K, Wu, Wi, fm_h, u_lat, i_lat, drop_p, drop_seed, drop_seed_dev, ebd_u_padding_idx,
+        ebd_i_padding_idx, user_bias_padding_idx, item_bias_padding_idx, users, items, pred_grad, u_text_grad, i_text_grad, Wu_grad, bu_grad, ebd_u_grad, Wi_grad, bi_grad,
         ebd_i_grad, fm_h_grad, user_bias_grad, item_bias_grad, g_bias_grad);
     RBR_LAUNCH_CHECK("head_bwd_kernel");
     return RBR_OK;

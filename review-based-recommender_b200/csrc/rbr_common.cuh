@@ -124,10 +124,30 @@ __device__ __forceinline__ float hash_uniform(uint64_t seed, uint64_t idx) {
     return (float)(z >> 40) * (1.0f / 16777216.0f);
 }
 
-__device__ __forceinline__ float act_apply(int act, float x) { return act == RBR_ACT_RELU ? fmaxf(x, 0.f) : tanhf(x); }
+// relu written as a select so that NaN propagates like torch.relu (fmaxf would return 0 for NaN)
+__device__ __forceinline__ float act_apply(int act, float x) { return act == RBR_ACT_RELU ? (x < 0.f ? 0.f : x) : tanhf(x); }
 // derivative expressed through the activation OUTPUT y (relu: y>0, tanh: 1-y^2)
 __device__ __forceinline__ float act_grad_from_out(int act, float y) {
     return act == RBR_ACT_RELU ? (y > 0.f ? 1.f : 0.f) : (1.f - y * y);
+}
+
+// token ids are int64 (torch.LongTensor) or int32 (RBR_IDS_I32: the staged input pipeline); a NULL mask means "all true"
+// or, with RBR_MASK_FROM_IDS, mask = (id != 0) — what the reference's collate_fn computes on the host (utils.py:30-42)
+struct IdView {
+    const void* p;
+    int i32;         // ids are int32
+    int mask_ids;    // NULL mask → id != 0
+};
+__host__ __device__ inline IdView id_view(const void* ids, int flags) {
+    IdView v;
+    v.p = ids; v.i32 = (flags & RBR_IDS_I32) ? 1 : 0; v.mask_ids = (flags & RBR_MASK_FROM_IDS) ? 1 : 0;
+    return v;
+}
+__device__ __forceinline__ int64_t ld_id(const IdView& v, int64_t i) {
+    return v.i32 ? (int64_t)__ldg(reinterpret_cast<const int32_t*>(v.p) + i) : __ldg(reinterpret_cast<const int64_t*>(v.p) + i);
+}
+__device__ __forceinline__ bool ld_mask(const IdView& v, const uint8_t* mask, int64_t i, int64_t id) {
+    return mask ? (__ldg(mask + i) != 0) : (v.mask_ids ? id != 0 : true);
 }
 
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }

@@ -6,10 +6,10 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from .layers import FM, LastFeat, NgramFeat, WordEmbedding, fused_head
+from .layers import FM, HotPathModule, LastFeat, NgramFeat, WordEmbedding, fused_head
 
 
-class DeepCoNNpp(nn.Module):
+class DeepCoNNpp(HotPathModule):
     def __init__(self, user_size, item_size, vocab_size, kernel_sizes, embedding_dim, hidden_dim, latent_dim, doc_len,
                  pretrained_embeddings, dropout, arch="CNN", precision=None):
         super().__init__()
@@ -39,8 +39,20 @@ class DeepCoNNpp(nn.Module):
         self.ngram.conv.invalidate_operand_cache()
 
     def forward(self, u_revs, i_revs, u_rev_masks, i_rev_masks, u_ids, i_ids):
-        """u_revs/i_revs [bz, doc_len] int64, masks [bz, doc_len] bool, ids [bz] int64 → preds [bz]."""
+        """u_revs/i_revs [bz, doc_len] int64 (or int32: the staged input pipeline), masks [bz, doc_len] bool (None: derived on
+        the device as ids != 0, which is what collate_fn computes, utils.py:30-42), ids [bz] int64 → preds [bz]."""
         arena = self._new_arena()
         u_rev_feats, i_rev_feats = self.ngram.encode(self.word_embeddings, [u_revs, i_revs], [u_rev_masks, i_rev_masks])
         preds = fused_head(self.user_feat, self.item_feat, self.fm, u_rev_feats, i_rev_feats, u_ids, i_ids, self.training, arena)
+        self._after_forward()
         return preds.view(u_revs.shape[0])
+
+    def forward_loss(self, u_revs, i_revs, u_rev_masks, i_rev_masks, u_ids, i_ids, ratings):
+        """forward + nn.MSELoss() in the head kernel's launch (trainer/train_deepconn_pp.py:162-164 as one call):
+        returns (loss, preds); `loss.backward()` as usual."""
+        arena = self._new_arena()
+        u_rev_feats, i_rev_feats = self.ngram.encode(self.word_embeddings, [u_revs, i_revs], [u_rev_masks, i_rev_masks])
+        loss, preds = fused_head(self.user_feat, self.item_feat, self.fm, u_rev_feats, i_rev_feats, u_ids, i_ids, self.training,
+                                 arena, ratings=ratings)
+        self._after_forward()
+        return loss, preds.view(u_revs.shape[0])

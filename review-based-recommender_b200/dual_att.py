@@ -10,7 +10,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from .layers import WordEmbedding, default_precision
+from .layers import HotPathModule, WordEmbedding, default_precision
 
 
 class LocalAttention(nn.Module):
@@ -42,7 +42,7 @@ class GlobalAttention(nn.Module):
         raise RuntimeError("rbr_b200.GlobalAttention is a parameter holder: DualAtt runs the fused gated encoder")
 
 
-class DualAtt(nn.Module):
+class DualAtt(HotPathModule):
     def __init__(self, vocab_size, doc_len, l_window_size=5, l_out_size=200, g_out_size=100, emb_size=100,
                  hidden_size_1=500, hidden_size_2=50, dropout=0.5, pretrained_embeddings=None, precision=None):
         super().__init__()
@@ -92,4 +92,5 @@ class DualAtt(nn.Module):
         u_cat, i_cat = self.encode([u_docs, i_docs], ["u", "i"], arena)
         u_feat = self.fc(u_cat)                                                                   # dual_att.py:49-51
         i_feat = self.fc(i_cat)                                                                   # dual_att.py:55-57
+        self._after_forward()
         return torch.sum(torch.mul(u_feat, i_feat), 1).view(-1)                                   # dual_att.py:59-61

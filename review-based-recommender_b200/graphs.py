@@ -28,7 +28,8 @@ import torch
 class GraphedTrainStep:
     def __init__(self, model: torch.nn.Module, loss_fn: Callable, example_batch: Sequence[torch.Tensor],
                  example_ratings: torch.Tensor, restage_operands: bool = True, warmup: int = 3,
-                 pool=None, device: Optional[torch.device] = None, post_backward: Optional[Callable[[], None]] = None):
+                 pool=None, device: Optional[torch.device] = None, post_backward: Optional[Callable[[], None]] = None,
+                 fuse_mse: bool = True):
         dev = device or next(model.parameters()).device
         if dev.type != "cuda":
             raise RuntimeError("GraphedTrainStep needs the model on a CUDA device")
@@ -36,13 +37,13 @@ class GraphedTrainStep:
         self.post_backward = post_backward      # e.g. lambda: parallel.allreduce_gradients(model) — captured with the step
         self.static_batch = [torch.empty(t.shape, dtype=t.dtype, device=dev) for t in example_batch]
         self.static_ratings = torch.empty(example_ratings.shape, dtype=example_ratings.dtype, device=dev)
-        fm = getattr(model, "fm", None)
-        self._seed_dev = None
-        if fm is not None:
-            self._seed_dev = fm.__dict__.get("_rbr_seed_dev")
-            if self._seed_dev is None:
-                self._seed_dev = torch.zeros(1, dtype=torch.int64, device=dev)
-                fm.__dict__["_rbr_seed_dev"] = self._seed_dev
+        self._fm = getattr(model, "fm", None)
+        # FM dropout seed counter: attached to the model only while this object's body runs (warm-up and capture), so eager
+        # calls made between replays keep drawing fresh host seeds
+        self._seed_dev = torch.zeros(1, dtype=torch.int64, device=dev) if self._fm is not None else None
+        # nn.MSELoss() (mean) is evaluated inside the head kernel's launch when the model offers forward_loss (fused K4 + loss)
+        self.fused_loss = (fuse_mse and isinstance(loss_fn, torch.nn.MSELoss) and loss_fn.reduction == "mean"
+                           and hasattr(model, "forward_loss"))
         self.load(example_batch, example_ratings)
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
@@ -60,15 +61,23 @@ class GraphedTrainStep:
     def _body(self) -> torch.Tensor:
         if self._seed_dev is not None:
             self._seed_dev.add_(1)                       # new FM dropout mask per replay; forward and backward read the same value
-        self.model.zero_grad(set_to_none=True)
-        if self.restage and hasattr(self.model, "invalidate_operand_cache"):
-            self.model.invalidate_operand_cache()        # the parameters change between replays: re-stage bf16 shadow / packed weights
-        out = self.model(*self.static_batch)
-        pred = out[0] if isinstance(out, tuple) else out
-        loss = self.loss_fn(pred, self.static_ratings)
-        loss.backward()
-        if self.post_backward is not None:
-            self.post_backward()
+            self._fm.__dict__["_rbr_seed_dev"] = self._seed_dev
+        try:
+            self.model.zero_grad(set_to_none=True)
+            if self.restage and hasattr(self.model, "invalidate_operand_cache"):
+                self.model.invalidate_operand_cache()    # the parameters change between replays: re-stage bf16 shadow / packed weights
+            if self.fused_loss:
+                loss, _ = self.model.forward_loss(*self.static_batch, self.static_ratings)
+            else:
+                out = self.model(*self.static_batch)
+                pred = out[0] if isinstance(out, tuple) else out
+                loss = self.loss_fn(pred, self.static_ratings)
+            loss.backward()
+            if self.post_backward is not None:
+                self.post_backward()
+        finally:
+            if self._fm is not None:
+                self._fm.__dict__.pop("_rbr_seed_dev", None)
         return loss
 
     def load(self, batch: Sequence[torch.Tensor], ratings: torch.Tensor, stream: Optional[torch.cuda.Stream] = None) -> None:

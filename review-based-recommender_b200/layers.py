@@ -32,6 +32,41 @@ def default_precision() -> str:
     return p
 
 
+class HotPathModule(nn.Module):
+    """Base of the three model classes: out-of-range id detection at mode switches.
+
+    The kernels read an id outside its table as a padding (zero) row and count it instead of faulting; the reference raises
+    IndexError (CPU) or trips a device assert (CUDA).  Reading the counter synchronises the stream, so it is polled where
+    the trainers switch mode — `model.train()` at the start of an epoch, `model.eval()` before validation
+    (trainer/train_deepconn_pp.py:149,196) — never inside a step or a CUDA-graph capture; RBR_CHECK_IDS=1 polls after every
+    forward (debugging)."""
+
+    def check_ids(self) -> None:
+        prm = next(self.parameters(), None)
+        if prm is None or not prm.is_cuda or torch.cuda.is_current_stream_capturing():
+            return
+        from ._lib import lib
+        with torch.cuda.device(prm.device):
+            n = lib.rbr_consume_oob_count(ops._stream(True))
+        if n < 0:
+            lib.check(n, "rbr_consume_oob_count")
+        if n > 0:
+            raise IndexError(f"rbr_b200: {n} token / id values outside their embedding tables since the last check "
+                             "(they were read as padding rows); check vocab_size / user_size / item_size against the data")
+
+    def train(self, mode: bool = True):
+        super().train(mode)
+        self.check_ids()
+        return self
+
+    def _after_forward(self):
+        if _CHECK_IDS_EVERY_FORWARD:
+            self.check_ids()
+
+
+_CHECK_IDS_EVERY_FORWARD = os.environ.get("RBR_CHECK_IDS", "0") == "1"
+
+
 class WordEmbedding(nn.Module):
     def __init__(self, vocab_size, embedding_dim, pretrained_embeddings=None, padding_idx=0, freeze_embeddings=False):
         super().__init__()
@@ -112,6 +147,7 @@ class NgramFeat(nn.Module):
         self.precision = precision or default_precision()
         self._arena = None
         self.table_grad_hook = None     # called with the word-table gradient buffer once it is complete (parallel.py)
+        self.conv_flags = 0             # ops.CONV_* kernel-selection flags passed with every call (tests, A/B timing)
 
     @property
     def conv(self) -> MyConv1d:
@@ -136,6 +172,8 @@ class NgramFeat(nn.Module):
             "bias_params": [c.bias for c in convs],
             "padding_idx": -1 if word_embeddings.padding_idx is None else word_embeddings.padding_idx,
             "table_ready": self.table_grad_hook,
+            "flags": self.conv_flags,
+            "mask_from_ids": True,      # a side passed without a mask: mask = (ids != 0), what collate_fn computes (utils.py:30-42)
         }
         flat = []
         for ids, m in zip(sides, masks):
@@ -157,7 +195,7 @@ class NgramFeat(nn.Module):
             "pads": [(k - 1) // 2 for k in conv.kernel_sizes],
             "shadow_fn": lambda: ops.table_to_bf16(x.detach()), "pack_fn": conv.packed, "arena": self._arena,
             "table_param": x, "weight_params": [c.weight for c in convs], "bias_params": [c.bias for c in convs],
-            "padding_idx": -1,
+            "padding_idx": -1, "flags": self.conv_flags,
         }
         (feat,) = ops.EncodeDocsFn.apply(x, cfg, *[c.weight for c in convs], *[c.bias for c in convs], ids, input_masks)
         return feat.view(bz, self.out_features, 1)
@@ -192,6 +230,7 @@ class FM(nn.Module):
         self.item_bias = nn.Embedding(item_size, 1, padding_idx=item_padding_idx)
         self.g_bias = nn.Parameter(torch.Tensor(1))
         self.padding_idx = user_padding_idx
+        self.item_padding_idx = item_padding_idx
         self.reset_parameters()
 
     def reset_parameters(self):
@@ -205,20 +244,26 @@ class FM(nn.Module):
         """Standalone convenience (the models run the fused K4 instead)."""
         fm = self.dropout(torch.relu(u_feat * i_feat))
         ub = ops.EmbeddingFn.apply(self.user_bias.weight, u_id, self.padding_idx, None)
-        ib = ops.EmbeddingFn.apply(self.item_bias.weight, i_id, self.padding_idx, None)
+        ib = ops.EmbeddingFn.apply(self.item_bias.weight, i_id, self.item_padding_idx, None)
         return fm @ self.h + ub + ib + self.g_bias
 
 
-def fused_head(user_feat: LastFeat, item_feat: LastFeat, fm: FM, u_text, i_text, u_id, i_id, training: bool, arena):
-    """K4: LastFeat(user) + LastFeat(item) + FM in one kernel (reference deepconn.py:48-51)."""
+def fused_head(user_feat: LastFeat, item_feat: LastFeat, fm: FM, u_text, i_text, u_id, i_id, training: bool, arena,
+               ratings: Optional[torch.Tensor] = None):
+    """K4: LastFeat(user) + LastFeat(item) + FM in one kernel (reference deepconn.py:48-51).  With `ratings` the same launch
+    also evaluates nn.MSELoss (trainer/train_deepconn_pp.py:140,164) and returns (loss, pred)."""
     p = fm.dropout.p if training else 0.0
-    # dropout mask seed: a fresh host value per call, or — inside a captured CUDA graph (graphs.GraphedTrainStep) — a fixed
+    # dropout mask seed: a fresh host value per call, or — inside graphs.GraphedTrainStep's body (warm-up and capture) — a fixed
     # base plus a step counter that lives on the device and is bumped at the start of every replay
     seed_dev = fm.__dict__.get("_rbr_seed_dev") if p > 0 else None
     seed = 0 if p <= 0 else (0x5EED if seed_dev is not None else int(torch.randint(0, 2 ** 62, (1,)).item()))
     params = [user_feat.W, user_feat.b, user_feat.ebd.weight, item_feat.W, item_feat.b, item_feat.ebd.weight, fm.h,
               fm.user_bias.weight, fm.item_bias.weight, fm.g_bias]
-    return ops.HeadFn.apply(u_text, i_text, u_id, i_id, *params, p, seed, fm.padding_idx, arena, params, seed_dev)
+    pads = (user_feat.padding_idx, item_feat.padding_idx, fm.padding_idx, fm.item_padding_idx)
+    fm.__dict__["_rbr_last_drop"] = (p, seed, seed_dev)          # for tests: ops.head_dropout_mask(B, K, *this)
+    if ratings is not None:
+        return ops.HeadLossFn.apply(u_text, i_text, u_id, i_id, ratings, *params, p, seed, pads, arena, params, seed_dev)
+    return ops.HeadFn.apply(u_text, i_text, u_id, i_id, *params, p, seed, pads, arena, params, seed_dev)
 
 
 class LinearAttention(nn.Module):

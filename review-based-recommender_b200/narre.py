@@ -6,10 +6,10 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from .layers import FM, LastFeat, LinearAttention, NgramFeat, WordEmbedding, fused_head
+from .layers import FM, HotPathModule, LastFeat, LinearAttention, NgramFeat, WordEmbedding, fused_head
 
 
-class NARRE(nn.Module):
+class NARRE(HotPathModule):
     def __init__(self, user_size, item_size, vocab_size, kernel_sizes, hidden_dim, embedding_dim, att_dim, latent_dim,
                  max_doc_num, max_doc_len, dropout, word_padding_idx, user_padding_idx, item_padding_idx,
                  pretrained_embeddings, arch, precision=None):
@@ -45,31 +45,45 @@ class NARRE(nn.Module):
         self.word_embeddings.invalidate_operand_cache()
         self.ngram.conv.invalidate_operand_cache()
 
-    def forward(self, u_text, i_text, u_text_masks, i_text_masks, u_id, i_id, reuid, reiid):
-        """u_text/i_text [bz, R, T] int64, masks [bz, R, T] bool, ids [bz], reuid/reiid [bz, R] →
-        (pred [bz], u_att_scores [bz, R, 1], i_att_scores [bz, R, 1])."""
-        arena = self._new_arena()
+    def _encode_attend(self, u_text, i_text, u_text_masks, i_text_masks, reuid, reiid):
         bz = u_text.shape[0]
         # every review is an independent doc of length T (narre.py:170-176)
         u_docs = u_text.reshape(-1, self.doc_len)
         i_docs = i_text.reshape(-1, self.doc_len)
-        u_m = u_text_masks.reshape(-1, self.doc_len)
-        i_m = i_text_masks.reshape(-1, self.doc_len)
+        u_m = None if u_text_masks is None else u_text_masks.reshape(-1, self.doc_len)
+        i_m = None if i_text_masks is None else i_text_masks.reshape(-1, self.doc_len)
         u_feat, i_feat = self.ngram.encode(self.word_embeddings, [u_docs, i_docs], [u_m, i_m])
         u_feat = u_feat.view(bz, self.doc_num, self.hiddem_dim)
         i_feat = i_feat.view(bz, self.doc_num, self.hiddem_dim)
-        # the user-side and item-side attentions are independent, latency-bound kernels (one warp per sample): the item side
-        # runs on an auxiliary stream, forward and (because autograd replays each node on its forward stream) backward
-        if u_feat.is_cuda:
-            main = torch.cuda.current_stream()
-            aux = ops._side_streams(u_feat.device, 1)[0]
-            aux.wait_stream(main)
-            with torch.cuda.stream(aux):
-                i_feat, i_att_scores = self.item_att(i_feat, reiid)    # narre.py:185
-            u_feat, u_att_scores = self.user_att(u_feat, reuid)        # narre.py:184
-            main.wait_stream(aux)
-        else:
-            u_feat, u_att_scores = self.user_att(u_feat, reuid)
-            i_feat, i_att_scores = self.item_att(i_feat, reiid)
+        # the user-side and item-side attentions are independent, latency-bound kernels: the item side runs on an auxiliary
+        # stream, forward and (because autograd replays each node on its forward stream) backward
+        main = torch.cuda.current_stream()
+        aux = ops._side_streams(u_feat.device, 1)[0]
+        aux.wait_stream(main)
+        with torch.cuda.stream(aux):
+            i_feat, i_att_scores = self.item_att(i_feat, reiid)    # narre.py:185
+        u_feat, u_att_scores = self.user_att(u_feat, reuid)        # narre.py:184
+        main.wait_stream(aux)
+        # allocated on the auxiliary stream, consumed (and possibly freed) on the main one: tell the caching allocator
+        i_feat.record_stream(main)
+        i_att_scores.record_stream(main)
+        return u_feat, i_feat, u_att_scores, i_att_scores
+
+    def forward(self, u_text, i_text, u_text_masks, i_text_masks, u_id, i_id, reuid, reiid):
+        """u_text/i_text [bz, R, T] int64 (or int32), masks [bz, R, T] bool (None: ids != 0), ids [bz], reuid/reiid [bz, R] →
+        (pred [bz], u_att_scores [bz, R, 1], i_att_scores [bz, R, 1])."""
+        arena = self._new_arena()
+        u_feat, i_feat, u_att_scores, i_att_scores = self._encode_attend(u_text, i_text, u_text_masks, i_text_masks, reuid, reiid)
         pred = fused_head(self.user_feat, self.item_feat, self.fm, u_feat, i_feat, u_id, i_id, self.training, arena)
+        self._after_forward()
         return pred.view(-1), u_att_scores, i_att_scores
+
+    def forward_loss(self, u_text, i_text, u_text_masks, i_text_masks, u_id, i_id, reuid, reiid, ratings):
+        """forward + nn.MSELoss() in the head kernel's launch (trainer/train_narre.py:165-167 as one call):
+        returns (loss, (pred, u_att_scores, i_att_scores))."""
+        arena = self._new_arena()
+        u_feat, i_feat, u_att_scores, i_att_scores = self._encode_attend(u_text, i_text, u_text_masks, i_text_masks, reuid, reiid)
+        loss, pred = fused_head(self.user_feat, self.item_feat, self.fm, u_feat, i_feat, u_id, i_id, self.training, arena,
+                                ratings=ratings)
+        self._after_forward()
+        return loss, (pred.view(-1), u_att_scores, i_att_scores)

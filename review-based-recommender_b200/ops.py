@@ -15,6 +15,8 @@ from ._lib import lib
 PREC_FP32, PREC_BF16 = 0, 1
 ACT_RELU, ACT_TANH = 0, 1
 _PREC = {"fp32": PREC_FP32, "bf16": PREC_BF16}
+# per-call `flags` of the conv entry points (include/rbr_b200.h)
+CONV_TC_SINGLE_CTA, CONV_TC_PAIR_ONLY, CONV_BWD_DENSE_TC, CONV_BWD_SPARSE, IDS_I32, MASK_FROM_IDS = 1, 2, 4, 8, 16, 32
 
 
 _STREAM_CACHE = [0, None]
@@ -55,6 +57,19 @@ def _req(t: torch.Tensor, dtype, name: str) -> torch.Tensor:
     return t if t.is_contiguous() else t.contiguous()
 
 
+def _ids(t: torch.Tensor, name: str) -> torch.Tensor:
+    """Token ids: int64 (torch.LongTensor, what the reference's collate_fn yields) or int32 (staged input pipeline)."""
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError(f"rbr_b200: `{name}` must be a CUDA tensor (the hot path has no CPU implementation)")
+    if t.dtype not in (torch.int64, torch.int32):
+        raise TypeError(f"rbr_b200: `{name}` must be int64 or int32, got {t.dtype}")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _id_flags(ids: torch.Tensor, mask: Optional[torch.Tensor], mask_from_ids: bool) -> int:
+    return (IDS_I32 if ids.dtype == torch.int32 else 0) | (MASK_FROM_IDS if (mask is None and mask_from_ids) else 0)
+
+
 def _mask_u8(mask: Optional[torch.Tensor], name: str) -> Optional[torch.Tensor]:
     if mask is None:
         return None
@@ -91,6 +106,7 @@ class GradArena:
         self.flat: Optional[torch.Tensor] = None
         self.device = None
         self.external: Optional[torch.Tensor] = None
+        self.params = named_params
 
     @staticmethod
     def signature_of(named_params) -> tuple:
@@ -120,6 +136,14 @@ class GradArena:
         if self.flat is None:
             ext = self.external
             if ext is not None:          # persistent buffer (symmetric memory for the NVLS all-reduce): re-zeroed, not re-allocated
+                lo, hi = ext.data_ptr(), ext.data_ptr() + ext.numel() * 4
+                for name, prm in self.params:
+                    g = prm.grad
+                    if g is not None and lo <= g.data_ptr() < hi:
+                        raise RuntimeError(
+                            f"rbr_b200: `{name}.grad` still aliases the persistent (NVLS symmetric-memory) gradient arena, which "
+                            "is re-zeroed by every backward: call zero_grad(set_to_none=True) before each step — gradient "
+                            "accumulation over micro-batches is not supported with enable_nvls_allreduce")
                 self.flat = ext[:self.total]
                 self.flat.zero_()
             else:
@@ -227,17 +251,19 @@ class EncodeDocsFn(torch.autograd.Function):
         n_conv = cfg["n_conv"]
         weights, biases = rest[:n_conv], rest[n_conv:2 * n_conv]
         sides = rest[2 * n_conv:]
-        ids_l = [_req(t, torch.int64, "token ids") for t in sides[0::2]]
+        ids_l = [_ids(t, "token ids") for t in sides[0::2]]
         mask_l = [_mask_u8(m, "token mask") for m in sides[1::2]]
         table = _req(table, torch.float32, "embedding table")
         prec = _PREC[cfg["precision"]]
+        mfi = bool(cfg.get("mask_from_ids", False))
+        flags_l = [cfg.get("flags", 0) | _id_flags(i, m, mfi) for i, m in zip(ids_l, mask_l)]
         act, pads = cfg["act"], cfg["pads"]
         vocab, emb = table.shape
         shadow = cfg["shadow_fn"]() if prec == PREC_BF16 else None
         packed = [cfg["pack_fn"](i) for i in range(n_conv)]
         h_total = sum(w.shape[0] for w in weights)
         feats, argmaxes = [], []
-        for ids, mask in zip(ids_l, mask_l):
+        for ids, mask, fl in zip(ids_l, mask_l, flags_l):
             doc_len = ids.shape[-1]
             n_docs = ids.numel() // doc_len
             if mask is not None and mask.numel() != ids.numel():
@@ -250,7 +276,7 @@ class EncodeDocsFn(torch.autograd.Function):
                 lib.check(lib.rbr_conv_act_maxpool_fwd(
                     prec, act, _p(table), _p(shadow), vocab, emb, _p(ids), _p(mask), None, 0, n_docs, doc_len, _p(pk),
                     _p(_req(b, torch.float32, "conv bias")), h, k, pad, feat.data_ptr() + 4 * col, amax.data_ptr() + 4 * col,
-                    None, h_total, _stream()), "rbr_conv_act_maxpool_fwd")
+                    None, h_total, fl, _stream()), "rbr_conv_act_maxpool_fwd")
                 col += h
             feats.append(feat)
             argmaxes.append(amax)
@@ -259,6 +285,7 @@ class EncodeDocsFn(torch.autograd.Function):
         ctx.shadow, ctx.packed = shadow, packed
         ctx.save_for_backward(*ids_l, *[m for m in mask_l if m is not None], *feats, *argmaxes)
         ctx.mask_present = [m is not None for m in mask_l]
+        ctx.flags_l = flags_l
         return tuple(feats)
 
     @staticmethod
@@ -317,9 +344,9 @@ class EncodeDocsFn(torch.autograd.Function):
                             lib.check(lib.rbr_conv_act_maxpool_bwd(
                                 prec, cfg["act"], _p(table), _p(ctx.shadow), vocab, emb, _p(ids), _p(mask), None, 0, n_docs, doc_len,
                                 _p(ctx.packed[i]), h, k, cfg["pads"][i], feats[s].data_ptr() + 4 * col,
-                                argmaxes[s].data_ptr() + 4 * col, fg.data_ptr() + 4 * col, None, None, h_total, cfg["padding_idx"],
+                                argmaxes[s].data_ptr() + 4 * col, fg.data_ptr() + 4 * col, None, h_total, cfg["padding_idx"],
                                 _p(g_w[i]) if do_weight else None, _p(g_b[i]) if do_weight else None, _p(gt), None, _p(ws),
-                                ws_bytes, sh), "rbr_conv_act_maxpool_bwd")
+                                ws_bytes, ctx.flags_l[s], sh), "rbr_conv_act_maxpool_bwd")
                         col += h
             for rank_s in range(1, len(live)):
                 main.wait_event(side_streams[rank_s - 1].record_event())
@@ -377,6 +404,8 @@ class HeadFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, u_text, i_text, u_id, i_id, Wu, bu, ebd_u, Wi, bi, ebd_i, fm_h, user_bias, item_bias, g_bias, drop_p,
                 drop_seed, padding_idx, arena, params, seed_dev=None):
+        """padding_idx: one int / None for all four id tables, or a 4-tuple (LastFeat_u.ebd, LastFeat_i.ebd, FM.user_bias,
+        FM.item_bias) — each nn.Embedding keeps its own padding row."""
         _stream(refresh=True)
         u_text = _req(u_text, torch.float32, "u_text")
         i_text = _req(i_text, torch.float32, "i_text")
@@ -392,6 +421,9 @@ class HeadFn(torch.autograd.Function):
                                    ebd_i.shape[0], float(drop_p), int(drop_seed), _p(seed_dev), _p(pred), _p(u_lat), _p(i_lat), None,
                                    0.0, None, None, _stream()), "rbr_head_fwd")
         ctx.save_for_backward(u_text, i_text, u_id, i_id, fl[0], fl[3], fl[6], u_lat, i_lat)
+        if not isinstance(padding_idx, (tuple, list)):
+            padding_idx = (padding_idx,) * 4
+        padding_idx = tuple(-1 if x is None else int(x) for x in padding_idx)
         ctx.drop, ctx.padding_idx, ctx.arena, ctx.params = (float(drop_p), int(drop_seed), seed_dev), padding_idx, arena, params
         ctx.sizes = (ebd_u.shape[0], ebd_i.shape[0])
         return pred
@@ -407,10 +439,75 @@ class HeadFn(torch.autograd.Function):
         # params order: Wu, bu, ebd_u, Wi, bi, ebd_i, fm_h, user_bias, item_bias, g_bias
         grads = [_grad_buf(ctx.arena, p, True) for p in ctx.params]
         lib.check(lib.rbr_head_bwd(_p(u_text), _p(i_text), _p(u_id), _p(i_id), B, H, K, _p(Wu), _p(Wi), _p(fm_h), _p(u_lat),
-                                   _p(i_lat), ctx.drop[0], ctx.drop[1], _p(ctx.drop[2]), -1 if ctx.padding_idx is None else ctx.padding_idx,
+                                   _p(i_lat), ctx.drop[0], ctx.drop[1], _p(ctx.drop[2]), *ctx.padding_idx,
                                    ctx.sizes[0], ctx.sizes[1], _p(g_pred), _p(g_ut), _p(g_it), *[_p(g) for g in grads],
                                    _stream()), "rbr_head_bwd")
         return (g_ut, g_it, None, None, *grads, None, None, None, None, None, None)
+
+
+class HeadLossFn(torch.autograd.Function):
+    """(loss, pred) = (MSELoss(pred, ratings), pred) with pred as in HeadFn: the fused-MSE branch of rbr_head_fwd
+    (reference layers.py:156-165, 188-209 + trainer/train_deepconn_pp.py:140,164: nn.MSELoss(), reduction 'mean').
+    The forward launch also writes d loss / d pred = 2 (pred - rating) / B, so the backward is one rbr_head_bwd launch."""
+
+    @staticmethod
+    def forward(ctx, u_text, i_text, u_id, i_id, ratings, Wu, bu, ebd_u, Wi, bi, ebd_i, fm_h, user_bias, item_bias, g_bias,
+                drop_p, drop_seed, padding_idx, arena, params, seed_dev=None):
+        _stream(refresh=True)
+        u_text = _req(u_text, torch.float32, "u_text")
+        i_text = _req(i_text, torch.float32, "i_text")
+        u_id = _req(u_id, torch.int64, "u_id")
+        i_id = _req(i_id, torch.int64, "i_id")
+        ratings = _req(ratings, torch.float32, "ratings").view(-1)
+        B, H = u_text.shape
+        if ratings.numel() != B:
+            raise ValueError("rbr_b200: ratings must have one value per sample")
+        K = Wu.shape[1]
+        fl = [_req(t, torch.float32, "head parameter") for t in (Wu, bu, ebd_u, Wi, bi, ebd_i, fm_h, user_bias, item_bias, g_bias)]
+        dev = u_text.device
+        pred = torch.empty(B, dtype=torch.float32, device=dev)
+        u_lat = torch.empty(B, K, dtype=torch.float32, device=dev)
+        i_lat = torch.empty(B, K, dtype=torch.float32, device=dev)
+        pred_grad = torch.empty(B, dtype=torch.float32, device=dev)
+        loss = torch.zeros((), dtype=torch.float32, device=dev)         # the kernel accumulates sum (pred - rating)^2 / B into it
+        lib.check(lib.rbr_head_fwd(_p(u_text), _p(i_text), _p(u_id), _p(i_id), B, H, K, *[_p(t) for t in fl], ebd_u.shape[0],
+                                   ebd_i.shape[0], float(drop_p), int(drop_seed), _p(seed_dev), _p(pred), _p(u_lat), _p(i_lat),
+                                   _p(ratings), 1.0 / B, _p(loss), _p(pred_grad), _stream()), "rbr_head_fwd")
+        ctx.save_for_backward(u_text, i_text, u_id, i_id, fl[0], fl[3], fl[6], u_lat, i_lat, pred_grad)
+        if not isinstance(padding_idx, (tuple, list)):
+            padding_idx = (padding_idx,) * 4
+        padding_idx = tuple(-1 if x is None else int(x) for x in padding_idx)
+        ctx.drop, ctx.padding_idx, ctx.arena, ctx.params = (float(drop_p), int(drop_seed), seed_dev), padding_idx, arena, params
+        ctx.sizes = (ebd_u.shape[0], ebd_i.shape[0])
+        ctx.mark_non_differentiable(pred)
+        return loss, pred
+
+    @staticmethod
+    def backward(ctx, g_loss, g_pred):
+        _stream(refresh=True)
+        u_text, i_text, u_id, i_id, Wu, Wi, fm_h, u_lat, i_lat, pred_grad = ctx.saved_tensors
+        B, H = u_text.shape
+        K = Wu.shape[1]
+        pg = pred_grad * g_loss                         # upstream d / d loss (a device scalar: no host read)
+        g_ut, g_it = torch.empty_like(u_text), torch.empty_like(i_text)
+        grads = [_grad_buf(ctx.arena, p, True) for p in ctx.params]
+        lib.check(lib.rbr_head_bwd(_p(u_text), _p(i_text), _p(u_id), _p(i_id), B, H, K, _p(Wu), _p(Wi), _p(fm_h), _p(u_lat),
+                                   _p(i_lat), ctx.drop[0], ctx.drop[1], _p(ctx.drop[2]), *ctx.padding_idx,
+                                   ctx.sizes[0], ctx.sizes[1], _p(pg), _p(g_ut), _p(g_it), *[_p(g) for g in grads],
+                                   _stream()), "rbr_head_bwd")
+        return (g_ut, g_it, None, None, None, *grads, None, None, None, None, None, None)
+
+
+def head_dropout_mask(batch: int, latent: int, drop_p: float, drop_seed: int, seed_dev: Optional[torch.Tensor],
+                      device=None) -> torch.Tensor:
+    """The FM dropout keep-scale [B, K] (values 0 or 1/(1-p)) the head kernels apply for this (p, seed, device counter) — a
+    test / debug aid: the mask is a counter hash, not torch's Philox stream, so parity at p > 0 is checked by feeding this mask
+    to the oracle."""
+    dev = device or (seed_dev.device if seed_dev is not None else torch.device("cuda"))
+    keep = torch.empty(batch, latent, dtype=torch.float32, device=dev)
+    lib.check(lib.rbr_head_dropout_mask(batch, latent, float(drop_p), int(drop_seed), _p(seed_dev), _p(keep), _stream(True)),
+              "rbr_head_dropout_mask")
+    return keep
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -418,10 +515,12 @@ class HeadFn(torch.autograd.Function):
 # ---------------------------------------------------------------------------------------------------
 def conv_act_maxpool(table: torch.Tensor, ids: torch.Tensor, mask: Optional[torch.Tensor], weight: torch.Tensor,
                      bias: torch.Tensor, pad: int, act: int = ACT_RELU, precision: str = "bf16",
-                     shadow: Optional[torch.Tensor] = None, packed: Optional[torch.Tensor] = None):
-    """One K2 launch: returns (feat [n_docs, H] fp32, argmax [n_docs, H] int32)."""
+                     shadow: Optional[torch.Tensor] = None, packed: Optional[torch.Tensor] = None, flags: int = 0,
+                     mask_from_ids: bool = False):
+    """One K2 launch: returns (feat [n_docs, H] fp32, argmax [n_docs, H] int32).  `flags`: CONV_TC_* kernel selection."""
     table = _req(table, torch.float32, "table")
-    ids = _req(ids, torch.int64, "ids")
+    ids = _ids(ids, "ids")
+    flags |= _id_flags(ids, mask, mask_from_ids)
     mask = _mask_u8(mask, "mask")
     prec = _PREC[precision]
     if prec == PREC_BF16 and shadow is None:
@@ -435,7 +534,7 @@ def conv_act_maxpool(table: torch.Tensor, ids: torch.Tensor, mask: Optional[torc
     amax = torch.empty(n_docs, h, dtype=torch.int32, device=table.device)
     lib.check(lib.rbr_conv_act_maxpool_fwd(prec, act, _p(table), _p(shadow), table.shape[0], emb, _p(ids), _p(mask), None, 0,
                                            n_docs, doc_len, _p(packed), _p(_req(bias, torch.float32, "bias")), h, k, pad,
-                                           _p(feat), _p(amax), None, h, _stream(True)), "rbr_conv_act_maxpool_fwd")
+                                           _p(feat), _p(amax), None, h, flags, _stream(True)), "rbr_conv_act_maxpool_fwd")
     return feat, amax
 
 
@@ -488,7 +587,7 @@ class DattEncodeFn(torch.autograd.Function):
                 h, _, k = w.shape
                 lib.check(lib.rbr_conv_act_maxpool_fwd(prec, ACT_TANH, _p(table), _p(shadow), vocab, emb, _p(ids), None, _p(gate),
                                                        mode, n_docs, doc_len, _p(pk), _p(b), h, k, 0, feat.data_ptr() + 4 * col,
-                                                       amax.data_ptr() + 4 * col, pre.data_ptr() + 4 * col, h_total, _stream()),
+                                                       amax.data_ptr() + 4 * col, pre.data_ptr() + 4 * col, h_total, 0, _stream()),
                           "rbr_conv_act_maxpool_fwd")
                 col += h
             saved += [ids, gate_l, gate_g, feat, amax, pre]
@@ -512,9 +611,11 @@ class DattEncodeFn(torch.autograd.Function):
         # the user and item sides only meet in the (atomic) table gradient: the second side runs on its own stream
         main = torch.cuda.current_stream()
         side_streams = _side_streams(dev, max(0, ctx.n_sides - 1))
-        ev_fork = main.record_event() if ctx.n_sides > 1 else None
+        # every buffer the side stream accumulates into is allocated AND zero-filled on the main stream before the fork event
+        # (a frozen table or arena=None materialises them here for the first time)
         all_grads = [[_grad_buf(arena, p, True) for p in cfg["params"][s]] for s in range(ctx.n_sides)]
         fgs = [None if feat_grads[s] is None else feat_grads[s].contiguous() for s in range(ctx.n_sides)]
+        ev_fork = main.record_event() if ctx.n_sides > 1 else None
         for s in range(ctx.n_sides):
             ids, gate_l, gate_g, feat, amax, pre = ctx.saved_tensors[6 * s:6 * s + 6]
             prm, packed = ctx.side_ctx[s]
@@ -556,8 +657,8 @@ class DattEncodeFn(torch.autograd.Function):
                 lib.check(lib.rbr_conv_act_maxpool_bwd(
                     prec, ACT_TANH, _p(table), _p(shadow), vocab, emb, _p(ids), None, _p(gate), mode, n_docs, doc_len, _p(pk),
                     h, k, 0, feat.data_ptr() + 4 * col, amax.data_ptr() + 4 * col, fg.data_ptr() + 4 * col,
-                    pre.data_ptr() + 4 * col, _p(b), h_total, cfg["padding_idx"], _p(grads[wi]), _p(grads[bi]), _p(g_table),
-                    _p(d_gate_l if mode == 1 else d_gate_g), _p(ws), ws_bytes, _stream()), "rbr_conv_act_maxpool_bwd")
+                    pre.data_ptr() + 4 * col, h_total, cfg["padding_idx"], _p(grads[wi]), _p(grads[bi]), _p(g_table),
+                    _p(d_gate_l if mode == 1 else d_gate_g), _p(ws), ws_bytes, 0, _stream()), "rbr_conv_act_maxpool_bwd")
                 col += h
             win = la_w.shape[2]
             ws_bytes = lib.rbr_datt_gate_workspace_bytes(n_docs, doc_len, emb, win, vocab)

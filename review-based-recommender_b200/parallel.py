@@ -53,11 +53,21 @@ def _arena_covers(model: torch.nn.Module) -> bool:
 
 
 class _EarlyTableReduce:
-    """State of the overlapped word-table all-reduce of one backward pass (see enable_overlap)."""
+    """State of the overlapped word-table all-reduce of one backward pass (see enable_overlap).
+
+    Only the ADDRESS RANGE of the gradient is remembered, never the tensor autograd is about to receive: an extra Python
+    reference to that tensor raises its use_count, AccumulateGrad then clones it instead of stealing it, and the clone —
+    made on the main stream while the collective is still writing the buffer — would be a data race and would detach `.grad`
+    from the arena.  The collective runs on a separate alias (own TensorImpl, same storage)."""
 
     def __init__(self):
         self.work = None
-        self.tensor: Optional[torch.Tensor] = None
+        self.alias: Optional[torch.Tensor] = None     # detached alias the collective reduces in place
+        self.ptr = 0
+        self.numel = 0
+
+    def clear(self):
+        self.work, self.alias, self.ptr, self.numel = None, None, 0, 0
 
 
 def enable_overlap(model: torch.nn.Module, group=None) -> None:
@@ -74,8 +84,9 @@ def enable_overlap(model: torch.nn.Module, group=None) -> None:
 
     def hook(g_table: torch.Tensor):
         if dist.is_initialized() and dist.get_world_size(group) > 1:
-            state.tensor = g_table
-            state.work = dist.all_reduce(g_table, op=dist.ReduceOp.AVG if dist.get_backend(group) == "nccl" else dist.ReduceOp.SUM,
+            state.ptr, state.numel = g_table.data_ptr(), g_table.numel()
+            state.alias = g_table.detach().view(-1)          # new TensorImpl on the same storage: g_table's use_count is untouched
+            state.work = dist.all_reduce(state.alias, op=dist.ReduceOp.AVG if dist.get_backend(group) == "nccl" else dist.ReduceOp.SUM,
                                          group=group, async_op=True)
 
     ngram.table_grad_hook = hook
@@ -202,10 +213,14 @@ def allreduce_gradients(model: torch.nn.Module, group=None, average: bool = True
             flat.copy_(half)
             return 1
         pieces = [flat]
-        if early is not None and early.work is not None and early.tensor is not None:
-            lo = (early.tensor.data_ptr() - flat.data_ptr()) // 4
-            hi = lo + early.tensor.numel()
-            pieces = [t for t in (flat[:lo], flat[hi:]) if t.numel() > 0]
+        if early is not None and early.work is not None:
+            lo = (early.ptr - flat.data_ptr()) // 4
+            hi = lo + early.numel
+            if 0 <= lo and hi <= flat.numel():
+                pieces = [t for t in (flat[:lo], flat[hi:]) if t.numel() > 0]
+            else:                                   # the early gradient did not come from this arena: nothing to exclude
+                early.work.wait()
+                early.clear()
         n = 0
         for t in pieces:
             dist.all_reduce(t, op=op, group=group)
@@ -215,19 +230,18 @@ def allreduce_gradients(model: torch.nn.Module, group=None, average: bool = True
         if early is not None and early.work is not None:
             early.work.wait()
             if average and not nccl:
-                early.tensor.mul_(1.0 / world)
-            early.work, early.tensor = None, None
+                early.alias.mul_(1.0 / world)
+            early.clear()
         return n
-    if early is not None and early.work is not None:          # mixed case: finish the early one, then the bucket below re-reduces nothing twice
+    done_ptr = None
+    if early is not None and early.work is not None:          # mixed case: finish the early one; the bucket below skips it
         early.work.wait()
-        done = early.tensor
         if average and not nccl:
-            done.mul_(1.0 / world)
-        early.work, early.tensor = None, None
-    else:
-        done = None
+            early.alias.mul_(1.0 / world)
+        done_ptr = early.ptr
+        early.clear()
     grads = [p.grad for p in model.parameters() if p.requires_grad and p.grad is not None
-             and not (done is not None and p.grad.data_ptr() == done.data_ptr())]
+             and not (done_ptr is not None and p.grad.data_ptr() == done_ptr)]
     if not grads:
         return 0
     flat = torch.cat([g.reshape(-1) for g in grads])

@@ -128,6 +128,33 @@ n = parallel.allreduce_gradients(model)
 assert n == 1                                             # only the remainder is reduced after backward
 assert torch.allclose(model.weight.grad, ref.weight.grad, atol=1e-6)
 assert torch.allclose(model.bias.grad, ref.bias.grad, atol=1e-6)
+# the same through AUTOGRAD: a backward that accumulates into an arena view, fires the hook and RETURNS that view (what
+# ops.EncodeDocsFn.backward does).  The hook must not keep a reference to the returned tensor: AccumulateGrad would then
+# clone it, `.grad` would leave the arena and the early reduction would be lost.
+class _ArenaMatmul(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, arena, hook):
+        ctx.save_for_backward(x); ctx.w, ctx.arena, ctx.hook = w, arena, hook
+        return x @ w.t()
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        buf = ctx.arena.view(ctx.w)
+        buf.add_(g.t() @ x)
+        ctx.hook(buf)
+        return None, buf, None, None
+model.zero_grad(set_to_none=True)
+arena3 = GradArena(list(model.named_parameters()))
+out = _ArenaMatmul.apply(x[sh.start:sh.stop], model.weight, arena3, model.ngram.table_grad_hook) + model.bias
+torch.nn.functional.mse_loss(out, y[sh.start:sh.stop]).backward()
+lo = arena3.flat.data_ptr(); hi = lo + arena3.flat.numel() * 4
+assert lo <= model.weight.grad.data_ptr() < hi, "the weight gradient was cloned out of the arena (hook kept a reference?)"
+bslot = arena3.view(model.bias); bslot.copy_(model.bias.grad); model.bias.grad = bslot
+model.last_arena = arena3
+n = parallel.allreduce_gradients(model)
+assert n == 1
+assert torch.allclose(model.weight.grad, ref.weight.grad, atol=1e-6), (model.weight.grad, ref.weight.grad)
+assert torch.allclose(model.bias.grad, ref.bias.grad, atol=1e-6)
 del model.ngram, model._rbr_early_table
 # slow path: grads not in the arena
 model.last_arena = None
@@ -191,6 +218,14 @@ def test_grad_arena_layout_is_cached_per_module_and_tracks_requires_grad():
     a4 = GradArena.for_module(m)
     w = a4.view(m[0].weight)
     assert w.data_ptr() == buf.data_ptr() and float(buf[:a4.total].sum()) == 0.0 and float(buf[a4.total:].sum()) == 1024 - a4.total
+    # ... and a `.grad` that still aliases it when the next backward starts (gradient accumulation, zero_grad(set_to_none=False))
+    # is an error instead of a silent wipe
+    m[0].weight.grad = w
+    a5 = GradArena.for_module(m)
+    with pytest.raises(RuntimeError, match="set_to_none=True"):
+        a5.view(m[0].weight)
+    m[0].weight.grad = None
+    assert GradArena.for_module(m).view(m[0].weight) is not None
 
 
 def test_conv_tc2_plan_invariants():

@@ -14,14 +14,12 @@ from test_gpu_parity import DEEPCONN_CASES, NARRE_CASES, build_model, run_step
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=[1, 2], ids=["cta1-cpasync", "pair-tma"], autouse=True)
-def tc_variant(request):
-    """Every test of this file runs on BOTH tensor-core kernels: conv_tc.cu (single CTA, cp.async operands) and
-    conv_tc2.cu (CTA pair, cta_group::2, TMA gather4 operands); variant 2 errors out instead of falling back."""
-    from rbr_b200._lib import lib
-    prev = lib.rbr_set_conv_tc_variant(request.param)
-    yield request.param
-    lib.rbr_set_conv_tc_variant(prev)
+@pytest.fixture(params=[ops.CONV_TC_SINGLE_CTA, ops.CONV_TC_PAIR_ONLY], ids=["cta1-cpasync", "pair-tma"])
+def tc_flags(request):
+    """Tests taking this fixture run on BOTH tensor-core kernels: conv_tc.cu (single CTA, cp.async operands) and
+    conv_tc2.cu (CTA pair, cta_group::2, TMA gather4 operands), selected per call through the C-ABI's `flags` argument
+    (either flag errors out instead of falling back)."""
+    return request.param
 
 
 def _bf16_round(t):
@@ -53,7 +51,7 @@ SHAPES = [
 
 
 @pytest.mark.parametrize("shape", SHAPES)
-def test_conv_tc_vs_bf16_rounded_oracle(shape):
+def test_conv_tc_vs_bf16_rounded_oracle(shape, tc_flags):
     n, L, V, E, H, k = shape
     gen = torch.Generator().manual_seed(n * 1000 + L)
     table = torch.randn(V, E, generator=gen)
@@ -67,7 +65,7 @@ def test_conv_tc_vs_bf16_rounded_oracle(shape):
         ids[2] = 0
         mask[2] = False                                  # fully padded document → relu(bias)
     feat, amax = ops.conv_act_maxpool(table.cuda(), ids.cuda(), mask.cuda(), w.cuda(), b.cuda(), (k - 1) // 2,
-                                      precision="bf16")
+                                      precision="bf16", flags=tc_flags)
     x = orc.mask_rows(orc.embedding_gather(_bf16_round(table), ids), mask)
     y = orc.conv1d_same(x, _bf16_round(w), b)
     ref, ref_arg = orc.first_argmax_pool(torch.relu(y))
@@ -80,14 +78,15 @@ def test_conv_tc_vs_bf16_rounded_oracle(shape):
         assert torch.allclose(feat[2].cpu(), torch.relu(b), atol=1e-6)
 
 
-def test_conv_tc_tanh_and_no_mask():
+def test_conv_tc_tanh_and_no_mask(tc_flags):
     gen = torch.Generator().manual_seed(4)
     V, E, H, k, n, L = 100, 64, 32, 3, 6, 200
     table = torch.randn(V, E, generator=gen)
     w = (torch.rand(H, E, k, generator=gen) * 2 - 1) / (E * k) ** 0.5
     b = (torch.rand(H, generator=gen) * 2 - 1) * 0.1
     ids = torch.randint(0, V, (n, L), generator=gen)
-    feat, _ = ops.conv_act_maxpool(table.cuda(), ids.cuda(), None, w.cuda(), b.cuda(), 1, act=ops.ACT_TANH, precision="bf16")
+    feat, _ = ops.conv_act_maxpool(table.cuda(), ids.cuda(), None, w.cuda(), b.cuda(), 1, act=ops.ACT_TANH, precision="bf16",
+                                   flags=tc_flags)
     y = orc.conv1d_same(orc.embedding_gather(_bf16_round(table), ids), _bf16_round(w), b)
     assert rel_err(feat.cpu(), torch.tanh(y).max(dim=1).values) < 1e-3
 
@@ -106,13 +105,14 @@ def _fro_err(a, b):
 
 
 @pytest.mark.parametrize("case", DEEPCONN_CASES + NARRE_CASES)
-def test_golden_bf16(case):
+def test_golden_bf16(case, tc_flags):
     """End-to-end bf16 step.  Outputs against the reference's own numbers at the 1e-2 tolerance.  Gradients:
     (a) within 1e-2 of the oracle run on the bf16-rounded operands (same arg-max routing as the kernel);
     (b) against the fp32 reference on the Frobenius norm — bf16 rounding can move an arg-max to a near-tied
         position, which moves a whole gradient row, so max-abs is not a stable metric there."""
     g = Golden(case)
     model = build_model(g, "bf16")
+    model.ngram.conv_flags = tc_flags
     out, loss, grads = run_step(model, g.batch, g.ratings)
     pred = out[0] if isinstance(out, tuple) else out
     assert rel_err(pred.detach().cpu(), g.out["pred"]) < 1e-2
@@ -125,13 +125,14 @@ def test_golden_bf16(case):
             assert _fro_err(grads[k], ref) < 1e-1, k
 
 
-def test_seeded_midsize_bf16_vs_oracle():
+def test_seeded_midsize_bf16_vs_oracle(tc_flags):
     B, L, V, U, I, E, H, K = 24, 500, 3000, 50, 40, 300, 100, 32
     params = synth.deepconn_params(U, I, V, E, H, K, (3,), seed=1)
     batch, ratings = synth.deepconn_batch(B, L, V, U, I, seed=123)
     model = rbr_b200.DeepCoNNpp(U, I, V, [3], E, H, K, L, None, 0.0, precision="bf16")
     model.load_state_dict(params)
     model.cuda()
+    model.ngram.conv_flags = tc_flags
     out, loss, grads = run_step(model, batch, ratings)
     rp, rl, rg = orc.loss_and_grads("deepconn", params, batch, ratings)
     assert rel_err(out.detach().cpu(), rp) < 1e-2
@@ -143,7 +144,7 @@ def test_seeded_midsize_bf16_vs_oracle():
         assert rel_err(grads[k], rgr[k], 1e-7) < 1e-2, k
 
 
-def test_bf16_full_batch_properties():
+def test_bf16_full_batch_properties(tc_flags):
     """B=4096-sized run of the tensor-core path: deterministic, mask-invariant, permutation-equivariant, and
     equal (within bf16 tolerance) to the fp32 CUDA-core variant on the same inputs."""
     B, L, V, U, I, E, H, K = 1024, 500, 50000, 2000, 1200, 300, 100, 32
@@ -155,6 +156,7 @@ def test_bf16_full_batch_properties():
         model = rbr_b200.DeepCoNNpp(U, I, V, [3], E, H, K, L, None, 0.5, precision=prec)
         model.load_state_dict(params)
         model.cuda().eval()
+        model.ngram.conv_flags = tc_flags if prec == "bf16" else 0
         with torch.no_grad():
             preds[prec] = model(*b)
             if prec == "bf16":
@@ -169,7 +171,6 @@ def test_bf16_full_batch_properties():
 
 def test_variants_agree_bitwise_on_values():
     """The two kernels issue the same K-step / tap order into fp32 TMEM accumulators: identical pooled values."""
-    from rbr_b200._lib import lib
     gen = torch.Generator().manual_seed(12)
     V, E, H, k, n, L = 4000, 300, 100, 3, 300, 500
     table = torch.randn(V, E, generator=gen)
@@ -177,8 +178,7 @@ def test_variants_agree_bitwise_on_values():
     b = (torch.rand(H, generator=gen) * 2 - 1) * 0.1
     ids, mask = synth.doc_batch(n, L, V, seed=99)
     outs = []
-    for variant in (1, 2):
-        lib.rbr_set_conv_tc_variant(variant)
-        outs.append(ops.conv_act_maxpool(table.cuda(), ids.cuda(), mask.cuda(), w.cuda(), b.cuda(), 1, precision="bf16"))
+    for fl in (ops.CONV_TC_SINGLE_CTA, ops.CONV_TC_PAIR_ONLY):
+        outs.append(ops.conv_act_maxpool(table.cuda(), ids.cuda(), mask.cuda(), w.cuda(), b.cuda(), 1, precision="bf16", flags=fl))
     assert torch.equal(outs[0][0], outs[1][0])
     assert torch.equal(outs[0][1], outs[1][1])

@@ -231,23 +231,3 @@ def test_two_pass_backward_with_table_hook_matches_single_pass():
     for k in grads[0]:
         assert rel_err(grads[1][k], grads[0][k]) < 1e-6, k
     assert rel_err(seen["table"].cpu(), g.grads["word_embeddings.embedding.weight"]) < FP32_GRAD_TOL
-
-
-@pytest.mark.parametrize("case", NARRE_CASES + ["deepconn_odd"])
-@pytest.mark.parametrize("precision", ["fp32", "bf16"])
-def test_short_document_backward_formulations_agree(case, precision):
-    """The per-document backward kernel (conv_bwd_short.cu, NARRE's 60-token reviews) against the generic entries/sort
-    kernels on the same inputs: identical routing, same gradients up to summation order."""
-    from rbr_b200._lib import lib
-    g = Golden(case)
-    grads = []
-    for mode in (0, 2):
-        prev = lib.rbr_set_conv_bwd_short(mode)
-        try:
-            model = build_model(g, precision)
-            _, _, gr = run_step(model, g.batch, g.ratings)
-        finally:
-            lib.rbr_set_conv_bwd_short(prev)
-        grads.append(gr)
-    for k in grads[0]:
-        assert rel_err(grads[1][k], grads[0][k], grad_floor(k)) < (2e-5 if precision == "fp32" else 2e-3), k
