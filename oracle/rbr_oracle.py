@@ -130,18 +130,26 @@ def first_argmax_pool(y: Tensor) -> Tuple[Tensor, Tensor]:
 
 
 def ngram_feat(x: Tensor, mask: Optional[Tensor], conv_weights: Sequence[Tensor], conv_biases: Sequence[Tensor],
-               return_argmax: bool = False):
+               return_argmax: bool = False, argmax_override: Optional[Tensor] = None):
     """NgramFeat.forward with arch="CNN" (layers.py:123-136): mask → conv(s) → ReLU → max over time.
 
     Several kernel sizes are concatenated on the filter dim (MyConv1d.forward, layers.py:54-58).
     Returns [N,H] (the reference returns [N,H,1]; callers `.view(bz, H)` it, deepconn.py:46).
+    `argmax_override` [N,H] (tests only): pool at these positions instead of the oracle's own first arg-max — used to compare
+    gradients under IDENTICAL routing when two positions tie to within rounding (each test first checks that every
+    overridden position attains the oracle's max up to summation-order noise).
     """
     if mask is not None:
         x = mask_rows(x, mask)
     feats, args = [], []
+    col = 0
     for w, b in zip(conv_weights, conv_biases):
         y = torch.relu(conv1d_same(x, w, b))
-        idx = (y == y.max(dim=1, keepdim=True).values).to(torch.uint8).argmax(dim=1)
+        if argmax_override is not None:
+            idx = argmax_override[:, col:col + w.shape[0]].to(torch.long)
+        else:
+            idx = (y == y.max(dim=1, keepdim=True).values).to(torch.uint8).argmax(dim=1)
+        col += w.shape[0]
         v = torch.gather(y, 1, idx.unsqueeze(1)).squeeze(1)       # differentiable, first-arg-max routed
         feats.append(v)
         args.append(idx)
@@ -210,19 +218,21 @@ def _conv_params(p: Params, prefix: str) -> Tuple[List[Tensor], List[Tensor]]:
 
 
 def deepconn_forward(p: Params, u_revs: Tensor, i_revs: Tensor, u_masks: Tensor, i_masks: Tensor, u_ids: Tensor,
-                     i_ids: Tensor, return_aux: bool = False):
+                     i_ids: Tensor, return_aux: bool = False, fm_drop_mask: Optional[Tensor] = None,
+                     argmax_override: Optional[Tuple[Tensor, Tensor]] = None):
     """DeepCoNNpp.forward, deepconn.py:28-53.  Embedding + conv weights are SHARED between the
     user and the item side (deepconn.py:20-22, 43-47)."""
     table = p["word_embeddings.embedding.weight"]
     ws, bs = _conv_params(p, "ngram.feature_layer.0.list_of_conv1d")
     u_x = embedding_gather(table, u_revs)                                        # deepconn.py:43
     i_x = embedding_gather(table, i_revs)                                        # deepconn.py:44
-    u_rev, u_arg = ngram_feat(u_x, u_masks, ws, bs, return_argmax=True)          # deepconn.py:46
-    i_rev, i_arg = ngram_feat(i_x, i_masks, ws, bs, return_argmax=True)          # deepconn.py:47
+    ao = argmax_override or (None, None)
+    u_rev, u_arg = ngram_feat(u_x, u_masks, ws, bs, return_argmax=True, argmax_override=ao[0])   # deepconn.py:46
+    i_rev, i_arg = ngram_feat(i_x, i_masks, ws, bs, return_argmax=True, argmax_override=ao[1])   # deepconn.py:47
     u_f = last_feat(u_rev, u_ids, p["user_feat.W"], p["user_feat.b"], p["user_feat.ebd.weight"])   # :48
     i_f = last_feat(i_rev, i_ids, p["item_feat.W"], p["item_feat.b"], p["item_feat.ebd.weight"])   # :49
     pred = fm_head(u_f, i_f, u_ids, i_ids, p["fm.h"], p["fm.g_bias"], p["fm.user_bias.weight"],
-                   p["fm.item_bias.weight"])                                      # deepconn.py:51
+                   p["fm.item_bias.weight"], drop_mask=fm_drop_mask)              # deepconn.py:51
     pred = pred.view(-1)                                                          # deepconn.py:53
     if return_aux:
         return pred, {"u_rev_feats": u_rev, "i_rev_feats": i_rev, "u_argmax": u_arg, "i_argmax": i_arg,
@@ -234,7 +244,8 @@ def deepconn_forward(p: Params, u_revs: Tensor, i_revs: Tensor, u_masks: Tensor,
 # a11: NARRE.forward  (models/narre/narre.py:165-192)
 # --------------------------------------------------------------------------------------
 def narre_forward(p: Params, u_text: Tensor, i_text: Tensor, u_masks: Tensor, i_masks: Tensor, u_id: Tensor,
-                  i_id: Tensor, reuid: Tensor, reiid: Tensor, return_aux: bool = False):
+                  i_id: Tensor, reuid: Tensor, reiid: Tensor, return_aux: bool = False, fm_drop_mask: Optional[Tensor] = None,
+                  argmax_override: Optional[Tuple[Tensor, Tensor]] = None):
     """NARRE.forward, narre.py:165-192.  [B,R,T] tokens are encoded as B*R independent docs
     (narre.py:170-176); the review-level masks computed at narre.py:180-181 are never used."""
     table = p["word_embeddings.embedding.weight"]
@@ -243,8 +254,9 @@ def narre_forward(p: Params, u_text: Tensor, i_text: Tensor, u_masks: Tensor, i_
     hdim = sum(w.shape[0] for w in ws)
     u_x = embedding_gather(table, u_text).view(b * r, t, -1)
     i_x = embedding_gather(table, i_text).view(b * r, t, -1)
-    u_rf = ngram_feat(u_x, u_masks.reshape(b * r, t), ws, bs).view(b, r, hdim)
-    i_rf = ngram_feat(i_x, i_masks.reshape(b * r, t), ws, bs).view(b, r, hdim)
+    ao = argmax_override or (None, None)
+    u_rf = ngram_feat(u_x, u_masks.reshape(b * r, t), ws, bs, argmax_override=ao[0]).view(b, r, hdim)
+    i_rf = ngram_feat(i_x, i_masks.reshape(b * r, t), ws, bs, argmax_override=ao[1]).view(b, r, hdim)
     ua = {k: p[f"user_att.{k}"] for k in ("W_rv", "W_id", "h", "b_1", "b_2")}
     ia = {k: p[f"item_att.{k}"] for k in ("W_rv", "W_id", "h", "b_1", "b_2")}
     u_feat, u_sc = linear_attention(u_rf, reuid, ebd_vals=p["user_att.ebd_vals.weight"], **ua)   # narre.py:184
@@ -252,7 +264,7 @@ def narre_forward(p: Params, u_text: Tensor, i_text: Tensor, u_masks: Tensor, i_
     u_f = last_feat(u_feat, u_id, p["user_feat.W"], p["user_feat.b"], p["user_feat.ebd.weight"])  # :187
     i_f = last_feat(i_feat, i_id, p["item_feat.W"], p["item_feat.b"], p["item_feat.ebd.weight"])  # :188
     pred = fm_head(u_f, i_f, u_id, i_id, p["fm.h"], p["fm.g_bias"], p["fm.user_bias.weight"],
-                   p["fm.item_bias.weight"]).view(-1)                                             # :190-192
+                   p["fm.item_bias.weight"], drop_mask=fm_drop_mask).view(-1)                     # :190-192
     if return_aux:
         return pred, u_sc, i_sc, {"u_rev_feats": u_rf, "i_rev_feats": i_rf, "u_att_out": u_feat,
                                   "i_att_out": i_feat}
@@ -314,17 +326,18 @@ _PADDED_TABLES = ("word_embeddings.embedding.weight", "user_feat.ebd.weight", "i
                   "item_att.ebd_vals.weight")
 
 
-def loss_and_grads(model: str, p: Params, batch: Sequence[Tensor], ratings: Tensor):
+def loss_and_grads(model: str, p: Params, batch: Sequence[Tensor], ratings: Tensor, **fwd_kw):
     """Run forward + MSE + backward with torch autograd over the functional forward above.
 
     Returns (pred, loss, grads) with grads keyed like `p`.  Rows `padding_idx=0` of every
     nn.Embedding table receive zero gradient (nn.Embedding(padding_idx=0) semantics).
+    fwd_kw: `fm_drop_mask`, `argmax_override` of deepconn_forward / narre_forward.
     """
     leaves = {k: v.detach().clone().requires_grad_(True) for k, v in p.items()}
     if model == "deepconn":
-        pred = deepconn_forward(leaves, *batch)
+        pred = deepconn_forward(leaves, *batch, **fwd_kw)
     elif model == "narre":
-        pred = narre_forward(leaves, *batch)[0]
+        pred = narre_forward(leaves, *batch, **fwd_kw)[0]
     elif model == "dual_att":
         pred = dual_att_forward(leaves, *batch)
     else:

@@ -154,8 +154,9 @@ class NgramFeat(nn.Module):
         return self.feature_layer[0]
 
     def encode(self, word_embeddings: WordEmbedding, sides: Sequence[torch.Tensor],
-               masks: Sequence[Optional[torch.Tensor]]) -> List[torch.Tensor]:
-        """Fused path used by the models: token ids → pooled features, [n_docs, H] per side."""
+               masks: Sequence[Optional[torch.Tensor]], return_argmax: bool = False) -> List[torch.Tensor]:
+        """Fused path used by the models: token ids → pooled features, [n_docs, H] per side (with return_argmax: followed by
+        the int32 [n_docs, H] first-arg-max positions per side)."""
         conv = self.conv
         convs = list(conv.list_of_conv1d)
         table = word_embeddings.embedding.weight
@@ -178,7 +179,8 @@ class NgramFeat(nn.Module):
         flat = []
         for ids, m in zip(sides, masks):
             flat += [ids, m]
-        return list(ops.EncodeDocsFn.apply(table, cfg, *[c.weight for c in convs], *[c.bias for c in convs], *flat))
+        outs = list(ops.EncodeDocsFn.apply(table, cfg, *[c.weight for c in convs], *[c.bias for c in convs], *flat))
+        return outs if return_argmax else outs[:len(sides)]
 
     def forward(self, inputs, input_masks):
         """Reference signature (layers.py:123-136): inputs [bz, seq_len, E] fp32, masks [bz, seq_len] → [bz, H, 1].
@@ -197,7 +199,7 @@ class NgramFeat(nn.Module):
             "table_param": x, "weight_params": [c.weight for c in convs], "bias_params": [c.bias for c in convs],
             "padding_idx": -1, "flags": self.conv_flags,
         }
-        (feat,) = ops.EncodeDocsFn.apply(x, cfg, *[c.weight for c in convs], *[c.bias for c in convs], ids, input_masks)
+        feat, _ = ops.EncodeDocsFn.apply(x, cfg, *[c.weight for c in convs], *[c.bias for c in convs], ids, input_masks)
         return feat.view(bz, self.out_features, 1)
 
 

@@ -286,12 +286,14 @@ class EncodeDocsFn(torch.autograd.Function):
         ctx.save_for_backward(*ids_l, *[m for m in mask_l if m is not None], *feats, *argmaxes)
         ctx.mask_present = [m is not None for m in mask_l]
         ctx.flags_l = flags_l
-        return tuple(feats)
+        ctx.mark_non_differentiable(*argmaxes)
+        return tuple(feats) + tuple(argmaxes)          # [n_docs, H] features per side, then the int32 arg-max positions
 
     @staticmethod
-    def backward(ctx, *feat_grads):
+    def backward(ctx, *out_grads):
         _stream(refresh=True)
         cfg, n_conv, ns = ctx.cfg, ctx.n_conv, ctx.n_sides
+        feat_grads = out_grads[:ns]
         saved = list(ctx.saved_tensors)
         ids_l = saved[:ns]
         n_masks = sum(ctx.mask_present)

@@ -22,10 +22,12 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
 REF = os.environ.get("RBR_REFERENCE", "/root/reference")
 sys.path.insert(0, REF)
-for name in ("nltk", "nltk.tokenize", "gensim", "gensim.models"):   # unused imports of the reference
+for name in ("nltk", "nltk.tokenize", "gensim", "gensim.models", "preprocess", "preprocess.divide_and_create_example_sent",
+             "preprocess.divide_and_create_example_word"):   # unused imports of the reference
     m = types.ModuleType(name)
     m.word_tokenize = lambda s: s.split()
     m.KeyedVectors = object
+    m.clean_str = lambda s: s
     sys.modules.setdefault(name, m)
 
 import rbr_b200  # noqa: E402
@@ -127,7 +129,24 @@ def edge_tweak(params, batch):
         params["ngram.feature_layer.0.list_of_conv1d.0.bias"].abs() + 0.05
 
 
+def trainer_case(kind):
+    """N Adam steps through the reference's UNMODIFIED trainer loop (train_one_epoch: zero_grad → forward → MSELoss →
+    backward → clip_grad_norm_(5.0) → Adam(lr 0.002).step) with the reference's own model, on the stub dataset of
+    tests/trainer_harness.py: per-step losses and the final parameters."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import trainer_harness as th
+    losses, final, _ = th.run_trainer_epoch(kind, model_module=None)
+    rec = {"losses": np.asarray(losses, dtype=np.float64)}
+    for k, v in final.items():
+        rec["final/" + k] = v.numpy()
+    path = os.path.join(HERE, f"trainer_{kind}_{th.N_STEPS}steps.npz")
+    np.savez_compressed(path, **rec)
+    print(f"trainer_{kind}: {os.path.getsize(path)/1024:.1f} KiB, losses={losses}")
+
+
 if __name__ == "__main__":
+    for kind in ("deepconn", "narre", "dual_att"):
+        trainer_case(kind)
     deepconn_case("deepconn_small", B=4, L=20, V=60, U=9, I=7, E=12, H=8, K=6, ks=(3,), seed=1)
     deepconn_case("deepconn_edge", B=4, L=16, V=40, U=9, I=7, E=10, H=6, K=5, ks=(3,), seed=2, tweak=edge_tweak)
     deepconn_case("deepconn_multik", B=3, L=18, V=50, U=6, I=6, E=9, H=12, K=4, ks=(3, 5), seed=3)

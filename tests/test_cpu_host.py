@@ -189,9 +189,13 @@ def test_bench_reference_arm_contract():
     assert len(lines) == 1
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["unit"] == "samples/s" and d["higher_is_better"] is True
-    assert d["value"] > 0 and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    from oracle import ref_loader
+    assert d["value"] > 0 and d["cpu_baseline"]["cores"] >= 1
+    assert d["cpu_baseline"]["kind"] == ("reference" if ref_loader.available() else "port")
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert "DeepCoNN" in d["metric"] and "workload" in d["config"]
+    assert d["steps"] == 1 and d["warmup"] == 1                         # the requested counts are echoed
+    assert d["narre"]["impl"] == "reference" and "NARRE" in d["narre"]["metric"] and d["narre"]["value"] > 0
     out2 = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
                           env=dict(env, RANK="1", WORLD_SIZE="2"), capture_output=True, text=True, timeout=120)
     assert out2.returncode == 0 and out2.stdout.strip() == ""

@@ -58,3 +58,61 @@ def test_graphed_step_dropout_mask_changes_between_replays():
     with torch.no_grad():
         p1, p2 = model(*b), model(*b)
     assert torch.equal(p1, p2)
+
+
+def _eager_step(model, batch, ratings):
+    model.zero_grad(set_to_none=True)
+    out = model(*batch)
+    pred = out[0] if isinstance(out, tuple) else out
+    loss = torch.nn.MSELoss()(pred, ratings)
+    loss.backward()
+    return float(loss), {k: p.grad.detach().clone() for k, p in model.named_parameters()}
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("fuse_mse", [True, False])
+def test_graphed_step_narre_matches_eager(precision, fuse_mse):
+    """NARRE: two attention sides on two streams (forward and backward) inside the capture."""
+    U, I, V, E, H, A, K, R, T = 40, 30, 600, 64, 48, 16, 16, 6, 20
+    params = synth.narre_params(U, I, V, E, H, A, K, (3,), seed=4)
+    model = rbr_b200.NARRE(U, I, V, [3], H, E, A, K, R, T, 0.0, 0, 0, 0, None, "CNN", precision=precision)
+    model.load_state_dict(params)
+    model.cuda().train()
+    batches = []
+    for seed in (5, 6, 7):
+        b, r = synth.narre_batch(24, R, T, V, U, I, seed=seed)
+        batches.append(([t.cuda() for t in b], r.cuda()))
+    ref = [_eager_step(model, b, r) for b, r in batches]
+    step = GraphedTrainStep(model, torch.nn.MSELoss(), *batches[0], fuse_mse=fuse_mse)
+    assert step.fused_loss == fuse_mse
+    for rep in range(2):                                         # every batch twice: replays do not leak state
+        for (b, r), (ref_loss, ref_grads) in zip(batches, ref):
+            loss = step(b, r)
+            torch.cuda.synchronize()
+            assert abs(float(loss) - ref_loss) <= 2e-6 * max(1.0, abs(ref_loss))
+            for k, p in model.named_parameters():
+                assert rel_err(p.grad.cpu(), ref_grads[k].cpu(), 1e-9) < 2e-6, k
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_graphed_step_dual_att_matches_eager(precision):
+    """D-ATT: the item side's backward runs on a side stream inside the capture; loss through torch's own MSELoss."""
+    V, L, E = 500, 64, 32
+    params = synth.dual_att_params(V, L, 5, 24, 16, E, 40, 10, seed=5)
+    model = rbr_b200.DualAtt(V, L, 5, 24, 16, E, 40, 10, 0.0, None, precision=precision)
+    model.load_state_dict(params)
+    model.cuda().train()
+    batches = []
+    for seed in (5, 6, 7):
+        b, r = synth.dual_att_batch(16, L, V, seed=seed)
+        batches.append(([t.cuda() for t in b], r.cuda()))
+    ref = [_eager_step(model, b, r) for b, r in batches]
+    step = GraphedTrainStep(model, torch.nn.MSELoss(), *batches[0])
+    assert not step.fused_loss                                   # DualAtt has no FM head: nn.MSELoss stays a torch op
+    for rep in range(2):
+        for (b, r), (ref_loss, ref_grads) in zip(batches, ref):
+            loss = step(b, r)
+            torch.cuda.synchronize()
+            assert abs(float(loss) - ref_loss) <= 2e-6 * max(1.0, abs(ref_loss))
+            for k, p in model.named_parameters():
+                assert rel_err(p.grad.cpu(), ref_grads[k].cpu(), 1e-9) < 2e-6, k

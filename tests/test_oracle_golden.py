@@ -55,3 +55,35 @@ def test_first_argmax_tie_rule():
     y = torch.tensor([[[1.0], [3.0], [3.0], [2.0]]])
     vals, idx = orc.first_argmax_pool(y)
     assert vals.item() == 3.0 and idx.item() == 1
+
+
+def test_vendored_reference_is_byte_identical_and_agrees_with_the_oracle():
+    """oracle/_ref (built by oracle/Makefile from /root/reference, git-ignored) is what bench.py's CPU arm times: its files
+    match the recorded SHA-256 sums and, on a seeded batch, the unmodified modules give the oracle's numbers."""
+    import hashlib
+    import os
+    import pytest
+    from oracle import ref_loader
+    from rbr_b200 import synth
+    if not ref_loader.available():
+        pytest.skip("oracle/_ref not built (make -C oracle where /root/reference exists)")
+    sums = open(os.path.join(ref_loader.REF_DIR, "SHA256SUMS")).read().split("\n")
+    n = 0
+    for line in sums:
+        if not line.strip():
+            continue
+        digest, rel = line.split()
+        assert hashlib.sha256(open(os.path.join(ref_loader.REF_DIR, rel), "rb").read()).hexdigest() == digest, rel
+        n += 1
+    assert n >= 15
+    cfg = dict(U=9, I=7, V=60, E=12, H=8, K=6, L=20, ks=(3,))
+    params = synth.deepconn_params(cfg["U"], cfg["I"], cfg["V"], cfg["E"], cfg["H"], cfg["K"], cfg["ks"], seed=1)
+    batch, ratings = synth.deepconn_batch(5, cfg["L"], cfg["V"], cfg["U"], cfg["I"], seed=3)
+    ref = ref_loader.build_reference("deepconn", cfg, params, dropout=0.0).train()
+    pred = ref(*batch)
+    loss = torch.nn.MSELoss()(pred, ratings)
+    loss.backward()
+    rp, rl, rg = orc.loss_and_grads("deepconn", params, batch, ratings)
+    assert rel_err(pred.detach(), rp) < 1e-6 and rel_err(loss.detach(), rl) < 1e-6
+    for k, p in ref.named_parameters():
+        assert rel_err(p.grad, rg[k]) < 1e-5, k
