@@ -355,6 +355,56 @@ def loss_and_grads(model: str, p: Params, batch: Sequence[Tensor], ratings: Tens
 
 
 # --------------------------------------------------------------------------------------
+# ReLU decision margins (test aid for full-size comparisons)
+# --------------------------------------------------------------------------------------
+def relu_margins(model: str, p: Params, batch: Sequence[Tensor], chunk: int = 512) -> Tensor:
+    """[B] per sample: the smallest |pre-activation| over every ReLU of the path that the sample owns — the pooled conv
+    features `max_t conv(x) + bias` (layers.py:108-109), NARRE's attention hidden units (narre.py:55) and the FM interaction
+    `u * i` (layers.py:200).  A ReLU whose input is within rounding of 0 may legitimately open on one implementation and
+    close on another (fp32 summation order), which moves that unit's whole gradient contribution; full-size parity tests
+    replace samples whose margin is below a threshold far above fp32 noise, then compare at the strict tolerance."""
+    assert model in ("deepconn", "narre")
+    table = p["word_embeddings.embedding.weight"]
+    ws, bs = _conv_params(p, "ngram.feature_layer.0.list_of_conv1d")
+
+    def pooled_pre(ids: Tensor, mask: Tensor) -> Tensor:                 # [N, L] → [N, H] (before the ReLU)
+        x = mask_rows(embedding_gather(table, ids), mask)
+        return torch.cat([conv1d_same(x, w, b).max(dim=1).values for w, b in zip(ws, bs)], dim=1)
+
+    n = batch[0].shape[0]
+    out = []
+    with torch.no_grad():
+        for lo in range(0, n, chunk):
+            sl = slice(lo, lo + chunk)
+            if model == "deepconn":
+                u_revs, i_revs, u_m, i_m, u_ids, i_ids = [t[sl] for t in batch]
+                u_pre, i_pre = pooled_pre(u_revs, u_m), pooled_pre(i_revs, i_m)
+                margin = torch.minimum(u_pre.abs().min(dim=1).values, i_pre.abs().min(dim=1).values)
+                u_txt, i_txt = torch.relu(u_pre), torch.relu(i_pre)
+            else:
+                u_text, i_text, u_m, i_m, u_ids, i_ids, reuid, reiid = [t[sl] for t in batch]
+                b, r, t = u_text.shape
+                u_pre = pooled_pre(u_text.reshape(b * r, t), u_m.reshape(b * r, t)).view(b, r, -1)
+                i_pre = pooled_pre(i_text.reshape(b * r, t), i_m.reshape(b * r, t)).view(b, r, -1)
+                margin = torch.minimum(u_pre.abs().flatten(1).min(dim=1).values, i_pre.abs().flatten(1).min(dim=1).values)
+                feats = []
+                for side, pre, oid in (("user", u_pre, reuid), ("item", i_pre, reiid)):
+                    f = torch.relu(pre)
+                    e = embedding_gather(p[f"{side}_att.ebd_vals.weight"], oid)
+                    hid = f @ p[f"{side}_att.W_rv"] + e @ p[f"{side}_att.W_id"] + p[f"{side}_att.b_1"]
+                    margin = torch.minimum(margin, hid.abs().flatten(1).min(dim=1).values)
+                    out_s, _ = linear_attention(f, oid, p[f"{side}_att.W_rv"], p[f"{side}_att.W_id"], p[f"{side}_att.h"],
+                                                p[f"{side}_att.b_1"], p[f"{side}_att.b_2"], p[f"{side}_att.ebd_vals.weight"])
+                    feats.append(out_s)
+                u_txt, i_txt = feats
+            u_f = last_feat(u_txt, u_ids, p["user_feat.W"], p["user_feat.b"], p["user_feat.ebd.weight"])
+            i_f = last_feat(i_txt, i_ids, p["item_feat.W"], p["item_feat.b"], p["item_feat.ebd.weight"])
+            margin = torch.minimum(margin, (u_f * i_f).abs().min(dim=1).values)
+            out.append(margin)
+    return torch.cat(out)
+
+
+# --------------------------------------------------------------------------------------
 # Timed CPU baseline (bench.py `cpu_baseline` / `--impl reference`)
 # --------------------------------------------------------------------------------------
 def time_fwd_bwd(model: str, p: Params, batch: Sequence[Tensor], ratings: Tensor, steps: int = 3,

@@ -54,7 +54,13 @@ def reference_classes():
 
 def build_reference(model: str, cfg: dict, params: dict, dropout: float = 0.0):
     """Reference nn.Module for `model` ("deepconn" | "narre" | "dual_att") with `params` (state_dict names) loaded."""
+    import contextlib
     D, N, A = reference_classes()
+    with contextlib.redirect_stdout(sys.stderr):            # the reference's constructors print; stdout belongs to bench.py's JSON line
+        return _build(D, N, A, model, cfg, params, dropout)
+
+
+def _build(D, N, A, model, cfg, params, dropout):
     if model == "deepconn":
         m = D(cfg["U"], cfg["I"], cfg["V"], list(cfg["ks"]), cfg["E"], cfg["H"], cfg["K"], cfg["L"], None, dropout)
     elif model == "narre":

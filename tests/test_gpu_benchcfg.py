@@ -50,6 +50,20 @@ def _encoder_oracle_pre(table64, w64, b64, ids, mask):
     return torch.relu(orc.conv1d_same(x, w64, b64))           # [N, L, H]
 
 
+def _clear_relu_margins(model_name, p64, batch, tau=2e-5):
+    """Replace (in place) the samples that own a ReLU whose input is within `tau` of 0 in the float64 oracle by copies of
+    samples that do not (orc.relu_margins): fp32 summation-order noise is ~1e-6 on these O(0.1-1) pre-activations, so on
+    the remaining batch every implementation opens and closes the same ReLUs.  Returns how many samples were replaced."""
+    margins = orc.relu_margins(model_name, p64, batch)
+    bad = (margins < tau).nonzero().flatten()
+    good = (margins >= 10 * tau).nonzero().flatten()
+    assert bad.numel() <= batch[0].shape[0] // 4 and good.numel() >= bad.numel()
+    for t in batch:
+        t[bad] = t[good[:bad.numel()]]
+    assert float(orc.relu_margins(model_name, p64, batch).min()) >= tau
+    return int(bad.numel())
+
+
 def _step(model, batch, ratings, fused_loss=False):
     model.zero_grad(set_to_none=True)
     if fused_loss:
@@ -77,6 +91,8 @@ def test_deepconn_full_config_vs_oracle(precision):
     bf = precision == "bf16"
     p64 = _f64(params, round_bf16=bf)
     tol, gtol = (BF16_TOL, BF16_TOL) if bf else (FP32_TOL, FP32_GRAD_TOL)
+    n_replaced = _clear_relu_margins("deepconn", p64, batch)
+    assert n_replaced < 200
     # forward routing: kernel arg-max positions attain the oracle's max
     with torch.no_grad():
         u_feat, i_feat, u_arg, i_arg = model.ngram.encode(model.word_embeddings, batch[:2], batch[2:4], return_argmax=True)
@@ -114,6 +130,7 @@ def test_narre_full_config_vs_oracle(precision):
     bf = precision == "bf16"
     p64 = _f64(params, round_bf16=bf)
     tol, gtol = (BF16_TOL, BF16_TOL) if bf else (FP32_TOL, FP32_GRAD_TOL)
+    _clear_relu_margins("narre", p64, batch)
     docs = [batch[0].view(-1, c["T"]), batch[1].view(-1, c["T"])]
     masks = [batch[2].view(-1, c["T"]), batch[3].view(-1, c["T"])]
     with torch.no_grad():
@@ -280,7 +297,7 @@ def test_fused_mse_head_matches_unfused_and_oracle(model_name):
     assert torch.equal(p0, p1)
     assert rel_err(l1.cpu(), l0.cpu()) < 1e-6
     for k in g0:
-        assert rel_err(g1[k].cpu(), g0[k].cpu(), grad_floor(k)) < 1e-6, k
+        assert rel_err(g1[k].cpu(), g0[k].cpu(), grad_floor(k)) < 5e-6, k          # two runs: fp32 atomics in a different order
     rp, rl, rg = orc.loss_and_grads(model_name, {k: v for k, v in params.items()}, [t.cpu() for t in batch], ratings.cpu())
     assert rel_err(l1.cpu(), orc.mse_loss(rp, ratings.cpu())) < FP32_TOL
     for k in rg:
