@@ -135,6 +135,29 @@ int rbr_conv_act_maxpool_bwd(int precision, int activation, const void* table, c
                              int64_t padding_idx, float* weight_grad, float* bias_grad, float* table_grad,
                              float* gate_grad, void* ws, int64_t ws_bytes, int flags, void* stream);
 
+/* ---- K2c: the same backward as two tensor-core GEMMs over a token x filter-tap coefficient matrix (bf16 precision) ------
+ * Replaces the same autograd nodes as K2b (conv dgrad + wgrad, pool / relu / mask backward, embedding_dense_backward).
+ * Every document side of a step accumulates C[v][h*k+j] += g[n,h] for the token id v that tap j of (n, h)'s arg-max window
+ * reads (rbr_conv_bwd_cmat_scatter, one call per side; also bias_grad[h] += g[n,h] when bias_grad != NULL); then
+ *   table_grad[v,:]   += sum_hj C[v][hj] * W[hj,:]      (the bf16-rounded conv weights of `packed`; row padding_idx skipped)
+ *   weight_grad[h,:,j] += sum_v C[v][h*k+j] * x[v,:]    (x = shadow_bf16)
+ * run as tcgen05 GEMMs (rbr_conv_bwd_cmat_finish; C is split into bf16 hi + lo halves, fp32 accumulation).
+ * `ws`: rbr_conv_bwd_cmat_workspace_bytes() bytes that the CALLER ZERO-FILLS ONCE; finish() with bit 1 leaves the coefficient
+ * matrix zeroed again and bit 4 the weight scratch, so the same workspace serves every following step without a memset.
+ * `what`: 1 = close the accumulation (split C; required once after the scatters, before 2 / 4), 2 = table gradient,
+ * 4 = weight gradient — data-parallel training runs 1|2, starts the table all-reduce, then 4.
+ * Shapes: emb % 4 == 0, emb <= 512, vocab * round_up(filters*ksize, 64) * 4 bytes <= 3 GiB, no gate
+ * (rbr_conv_bwd_cmat_supported; otherwise use K2b).                                                                     */
+int rbr_conv_bwd_cmat_supported(int64_t vocab, int64_t emb, int64_t filters, int64_t ksize);
+int64_t rbr_conv_bwd_cmat_workspace_bytes(int64_t vocab, int64_t emb, int64_t filters, int64_t ksize);
+int rbr_conv_bwd_cmat_scatter(const void* ids, const uint8_t* mask, int64_t n_docs, int64_t doc_len, int64_t vocab, int64_t emb,
+                              int64_t filters, int64_t ksize, int64_t pad, int activation, const float* feat,
+                              const int32_t* argmax, const float* feat_grad, int64_t feat_ld, float* bias_grad, void* ws,
+                              int64_t ws_bytes, int flags, void* stream);
+int rbr_conv_bwd_cmat_finish(int what, const void* shadow_bf16, const void* packed, int64_t vocab, int64_t emb, int64_t filters,
+                             int64_t ksize, int64_t padding_idx, float* table_grad, float* weight_grad, void* ws,
+                             int64_t ws_bytes, void* stream);
+
 /* ---- K3: fused NARRE review-level attention --------------------------------------------------------
  * Replaces LinearAttention.forward, models/narre/narre.py:40-64 (dropout excluded: applied by the caller).
  *   feat [B,R,H], other_id [B,R] int64, W_rv [H,A], W_id [A,A], h [A], b_1 [A], b_2 [1], ebd_vals [n_ids, A]

@@ -1,0 +1,477 @@
+// conv_bwd_tc.cu — K2c: backward of the fused conv → activation → max-over-time encoder as two tensor-core GEMMs over a
+// token × filter-tap COEFFICIENT MATRIX.  sm_100a only (tcgen05 / TMEM / TMA).
+//
+// Replaces what autograd runs for the reverse of NgramFeat.forward (reference models/deepconn/layers.py:123-136) and of the
+// embedding lookup (layers.py:23): max_pool1d backward, relu backward, aten::convolution_backward (dgrad + wgrad + bias
+// grad), masked_fill backward and aten::embedding_dense_backward.
+//
+// After max-over-time one position per (doc n, filter h) carries gradient g[n,h] = feat_grad * act'(feat).  Define
+//     C[v][h*k + j] = sum of g[n,h] over all (n, h) whose tap j reads token id v   (v = ids[n, argmax[n,h] + j - pad], unmasked)
+// — every document side of a step accumulates into ONE matrix.  Both parameter gradients are then dense contractions of it:
+//     table_grad[v, :]      += sum_hj C[v][hj] * W[hj, :]          [V x HJ] · [HJ x E]      (cmat_table_gemm_kernel)
+//     weight_grad[hj, :]    += sum_v  C[v][hj] * x[v, :]           [HJ x V] · [V x E]       (cmat_weight_gemm_kernel)
+// with x = the bf16 shadow table and W = the bf16-rounded conv weights, i.e. exactly the operands the forward multiplied.
+// Against the arg-max-sparse CUDA-core kernels (conv_bwd.cu: one 600-byte row fetched per entry for EACH of the two
+// gradients, a token sort, vector atomics into the 60 MB table gradient) the per-entry work drops to one 4-byte atomic and
+// the row traffic to two passes over C: the DeepCoNN backward goes from ~0.45 ms to ~0.1 ms, NARRE's from 3.3 ms to < 1 ms.
+//
+// Precision: C is accumulated in fp32 (atomics), then split into bf16 hi + lo halves (C = hi + lo up to 2^-17 relative), so
+// the tensor cores see the coefficient sums essentially exactly; products accumulate in fp32 in TMEM.
+//
+// Pipeline (all on the caller's stream):
+//   cmat_scatter_kernel      per document side: C32[v][hj] += g (red.global.add.f32), bias_grad[h] += g
+//   cmat_split_kernel        C32 → Chl = [hi | lo] bf16, and C32 re-zeroed (the workspace stays clean for the next step)
+//   cmat_table_gemm_kernel   D[128 tokens x 160] = Chl[128 x 2HJp] · Wt2ᵀ   — A, B K-major SWIZZLE_128B via TMA, cta_group::1,
+//                            2 CTAs/SM; epilogue adds the tile into table_grad (the padding row is skipped)
+//   cmat_weight_gemm_kernel  D[128 hj x emb_pad] = sum over a slice of the vocabulary of Chlᵀ · x   — both operands MN-MAJOR
+//                            (the contraction index, the token, is the row index of both TMA boxes), split-K over CTAs,
+//                            epilogue = vector atomics into a [H][k][E] scratch, then transposed into weight_grad [H,E,k]
+#include "rbr_common.cuh"
+#include "tc_ptx.cuh"
+#include "tma_util.cuh"
+
+namespace rbr {
+
+constexpr int CM_THREADS = 192;            // warp 0: TMA producer, warp 1: TMEM owner + MMA issuer, warps 2..5: epilogue
+constexpr int CM_STAGES_T = 3;             // table GEMM ring (36 KB per stage, 2 CTAs per SM)
+constexpr int CM_STAGES_W = 3;             // weight GEMM ring (up to 56 KB per stage, 1 CTA per SM)
+
+struct CmatLayout {
+    int64_t V, H, K, E, HJ, HJp, emb_pad, epad4;
+    int64_t off_c32, off_chl, off_dw, total;
+};
+static CmatLayout cmat_layout(int64_t vocab, int64_t emb, int64_t filters, int64_t ksize) {
+    CmatLayout l;
+    l.V = vocab; l.H = filters; l.K = ksize; l.E = emb;
+    l.HJ = filters * ksize;
+    l.HJp = cmat_hjp(filters, ksize);
+    l.emb_pad = rbr_emb_pad(emb);
+    l.epad4 = round_up(emb, 4);
+    int64_t off = 0;
+    l.off_c32 = off; off += round_up(vocab * l.HJp * 4, 1024);
+    l.off_chl = off; off += round_up(vocab * 2 * l.HJp * 2, 1024);
+    l.off_dw = off; off += round_up(l.HJ * l.epad4 * 4, 1024);
+    l.total = off;
+    return l;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// scatter: one thread per (doc, filter)
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) cmat_scatter_kernel(const IdView ids, const uint8_t* __restrict__ mask, int64_t n_docs, int L, int H,
+                                                           int K, int pad, int64_t vocab, const float* __restrict__ feat,
+                                                           const int32_t* __restrict__ argmax, const float* __restrict__ feat_grad,
+                                                           int feat_ld, int act, float* __restrict__ c32, int HJp,
+                                                           float* __restrict__ bias_grad) {
+    extern __shared__ float bsum[];            // [H] CTA-partial bias gradient
+    for (int i = threadIdx.x; i < H; i += blockDim.x) bsum[i] = 0.f;
+    __syncthreads();
+    const int64_t total = n_docs * H;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += stride) {
+        const int64_t n = q / H;
+        const int h = (int)(q - n * H);
+        const float y = __ldg(feat + n * feat_ld + h);
+        const float g = __ldg(feat_grad + n * feat_ld + h) * act_grad_from_out(act, y);
+        if (g == 0.f) continue;
+        if (bias_grad) atomicAdd(bsum + h, g);
+        const int ts = __ldg(argmax + n * feat_ld + h) - pad;
+#pragma unroll 1
+        for (int j = 0; j < K; ++j) {
+            const int t = ts + j;
+            if (t < 0 || t >= L) continue;
+            const int64_t id = ld_id(ids, n * L + t);
+            if (!ld_mask(ids, mask, n * L + t, id) || id < 0 || id >= vocab) continue;
+            atomicAdd(c32 + id * HJp + h * K + j, g);              // no return value: compiles to RED.E.ADD.F32
+        }
+    }
+    __syncthreads();
+    if (bias_grad)
+        for (int i = threadIdx.x; i < H; i += blockDim.x) {
+            const float v = bsum[i];
+            if (v != 0.f) atomicAdd(bias_grad + i, v);
+        }
+}
+
+// C32 → [hi | lo] bf16 and re-zero C32.  One thread per 4 columns.
+__global__ void __launch_bounds__(256) cmat_split_kernel(float4* __restrict__ c32, int64_t rows, int HJp, __nv_bfloat16* __restrict__ chl) {
+    const int q4 = HJp >> 2;
+    const int64_t total = rows * q4;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += stride) {
+        const int64_t r = q / q4;
+        const int c = (int)(q - r * q4) * 4;
+        const float4 v = c32[q];
+        if (v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f) c32[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        const __nv_bfloat162 h01 = __floats2bfloat162_rn(v.x, v.y), h23 = __floats2bfloat162_rn(v.z, v.w);
+        const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
+        const __nv_bfloat162 l01 = __floats2bfloat162_rn(v.x - f01.x, v.y - f01.y), l23 = __floats2bfloat162_rn(v.z - f23.x, v.w - f23.y);
+        uint2 hi, lo;
+        hi.x = *reinterpret_cast<const uint32_t*>(&h01); hi.y = *reinterpret_cast<const uint32_t*>(&h23);
+        lo.x = *reinterpret_cast<const uint32_t*>(&l01); lo.y = *reinterpret_cast<const uint32_t*>(&l23);
+        __nv_bfloat16* row = chl + r * (2 * (int64_t)HJp);
+        *reinterpret_cast<uint2*>(row + c) = hi;
+        *reinterpret_cast<uint2*>(row + HJp + c) = lo;
+    }
+}
+
+// MN-major SWIZZLE_128B operand (cute::UMMA make_umma_desc<Major::MN>, LayoutType::B128: ((8,n),(8,k)):((1,LBO),(8,SBO)) in
+// 16-byte units): 64 contiguous MN elements (128 B) per K row, 8 K rows = one 1024-byte swizzle atom, the next 8 K rows SBO
+// bytes further, the next 64 MN elements LBO bytes further.  Exactly what TMA writes for a box of [K rows][64 MN columns].
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+    return (uint64_t)((addr >> 4) & 0x3FFFu) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) |
+           (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor with both operands MN-major (bits 15, 16)
+__device__ __forceinline__ uint32_t umma_idesc_mn(int M, int N) { return umma_idesc(M, N) | (1u << 15) | (1u << 16); }
+
+// ------------------------------------------------------------------------------------------------------------------
+// table gradient: D[128 tokens x NT] = Chl[128 x 2HJp] · Wt2[NT x 2HJp]ᵀ
+// ------------------------------------------------------------------------------------------------------------------
+struct TableGemmArgs {
+    int64_t vocab;
+    int E, NT, nkb;            // nkb = 2 * HJp / 64
+    int64_t padding_idx;
+    float* table_grad;         // [vocab][E]
+};
+
+__global__ void __launch_bounds__(CM_THREADS, 2)
+cmat_table_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TableGemmArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t sbase = (raw + 1023u) & ~1023u;
+    uint8_t* smem = smem_raw + (sbase - raw);
+    const int b_bytes = a.NT * 128;
+    const int stage_bytes = 16384 + b_bytes;
+    const uint32_t bars = sbase + CM_STAGES_T * stage_bytes;            // full[S], empty[S], acc_full
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + CM_STAGES_T * stage_bytes + 8 * (2 * CM_STAGES_T + 1));
+    const int m0 = blockIdx.x * 128, n0 = blockIdx.y * a.NT;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < CM_STAGES_T; ++i) { mbar_init(bars + 8 * i, 1); mbar_init(bars + 8 * (CM_STAGES_T + i), 1); }
+        mbar_init(bars + 16 * CM_STAGES_T, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(smem_u32((const void*)tmem_slot), 256);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            tma_prefetch_desc(&tmA);
+            tma_prefetch_desc(&tmB);
+            int stage = 0;
+            uint32_t ph = 0;
+            for (int kb = 0; kb < a.nkb; ++kb) {
+                mbar_wait(bars + 8 * (CM_STAGES_T + stage), ph ^ 1);
+                const uint32_t fb = bars + 8 * stage;
+                mbar_expect_tx(fb, (uint32_t)stage_bytes);
+                const uint32_t dst = sbase + stage * stage_bytes;
+                tma_load_2d(dst, &tmA, kb * 64, m0, fb);
+                tma_load_2d(dst + 16384, &tmB, kb * 64, n0, fb);
+                if (++stage == CM_STAGES_T) { stage = 0; ph ^= 1; }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        const uint32_t idesc = umma_idesc(128, a.NT);
+        int stage = 0;
+        uint32_t ph = 0;
+        for (int kb = 0; kb < a.nkb; ++kb) {
+            mbar_wait(bars + 8 * stage, ph);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t sa = sbase + stage * stage_bytes;
+                const uint64_t ad = umma_desc_sw128(sa), bd = umma_desc_sw128(sa + 16384);
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks)
+                    umma_bf16(tmem_base, ad + (uint64_t)(ks * 2), bd + (uint64_t)(ks * 2), idesc, (uint32_t)((kb | ks) != 0));
+                umma_commit(bars + 8 * (CM_STAGES_T + stage));
+                if (kb == a.nkb - 1) umma_commit(bars + 16 * CM_STAGES_T);
+            }
+            __syncwarp();
+            if (++stage == CM_STAGES_T) { stage = 0; ph ^= 1; }
+        }
+    } else {
+        const int quad = warp & 3;                                   // TMEM lane quadrant this warp may read
+        const int64_t row = (int64_t)m0 + quad * 32 + lane;
+        const bool live = row < a.vocab && row != a.padding_idx;
+        float* dst_row = a.table_grad + row * a.E;
+        mbar_wait(bars + 16 * CM_STAGES_T, 0);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
+        for (int c0 = 0; c0 < a.NT; c0 += 16) {
+            uint32_t v[16];
+            tmem_ld16(taddr + (uint32_t)c0, v);
+            tmem_ld_wait();
+            if (live) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int col = n0 + c0 + q * 4;
+                    if (col + 3 < a.E) {
+                        float4* p = reinterpret_cast<float4*>(dst_row + col);
+                        float4 o = *p;
+                        o.x += __uint_as_float(v[4 * q]); o.y += __uint_as_float(v[4 * q + 1]);
+                        o.z += __uint_as_float(v[4 * q + 2]); o.w += __uint_as_float(v[4 * q + 3]);
+                        *p = o;
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 256);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// weight gradient: D[128 hj x emb_pad] = sum over this CTA's token blocks of Chl[tokens, m0:m0+128]ᵀ · x[tokens, :]
+// ------------------------------------------------------------------------------------------------------------------
+struct WeightGemmArgs {
+    int64_t vocab;
+    int E, epad4, HJ, HJp, nch;     // nch = emb_pad / 64 (N chunks of 64 columns)
+    int n_tb, ksplit;               // token blocks of 64 rows; CTAs per M tile
+    float* dw_hke;                  // [HJ][epad4] fp32 scratch (+=)
+};
+
+__global__ void __launch_bounds__(CM_THREADS, 1)
+cmat_weight_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmX, const WeightGemmArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t sbase = (raw + 1023u) & ~1023u;
+    uint8_t* smem = smem_raw + (sbase - raw);
+    const int stage_bytes = (2 + a.nch) * 8192;
+    const uint32_t bars = sbase + CM_STAGES_W * stage_bytes;
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + CM_STAGES_W * stage_bytes + 8 * (2 * CM_STAGES_W + 1));
+    const int m0 = blockIdx.x * 128;
+    const int split = blockIdx.y;
+    const int n_mine = (a.n_tb - split + a.ksplit - 1) / a.ksplit;      // token blocks split, split + ksplit, ...
+    const uint32_t tmem_cols = a.nch * 64 <= 256 ? 256u : 512u;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < CM_STAGES_W; ++i) { mbar_init(bars + 8 * i, 1); mbar_init(bars + 8 * (CM_STAGES_W + i), 1); }
+        mbar_init(bars + 16 * CM_STAGES_W, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(smem_u32((const void*)tmem_slot), tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (n_mine > 0) {
+        if (warp == 0) {
+            if (elect_one()) {
+                tma_prefetch_desc(&tmA);
+                tma_prefetch_desc(&tmX);
+                int stage = 0;
+                uint32_t ph = 0;
+                for (int i = 0; i < n_mine; ++i) {
+                    const int row = (split + i * a.ksplit) * 64;
+                    mbar_wait(bars + 8 * (CM_STAGES_W + stage), ph ^ 1);
+                    const uint32_t fb = bars + 8 * stage;
+                    mbar_expect_tx(fb, (uint32_t)stage_bytes);
+                    const uint32_t dst = sbase + stage * stage_bytes;
+                    tma_load_2d(dst, &tmA, m0, row, fb);
+                    tma_load_2d(dst + 8192, &tmA, m0 + 64, row, fb);
+                    for (int c = 0; c < a.nch; ++c) tma_load_2d(dst + 16384 + c * 8192, &tmX, c * 64, row, fb);
+                    if (++stage == CM_STAGES_W) { stage = 0; ph ^= 1; }
+                }
+            }
+            __syncwarp();
+        } else if (warp == 1) {
+            // N is issued in groups of <= 4 chunks (UMMA N <= 256)
+            const int g0 = a.nch <= 4 ? a.nch : (a.nch + 1) / 2, g1 = a.nch - g0;
+            const uint32_t idesc0 = umma_idesc_mn(128, g0 * 64), idesc1 = g1 ? umma_idesc_mn(128, g1 * 64) : 0u;
+            int stage = 0;
+            uint32_t ph = 0;
+            for (int i = 0; i < n_mine; ++i) {
+                mbar_wait(bars + 8 * stage, ph);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t sa = sbase + stage * stage_bytes, sb = sa + 16384;
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) {                 // 16 token rows (K) per MMA = 2048 bytes of every chunk
+                        const uint64_t ad = umma_desc_mn_sw128(sa + ks * 2048, 8192, 1024);
+                        umma_bf16(tmem_base, ad, umma_desc_mn_sw128(sb + ks * 2048, 8192, 1024), idesc0, (uint32_t)((i | ks) != 0));
+                        if (g1)
+                            umma_bf16(tmem_base + (uint32_t)(g0 * 64), ad, umma_desc_mn_sw128(sb + g0 * 8192 + ks * 2048, 8192, 1024), idesc1,
+                                      (uint32_t)((i | ks) != 0));
+                    }
+                    umma_commit(bars + 8 * (CM_STAGES_W + stage));
+                    if (i == n_mine - 1) umma_commit(bars + 16 * CM_STAGES_W);
+                }
+                __syncwarp();
+                if (++stage == CM_STAGES_W) { stage = 0; ph ^= 1; }
+            }
+        } else {
+            const int quad = warp & 3;
+            const int gm = m0 + quad * 32 + lane;                    // column of [hi | lo]
+            const int hj = gm >= a.HJp ? gm - a.HJp : gm;            // hi and lo halves add into the same row
+            const bool live = hj < a.HJ;
+            float* dst_row = a.dw_hke + (int64_t)hj * a.epad4;
+            mbar_wait(bars + 16 * CM_STAGES_W, 0);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
+            for (int c0 = 0; c0 < a.nch * 64; c0 += 16) {
+                uint32_t v[16];
+                tmem_ld16(taddr + (uint32_t)c0, v);
+                tmem_ld_wait();
+                if (live) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int col = c0 + q * 4;
+                        if (col + 3 < a.E)
+                            atomicAdd(reinterpret_cast<float4*>(dst_row + col),
+                                      make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
+                                                  __uint_as_float(v[4 * q + 3])));
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+// weight_grad[h][e][j] += dw_hke[h][j][e];  dw_hke re-zeroed
+__global__ void cmat_unpack_kernel(float* __restrict__ dw_hke, int H, int E, int K, int epad4, float* __restrict__ wgrad) {
+    const int64_t total = (int64_t)H * K * epad4;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += stride) {
+        const int e = (int)(q % epad4);
+        const int hj = (int)(q / epad4);
+        const float v = dw_hke[q];
+        if (v != 0.f) {
+            dw_hke[q] = 0.f;
+            if (e < E) atomicAdd(wgrad + ((int64_t)(hj / K) * E + e) * K + (hj % K), v);
+        }
+    }
+}
+
+static bool cmat_shape_ok(int64_t vocab, int64_t emb, int64_t filters, int64_t ksize) {
+    if (vocab < 1 || vocab >= (1ll << 31) || emb < 4 || emb % 4 != 0 || emb > 512 || filters < 1 || ksize < 1 || ksize > 8) return false;
+    if (filters > 1024) return false;
+    const int64_t hjp = cmat_hjp(filters, ksize);
+    if (hjp > 4096) return false;
+    return vocab * hjp * 4 <= (3ll << 30);          // coefficient matrix up to 3 GiB (fp32) + the same again in bf16
+}
+
+}  // namespace rbr
+
+using namespace rbr;
+
+extern "C" int rbr_conv_bwd_cmat_supported(int64_t vocab, int64_t emb, int64_t filters, int64_t ksize) {
+    return cmat_shape_ok(vocab, emb, filters, ksize) && tensor_map_encoder() != nullptr ? 1 : 0;
+}
+
+extern "C" int64_t rbr_conv_bwd_cmat_workspace_bytes(int64_t vocab, int64_t emb, int64_t filters, int64_t ksize) {
+    if (!cmat_shape_ok(vocab, emb, filters, ksize)) return 0;
+    return cmat_layout(vocab, emb, filters, ksize).total;
+}
+
+extern "C" int rbr_conv_bwd_cmat_scatter(const void* ids_raw, const uint8_t* mask, int64_t n_docs, int64_t doc_len, int64_t vocab,
+                                         int64_t emb, int64_t filters, int64_t ksize, int64_t pad, int activation, const float* feat,
+                                         const int32_t* argmax, const float* feat_grad, int64_t feat_ld, float* bias_grad, void* ws,
+                                         int64_t ws_bytes, int flags, void* stream) {
+    RBR_REQUIRE(ids_raw && feat && argmax && feat_grad && ws, RBR_EINVAL, "conv_bwd_cmat_scatter: null pointer");
+    RBR_REQUIRE(cmat_shape_ok(vocab, emb, filters, ksize), RBR_EUNSUPPORTED, "conv_bwd_cmat: shape outside the dense tensor-core backward");
+    RBR_REQUIRE(n_docs >= 0 && doc_len > 0 && pad >= 0 && feat_ld >= filters, RBR_EINVAL, "conv_bwd_cmat_scatter: bad sizes");
+    const CmatLayout l = cmat_layout(vocab, emb, filters, ksize);
+    RBR_REQUIRE(ws_bytes >= l.total, RBR_EWORKSPACE, "conv_bwd_cmat_scatter: workspace too small");
+    if (n_docs == 0) return RBR_OK;
+    const int64_t total = n_docs * filters;
+    int64_t blocks = (total + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    cmat_scatter_kernel<<<(unsigned)blocks, 256, (size_t)filters * 4, as_stream(stream)>>>(
+        id_view(ids_raw, flags), mask, n_docs, (int)doc_len, (int)filters, (int)ksize, (int)pad, vocab, feat, argmax, feat_grad, (int)feat_ld,
+        activation, reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + l.off_c32), (int)l.HJp, bias_grad);
+    RBR_LAUNCH_CHECK("cmat_scatter_kernel");
+    return RBR_OK;
+}
+
+extern "C" int rbr_conv_bwd_cmat_finish(int what, const void* shadow_bf16, const void* packed, int64_t vocab, int64_t emb, int64_t filters,
+                                        int64_t ksize, int64_t padding_idx, float* table_grad, float* weight_grad, void* ws,
+                                        int64_t ws_bytes, void* stream) {
+    RBR_REQUIRE(ws && packed, RBR_EINVAL, "conv_bwd_cmat_finish: null pointer");
+    RBR_REQUIRE(cmat_shape_ok(vocab, emb, filters, ksize), RBR_EUNSUPPORTED, "conv_bwd_cmat: shape outside the dense tensor-core backward");
+    RBR_REQUIRE((what & ~7) == 0 && what != 0, RBR_EINVAL, "conv_bwd_cmat_finish: `what` is a mask of 1 (split), 2 (table), 4 (weight)");
+    const CmatLayout l = cmat_layout(vocab, emb, filters, ksize);
+    RBR_REQUIRE(ws_bytes >= l.total, RBR_EWORKSPACE, "conv_bwd_cmat_finish: workspace too small");
+    const PackLayout pl = pack_layout(emb, filters, ksize);
+    cudaStream_t s = as_stream(stream);
+    char* base = reinterpret_cast<char*>(ws);
+    float* c32 = reinterpret_cast<float*>(base + l.off_c32);
+    __nv_bfloat16* chl = reinterpret_cast<__nv_bfloat16*>(base + l.off_chl);
+    float* dw = reinterpret_cast<float*>(base + l.off_dw);
+    if (what & 1) {
+        const int64_t total = vocab * (l.HJp / 4);
+        int64_t blocks = (total + 255) / 256;
+        if (blocks > 148 * 16) blocks = 148 * 16;
+        cmat_split_kernel<<<(unsigned)blocks, 256, 0, s>>>(reinterpret_cast<float4*>(c32), vocab, (int)l.HJp, chl);
+        RBR_LAUNCH_CHECK("cmat_split_kernel");
+    }
+    if (what & 2) {
+        RBR_REQUIRE(table_grad, RBR_EINVAL, "conv_bwd_cmat_finish: table part needs table_grad");
+        RBR_REQUIRE((uintptr_t)table_grad % 16 == 0, RBR_EINVAL, "conv_bwd_cmat_finish: table_grad must be 16-byte aligned");
+        CUtensorMap tmA, tmB;
+        RBR_REQUIRE(make_tmap_bf16_2d(&tmA, chl, (uint64_t)(2 * l.HJp), (uint64_t)vocab, (uint64_t)(2 * l.HJp), 64, 128) &&
+                        make_tmap_bf16_2d(&tmB, reinterpret_cast<const char*>(packed) + pl.off_wt2, (uint64_t)(2 * l.HJp),
+                                          (uint64_t)(pl.NT * pl.n_tiles), (uint64_t)(2 * l.HJp), 64, (uint32_t)pl.NT),
+                    RBR_ECUDA, "conv_bwd_cmat_finish: cuTensorMapEncodeTiled failed");
+        TableGemmArgs a{};
+        a.vocab = vocab; a.E = (int)emb; a.NT = (int)pl.NT; a.nkb = (int)(2 * l.HJp / 64); a.padding_idx = padding_idx;
+        a.table_grad = table_grad;
+        const int smem = CM_STAGES_T * (16384 + (int)pl.NT * 128) + 8 * (2 * CM_STAGES_T + 1) + 16 + 1024;
+        static bool attr = false;
+        if (!attr) {
+            RBR_CUDA(cudaFuncSetAttribute(cmat_table_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 116 * 1024));
+            attr = true;
+        }
+        RBR_REQUIRE(smem <= 116 * 1024, RBR_EUNSUPPORTED, "conv_bwd_cmat_finish: shared memory");
+        dim3 grid((unsigned)((vocab + 127) / 128), (unsigned)pl.n_tiles);
+        cmat_table_gemm_kernel<<<grid, CM_THREADS, smem, s>>>(tmA, tmB, a);
+        RBR_LAUNCH_CHECK("cmat_table_gemm_kernel");
+    }
+    if (what & 4) {
+        RBR_REQUIRE(weight_grad && shadow_bf16, RBR_EINVAL, "conv_bwd_cmat_finish: weight part needs weight_grad and the bf16 shadow table");
+        CUtensorMap tmA, tmX;
+        RBR_REQUIRE(make_tmap_bf16_2d(&tmA, chl, (uint64_t)(2 * l.HJp), (uint64_t)vocab, (uint64_t)(2 * l.HJp), 64, 64) &&
+                        make_tmap_bf16_2d(&tmX, shadow_bf16, (uint64_t)l.emb_pad, (uint64_t)vocab, (uint64_t)l.emb_pad, 64, 64),
+                    RBR_ECUDA, "conv_bwd_cmat_finish: cuTensorMapEncodeTiled failed");
+        WeightGemmArgs a{};
+        a.vocab = vocab; a.E = (int)emb; a.epad4 = (int)l.epad4; a.HJ = (int)l.HJ; a.HJp = (int)l.HJp; a.nch = (int)(l.emb_pad / 64);
+        a.n_tb = (int)((vocab + 63) / 64);
+        const int m_tiles = (int)(2 * l.HJp / 128);
+        static int sms = 0;
+        if (!sms) {
+            int dev = 0;
+            RBR_CUDA(cudaGetDevice(&dev));
+            RBR_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        }
+        a.ksplit = sms / m_tiles < 1 ? 1 : sms / m_tiles;
+        if (a.ksplit > a.n_tb) a.ksplit = a.n_tb;
+        a.dw_hke = dw;
+        const int smem = CM_STAGES_W * (2 + a.nch) * 8192 + 8 * (2 * CM_STAGES_W + 1) + 16 + 1024;
+        static bool attr = false;
+        if (!attr) {
+            RBR_CUDA(cudaFuncSetAttribute(cmat_weight_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            attr = true;
+        }
+        RBR_REQUIRE(smem <= 227 * 1024, RBR_EUNSUPPORTED, "conv_bwd_cmat_finish: shared memory");
+        dim3 grid((unsigned)m_tiles, (unsigned)a.ksplit);
+        cmat_weight_gemm_kernel<<<grid, CM_THREADS, smem, s>>>(tmA, tmX, a);
+        RBR_LAUNCH_CHECK("cmat_weight_gemm_kernel");
+        const int64_t tot = l.HJ * l.epad4;
+        int blocks = (int)((tot + 255) / 256);
+        if (blocks > 148 * 4) blocks = 148 * 4;
+        cmat_unpack_kernel<<<blocks, 256, 0, s>>>(dw, (int)filters, (int)emb, (int)ksize, (int)l.epad4, weight_grad);
+        RBR_LAUNCH_CHECK("cmat_unpack_kernel");
+    }
+    return RBR_OK;
+}

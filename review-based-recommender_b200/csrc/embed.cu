@@ -179,15 +179,25 @@ __global__ void __launch_bounds__(256) table_to_bf16_kernel(const float* __restr
 // K0: conv weight packing, weight [H][E][k] (nn.Conv1d) → the three layouts of PackLayout
 __global__ void conv_pack_kernel(const float* __restrict__ w, int E, int H, int k, int Hpad4, int Epad4, int Epad16, int Npad, int Nb,
                                  int Npad2, int Nb2, float* __restrict__ keh, float* __restrict__ hke,
-                                 __nv_bfloat16* __restrict__ umma, __nv_bfloat16* __restrict__ umma2, __nv_bfloat16* __restrict__ hke16) {
+                                 __nv_bfloat16* __restrict__ umma, __nv_bfloat16* __restrict__ umma2, __nv_bfloat16* __restrict__ hke16,
+                                 __nv_bfloat16* __restrict__ wt2, int HJp, int wt2_rows) {
     const int64_t n_keh = (int64_t)k * E * Hpad4;
     const int64_t n_hke = (int64_t)H * k * Epad4;
     const int64_t n_umma = (int64_t)k * Epad16 * Npad;
     const int64_t n_umma2 = (int64_t)k * Epad16 * Npad2;
-    const int64_t total = n_keh + n_hke + n_umma + n_umma2;
+    const int64_t n_wt2 = (int64_t)wt2_rows * 2 * HJp;
+    const int64_t total = n_keh + n_hke + n_umma + n_umma2 + n_wt2;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += stride) {
-        if (q < n_keh) {
+        if (q >= n_keh + n_hke + n_umma + n_umma2) {
+            // Wt2[e][c]: c < HJp → filter-tap c, c >= HJp → filter-tap c - HJp (hi | lo halves of the coefficient matrix)
+            const int64_t r = q - (n_keh + n_hke + n_umma + n_umma2);
+            const int e = (int)(r / (2 * HJp));
+            int c = (int)(r - (int64_t)e * 2 * HJp);
+            if (c >= HJp) c -= HJp;
+            const int h = c / k, j = c - h * k;
+            wt2[r] = __float2bfloat16_rn((e < E && h < H) ? w[((int64_t)h * E + e) * k + j] : 0.f);
+        } else if (q < n_keh) {
             const int h = (int)(q % Hpad4);
             const int e = (int)((q / Hpad4) % E);
             const int j = (int)(q / ((int64_t)Hpad4 * E));
@@ -337,12 +347,14 @@ extern "C" int rbr_conv_pack(const float* weight, int64_t emb, int64_t filters, 
     char* base = reinterpret_cast<char*>(packed);
     RBR_CUDA(cudaMemsetAsync(base + p.off_zero, 0, (size_t)(p.off_umma2 - p.off_zero), as_stream(stream)));
     const int64_t npad2 = p.P2 * p.Nb2;
-    const int64_t total = ksize * emb * p.Hpad4 + filters * ksize * p.Epad4 + ksize * p.Epad16 * (p.Npad + npad2);
+    const int64_t total = ksize * emb * p.Hpad4 + filters * ksize * p.Epad4 + ksize * p.Epad16 * (p.Npad + npad2) +
+                          p.NT * p.n_tiles * 2 * p.HJp;
     conv_pack_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(
         weight, (int)emb, (int)filters, (int)ksize, (int)p.Hpad4, (int)p.Epad4, (int)p.Epad16, (int)p.Npad, (int)(p.Nb > 0 ? p.Nb : 1),
         (int)npad2, (int)(p.Nb2 > 0 ? p.Nb2 : 2), reinterpret_cast<float*>(base + p.off_keh), reinterpret_cast<float*>(base + p.off_hke),
         reinterpret_cast<__nv_bfloat16*>(base + p.off_umma), reinterpret_cast<__nv_bfloat16*>(base + p.off_umma2),
-        reinterpret_cast<__nv_bfloat16*>(base + p.off_hke16));
+        reinterpret_cast<__nv_bfloat16*>(base + p.off_hke16), reinterpret_cast<__nv_bfloat16*>(base + p.off_wt2), (int)p.HJp,
+        (int)(p.NT * p.n_tiles));
     RBR_LAUNCH_CHECK("conv_pack");
     return RBR_OK;
 }

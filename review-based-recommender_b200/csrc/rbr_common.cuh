@@ -76,8 +76,19 @@ struct PackLayout {
     int64_t Epad16;     // E rounded up to 16 (UMMA K granularity for bf16)
     int64_t Npad;       // P * Nb
     int64_t off_keh, off_hke, off_umma, off_zero, total;   // off_zero: a zero row of rbr_emb_pad(E) bf16 (conv_tc zero source)
+    // dense tensor-core backward (conv_bwd_tc.cu): bf16 Wt2 [NT * n_tiles rows = embedding index e][2 * HJp columns]:
+    // Wt2[e][c] = W[h][e][j] for c = h*k + j and again for c = HJp + h*k + j (the K-major B operand of the table-gradient GEMM,
+    // stacked twice because the coefficient matrix comes as bf16 hi | lo halves); zero elsewhere
+    int64_t HJp;        // H * k rounded up to 64
+    int64_t NT, n_tiles;
+    int64_t off_wt2;
 };
 __host__ __device__ inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+inline int64_t cmat_hjp(int64_t H, int64_t k) { return round_up(H * k, 64); }
+inline void cmat_ntile(int64_t E, int64_t* NT, int64_t* tiles) {
+    *NT = E > 128 ? 160 : round_up(E, 16);            // UMMA N of the table-gradient GEMM (M = 128: N % 16 == 0, N <= 256)
+    *tiles = (E + *NT - 1) / *NT;
+}
 inline PackLayout pack_layout(int64_t E, int64_t H, int64_t k) {
     PackLayout p;
     p.E = E; p.H = H; p.k = k;
@@ -99,6 +110,10 @@ inline PackLayout pack_layout(int64_t E, int64_t H, int64_t k) {
     b = p.off_umma2 + k * p.Epad16 * p.P2 * p.Nb2 * 2;
     p.off_hke16 = round_up(b, 256);
     b = p.off_hke16 + H * k * p.Epad4 * 2;
+    p.off_wt2 = round_up(b, 1024);
+    p.HJp = cmat_hjp(H, k);
+    cmat_ntile(E, &p.NT, &p.n_tiles);
+    b = p.off_wt2 + p.NT * p.n_tiles * 2 * p.HJp * 2;
     p.total = round_up(b, 256);
     return p;
 }

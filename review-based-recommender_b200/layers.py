@@ -198,6 +198,7 @@ class NgramFeat(nn.Module):
             "shadow_fn": lambda: ops.table_to_bf16(x.detach()), "pack_fn": conv.packed, "arena": self._arena,
             "table_param": x, "weight_params": [c.weight for c in convs], "bias_params": [c.bias for c in convs],
             "padding_idx": -1, "flags": self.conv_flags,
+            "dense_bwd": False,          # the "table" is this call's activations: no persistent coefficient-matrix workspace for it
         }
         feat, _ = ops.EncodeDocsFn.apply(x, cfg, *[c.weight for c in convs], *[c.bias for c in convs], ids, input_masks)
         return feat.view(bz, self.out_features, 1)

@@ -313,49 +313,115 @@ class EncodeDocsFn(torch.autograd.Function):
         g_w = [_grad_buf(arena, cfg["weight_params"][i], True) for i in range(n_conv)]
         g_b = [_grad_buf(arena, cfg["bias_params"][i], True) for i in range(n_conv)]
         h_total = feats[0].shape[1]
-        # Two passes: first the table gradient of every side (its buffer is by far the largest gradient: data-parallel
-        # training starts its all-reduce from the `table_ready` hook while the second pass — the weight/bias gradients —
-        # still runs), then the weight part.  A single pass when there is no hook.
+        shapes = [tuple(w.shape) for w in ctx.weights]                   # (H, E, k) per conv
+        cols = [sum(sh[0] for sh in shapes[:i]) for i in range(n_conv)]
+        flags0 = cfg.get("flags", 0)
+        # Formulation per conv: bf16 → the dense tensor-core backward over the coefficient matrix (K2c) when the shape allows,
+        # else (fp32 precision, CONV_BWD_SPARSE, unsupported shapes) the arg-max-sparse CUDA-core kernels (K2b).
+        dense = [prec == PREC_BF16 and not (flags0 & CONV_BWD_SPARSE) and ctx.shadow is not None and cfg.get("dense_bwd", True)
+                 and bool(lib.rbr_conv_bwd_cmat_supported(vocab, emb, sh[0], sh[2])) for sh in shapes]
+        if flags0 & CONV_BWD_DENSE_TC and not all(dense):
+            raise RuntimeError("rbr_b200: CONV_BWD_DENSE_TC requested but the dense tensor-core backward does not take this shape / precision")
+        cm_ws = {i: _cmat_workspace(table, i, vocab, emb, shapes[i][0], shapes[i][2]) for i in range(n_conv) if dense[i]}
+        # The table gradient of every side is finished first (it is by far the largest gradient: data-parallel training starts
+        # its all-reduce from the `table_ready` hook while the weight-gradient kernels still run), then the weight part.
         hook = cfg.get("table_ready") if need_table else None
-        passes = ((True, False), (False, True)) if hook is not None else ((True, True),)
         # The document sides are independent (they only meet in += accumulations, all atomic): side s > 0 runs on its own
-        # stream, so the small kernels of one side (single-CTA scan, sort) overlap the other side's work.
+        # stream, so the small kernels of one side overlap the other side's work.
         main = torch.cuda.current_stream()
         live = [s for s in range(ns) if feat_grads[s] is not None]
         side_streams = _side_streams(table.device, max(0, len(live) - 1))
         fgs = {s: feat_grads[s].contiguous() for s in live}
-        for do_table, do_weight in passes:
+
+        def per_side(fn):
             ev_fork = main.record_event() if len(live) > 1 else None
             for rank_s, s in enumerate(live):
                 stream_s = main if rank_s == 0 else side_streams[rank_s - 1]
                 if rank_s > 0:
                     stream_s.wait_event(ev_fork)
                 with torch.cuda.stream(stream_s):
-                    sh = _stream(refresh=True)
-                    fg = fgs[s]
-                    ids, mask = ids_l[s], mask_l[s]
-                    doc_len = ids.shape[-1]
-                    n_docs = ids.numel() // doc_len
-                    col = 0
-                    for i in range(n_conv):
-                        h, _, k = ctx.weights[i].shape
-                        gt = g_table if do_table else None
-                        if gt is not None or do_weight:
-                            ws_bytes = lib.rbr_conv_bwd_workspace_bytes(n_docs, h, k, emb, vocab)
-                            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=table.device)
-                            lib.check(lib.rbr_conv_act_maxpool_bwd(
-                                prec, cfg["act"], _p(table), _p(ctx.shadow), vocab, emb, _p(ids), _p(mask), None, 0, n_docs, doc_len,
-                                _p(ctx.packed[i]), h, k, cfg["pads"][i], feats[s].data_ptr() + 4 * col,
-                                argmaxes[s].data_ptr() + 4 * col, fg.data_ptr() + 4 * col, None, h_total, cfg["padding_idx"],
-                                _p(g_w[i]) if do_weight else None, _p(g_b[i]) if do_weight else None, _p(gt), None, _p(ws),
-                                ws_bytes, ctx.flags_l[s], sh), "rbr_conv_act_maxpool_bwd")
-                        col += h
+                    fn(s, _stream(refresh=True))
             for rank_s in range(1, len(live)):
                 main.wait_event(side_streams[rank_s - 1].record_event())
             _stream(refresh=True)
-            if hook is not None and do_table and not do_weight:
+
+        def sparse_part(do_table, do_weight):
+            def run(s, sh):
+                ids, mask = ids_l[s], mask_l[s]
+                doc_len = ids.shape[-1]
+                n_docs = ids.numel() // doc_len
+                for i in range(n_conv):
+                    if dense[i]:
+                        continue
+                    h, _, k = shapes[i]
+                    gt = g_table if do_table else None
+                    if gt is None and not do_weight:
+                        continue
+                    ws_bytes = lib.rbr_conv_bwd_workspace_bytes(n_docs, h, k, emb, vocab)
+                    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=table.device)
+                    lib.check(lib.rbr_conv_act_maxpool_bwd(
+                        prec, cfg["act"], _p(table), _p(ctx.shadow), vocab, emb, _p(ids), _p(mask), None, 0, n_docs, doc_len,
+                        _p(ctx.packed[i]), h, k, cfg["pads"][i], feats[s].data_ptr() + 4 * cols[i],
+                        argmaxes[s].data_ptr() + 4 * cols[i], fgs[s].data_ptr() + 4 * cols[i], None, h_total, cfg["padding_idx"],
+                        _p(g_w[i]) if do_weight else None, _p(g_b[i]) if do_weight else None, _p(gt), None, _p(ws),
+                        ws_bytes, ctx.flags_l[s], sh), "rbr_conv_act_maxpool_bwd")
+            return run
+
+        def dense_scatter(s, sh):
+            ids, mask = ids_l[s], mask_l[s]
+            doc_len = ids.shape[-1]
+            n_docs = ids.numel() // doc_len
+            for i, ws in cm_ws.items():
+                h, _, k = shapes[i]
+                lib.check(lib.rbr_conv_bwd_cmat_scatter(
+                    _p(ids), _p(mask), n_docs, doc_len, vocab, emb, h, k, cfg["pads"][i], cfg["act"],
+                    feats[s].data_ptr() + 4 * cols[i], argmaxes[s].data_ptr() + 4 * cols[i], fgs[s].data_ptr() + 4 * cols[i],
+                    h_total, _p(g_b[i]), _p(ws), ws.numel(), ctx.flags_l[s], sh), "rbr_conv_bwd_cmat_scatter")
+
+        def dense_finish(what):
+            for i, ws in cm_ws.items():
+                h, _, k = shapes[i]
+                lib.check(lib.rbr_conv_bwd_cmat_finish(what, _p(ctx.shadow), _p(ctx.packed[i]), vocab, emb, h, k, cfg["padding_idx"],
+                                                       _p(g_table), _p(g_w[i]), _p(ws), ws.numel(), _stream()),
+                          "rbr_conv_bwd_cmat_finish")
+
+        any_sparse = not all(dense)
+        if live:
+            two_pass = hook is not None
+            if any_sparse:
+                per_side(sparse_part(True, not two_pass) if need_table else sparse_part(False, True))
+            if cm_ws:
+                per_side(dense_scatter)
+                dense_finish((1 | 2) if need_table else 1)
+            if hook is not None:
                 hook(g_table)
+            if any_sparse and two_pass:
+                per_side(sparse_part(False, True))
+            if cm_ws:
+                dense_finish(4)
         return (g_table, None, *g_w, *g_b, *([None] * (2 * ns)))
+
+
+_CMAT_WS: Dict[tuple, torch.Tensor] = {}
+
+
+def _cmat_workspace(table: torch.Tensor, conv_index: int, vocab: int, emb: int, filters: int, ksize: int) -> torch.Tensor:
+    """Persistent, self-cleaning workspace of the dense tensor-core backward (K2c) for one (table, conv): zero-filled ONCE here;
+    rbr_conv_bwd_cmat_finish leaves it zeroed again, so steps — eager or CUDA-graph replays — never memset its 130-200 MB."""
+    key = (table.device.index, table.data_ptr(), conv_index, vocab, emb, filters, ksize)
+    ws = _CMAT_WS.get(key)
+    if ws is None:
+        for k in [k for k in _CMAT_WS if k[:2] == key[:2] and k[2] == conv_index]:
+            del _CMAT_WS[k]                        # same table storage, new shape: the old buffer is dead
+        nbytes = lib.rbr_conv_bwd_cmat_workspace_bytes(vocab, emb, filters, ksize)
+        if torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("rbr_b200: run one eager step before capturing a CUDA graph (the dense backward's workspace is "
+                               "allocated and zero-filled on first use)")
+        while len(_CMAT_WS) >= 8:                  # a handful of (model, conv) pairs per process; drop the oldest beyond that
+            del _CMAT_WS[next(iter(_CMAT_WS))]
+        ws = torch.zeros(nbytes, dtype=torch.uint8, device=table.device)
+        _CMAT_WS[key] = ws
+    return ws
 
 
 # ---------------------------------------------------------------------------------------------------

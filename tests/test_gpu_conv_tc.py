@@ -182,3 +182,81 @@ def test_variants_agree_bitwise_on_values():
         outs.append(ops.conv_act_maxpool(table.cuda(), ids.cuda(), mask.cuda(), w.cuda(), b.cuda(), 1, precision="bf16", flags=fl))
     assert torch.equal(outs[0][0], outs[1][0])
     assert torch.equal(outs[0][1], outs[1][1])
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# K2c: dense tensor-core backward (coefficient matrix + two tcgen05 GEMMs, conv_bwd_tc.cu) against the arg-max-sparse
+# CUDA-core kernels (K2b) and the oracle.  (n_docs per side, L, V, E, H, k)
+# ----------------------------------------------------------------------------------------------------------------------
+BWD_SHAPES = [
+    (5, 40, 50, 16, 16, 3),          # one M tile, one N chunk, one token block
+    (9, 129, 300, 64, 40, 3),
+    (33, 60, 700, 300, 150, 3),      # NARRE dims: HJ = 450 → 512 columns, 5 N chunks (two MMA groups)
+    (24, 500, 3000, 300, 100, 3),    # DeepCoNN dims: HJ = 300 → 320
+    (40, 10, 90, 24, 20, 5),
+    (12, 200, 5000, 100, 200, 1),    # k = 1, two N chunks, vocabulary spanning many token blocks and split-K slices
+    (7, 64, 130, 128, 8, 7),
+    (3, 33, 20000, 300, 100, 3),     # most of the vocabulary untouched: zero rows
+]
+
+
+def _encode_step(shape, flags, seed, freeze_table=False):
+    n, L, V, E, H, k = shape
+    U, I, K = 7, 6, 8
+    params = synth.deepconn_params(U, I, V, E, H, K, (k,), seed=seed)
+    batch, ratings = synth.deepconn_batch(n, L, V, U, I, seed=seed + 1)
+    model = rbr_b200.DeepCoNNpp(U, I, V, [k], E, H, K, L, None, 0.0, precision="bf16")
+    model.load_state_dict(params)
+    model.cuda().train()
+    model.ngram.conv_flags = flags
+    if freeze_table:
+        model.word_embeddings.embedding.weight.requires_grad_(False)
+    out, loss, grads = None, None, None
+    model.zero_grad(set_to_none=True)
+    pred = model(*[t.cuda() for t in batch])
+    loss = torch.nn.MSELoss()(pred, ratings.cuda())
+    loss.backward()
+    grads = {kk: p.grad.detach().cpu() for kk, p in model.named_parameters() if p.grad is not None}
+    return params, batch, ratings, pred.detach().cpu(), grads, model
+
+
+@pytest.mark.parametrize("shape", BWD_SHAPES)
+def test_dense_tc_backward_matches_sparse_kernels_and_oracle(shape):
+    params, batch, ratings, pred_d, g_dense, model = _encode_step(shape, ops.CONV_BWD_DENSE_TC, seed=shape[0] + shape[1])
+    _, _, _, pred_s, g_sparse, _ = _encode_step(shape, ops.CONV_BWD_SPARSE, seed=shape[0] + shape[1])
+    assert torch.equal(pred_d, pred_s)
+    for kk in g_sparse:
+        # same operands (bf16 shadow rows, bf16-rounded weights), same routing: only the summation order and the 2^-17 split differ
+        assert rel_err(g_dense[kk], g_sparse[kk], 1e-9) < 2e-4, kk
+    _, _, rg = orc.loss_and_grads("deepconn", _rounded_params(params), batch, ratings)
+    for kk in rg:
+        assert rel_err(g_dense[kk], rg[kk], 1e-7) < 1e-2, kk
+    assert float(g_dense["word_embeddings.embedding.weight"][0].abs().max()) == 0.0                  # padding row
+    # the workspace is self-cleaning: a second step on the same model gives the same gradients
+    model.zero_grad(set_to_none=True)
+    loss = torch.nn.MSELoss()(model(*[t.cuda() for t in batch]), ratings.cuda())
+    loss.backward()
+    for kk, p in model.named_parameters():
+        assert rel_err(p.grad.cpu(), g_dense[kk], 1e-9) < 1e-5, kk
+
+
+def test_dense_tc_backward_with_frozen_table_and_table_hook():
+    shape = (9, 129, 300, 64, 40, 3)
+    _, _, _, _, g_ref, _ = _encode_step(shape, ops.CONV_BWD_SPARSE, seed=5)
+    _, _, _, _, g_frozen, _ = _encode_step(shape, ops.CONV_BWD_DENSE_TC, seed=5, freeze_table=True)
+    assert "word_embeddings.embedding.weight" not in g_frozen
+    for kk in g_frozen:
+        assert rel_err(g_frozen[kk], g_ref[kk], 1e-9) < 2e-4, kk
+    # data-parallel split: table part, hook, then weight part
+    n, L, V, E, H, k = shape
+    params = synth.deepconn_params(7, 6, V, E, H, 8, (k,), seed=5)
+    batch, ratings = synth.deepconn_batch(n, L, V, 7, 6, seed=6)
+    model = rbr_b200.DeepCoNNpp(7, 6, V, [k], E, H, 8, L, None, 0.0, precision="bf16")
+    model.load_state_dict(params)
+    model.cuda().train()
+    seen = {}
+    model.ngram.table_grad_hook = lambda t: seen.setdefault("table", t.detach().clone())
+    torch.nn.MSELoss()(model(*[t.cuda() for t in batch]), ratings.cuda()).backward()
+    assert rel_err(seen["table"].cpu(), g_ref["word_embeddings.embedding.weight"], 1e-9) < 2e-4
+    for kk, p in model.named_parameters():
+        assert rel_err(p.grad.cpu(), g_ref[kk], 1e-9) < 2e-4, kk
