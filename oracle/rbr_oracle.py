@@ -371,6 +371,14 @@ def relu_margins(model: str, p: Params, batch: Sequence[Tensor], chunk: int = 51
         x = mask_rows(embedding_gather(table, ids), mask)
         return torch.cat([conv1d_same(x, w, b).max(dim=1).values for w, b in zip(ws, bs)], dim=1)
 
+    bias_all = torch.cat(list(bs))
+
+    def conv_margin(pre: Tensor) -> Tensor:
+        """|pre| per unit, except units that pooled an all-zero window (fully padded document): their value is EXACTLY the
+        bias in every implementation (0 + bias), so their ReLU decision cannot differ however small the bias is."""
+        m = pre.abs()
+        return torch.where(pre == bias_all.view(*([1] * (pre.dim() - 1)), -1), torch.full_like(m, float("inf")), m)
+
     n = batch[0].shape[0]
     out = []
     with torch.no_grad():
@@ -379,14 +387,14 @@ def relu_margins(model: str, p: Params, batch: Sequence[Tensor], chunk: int = 51
             if model == "deepconn":
                 u_revs, i_revs, u_m, i_m, u_ids, i_ids = [t[sl] for t in batch]
                 u_pre, i_pre = pooled_pre(u_revs, u_m), pooled_pre(i_revs, i_m)
-                margin = torch.minimum(u_pre.abs().min(dim=1).values, i_pre.abs().min(dim=1).values)
+                margin = torch.minimum(conv_margin(u_pre).min(dim=1).values, conv_margin(i_pre).min(dim=1).values)
                 u_txt, i_txt = torch.relu(u_pre), torch.relu(i_pre)
             else:
                 u_text, i_text, u_m, i_m, u_ids, i_ids, reuid, reiid = [t[sl] for t in batch]
                 b, r, t = u_text.shape
                 u_pre = pooled_pre(u_text.reshape(b * r, t), u_m.reshape(b * r, t)).view(b, r, -1)
                 i_pre = pooled_pre(i_text.reshape(b * r, t), i_m.reshape(b * r, t)).view(b, r, -1)
-                margin = torch.minimum(u_pre.abs().flatten(1).min(dim=1).values, i_pre.abs().flatten(1).min(dim=1).values)
+                margin = torch.minimum(conv_margin(u_pre).flatten(1).min(dim=1).values, conv_margin(i_pre).flatten(1).min(dim=1).values)
                 feats = []
                 for side, pre, oid in (("user", u_pre, reuid), ("item", i_pre, reiid)):
                     f = torch.relu(pre)

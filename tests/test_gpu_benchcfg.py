@@ -292,16 +292,26 @@ def test_fused_mse_head_matches_unfused_and_oracle(model_name):
                                precision="fp32")
         model.load_state_dict(params)
         batch, ratings, model = _cuda(b), r.cuda(), model.cuda().train()
+    p64 = _f64(params)
+    _clear_relu_margins(model_name, p64, batch)
     p0, l0, g0 = _step(model, batch, ratings, fused_loss=False)
     p1, l1, g1 = _step(model, batch, ratings, fused_loss=True)
     assert torch.equal(p0, p1)
     assert rel_err(l1.cpu(), l0.cpu()) < 1e-6
     for k in g0:
         assert rel_err(g1[k].cpu(), g0[k].cpu(), grad_floor(k)) < 5e-6, k          # two runs: fp32 atomics in a different order
-    rp, rl, rg = orc.loss_and_grads(model_name, {k: v for k, v in params.items()}, [t.cpu() for t in batch], ratings.cpu())
-    assert rel_err(l1.cpu(), orc.mse_loss(rp, ratings.cpu())) < FP32_TOL
+    if model_name == "deepconn":
+        with torch.no_grad():
+            _, _, ua, ia = model.ngram.encode(model.word_embeddings, batch[:2], batch[2:4], return_argmax=True)
+    else:
+        T = batch[0].shape[-1]
+        with torch.no_grad():
+            _, _, ua, ia = model.ngram.encode(model.word_embeddings, [batch[0].view(-1, T), batch[1].view(-1, T)],
+                                              [batch[2].view(-1, T), batch[3].view(-1, T)], return_argmax=True)
+    rp, rl, rg = orc.loss_and_grads(model_name, p64, batch, ratings.double(), argmax_override=(ua, ia))
+    assert rel_err(l1.cpu(), orc.mse_loss(rp, ratings.double()).cpu()) < FP32_TOL
     for k in rg:
-        assert rel_err(g1[k].cpu(), rg[k], grad_floor(k)) < FP32_GRAD_TOL, k
+        assert rel_err(g1[k].cpu(), rg[k].cpu(), grad_floor(k)) < FP32_GRAD_TOL, k
     # the loss scales through: backward of 3*loss gives 3x the gradients (upstream d/d loss is applied on the device)
     model.zero_grad(set_to_none=True)
     loss, _ = model.forward_loss(*batch, ratings)
