@@ -145,7 +145,9 @@ int rbr_conv_act_maxpool_bwd(int precision, int activation, const void* table, c
  * `ws`: rbr_conv_bwd_cmat_workspace_bytes() bytes that the CALLER ZERO-FILLS ONCE; finish() with bit 1 leaves the coefficient
  * matrix zeroed again and bit 4 the weight scratch, so the same workspace serves every following step without a memset.
  * `what`: 1 = close the accumulation (split C; required once after the scatters, before 2 / 4), 2 = table gradient,
- * 4 = weight gradient — data-parallel training runs 1|2, starts the table all-reduce, then 4.
+ * 4 = weight gradient — data-parallel training runs 1|2, starts the table all-reduce, then 4; 8 (with 2) = the table
+ * gradient is OVERWRITTEN (every row and column is written, the padding row with zeros) instead of accumulated into: the
+ * caller then need not zero-fill table_grad, and the epilogue stores without reading (halves its HBM traffic).
  * Shapes: emb % 4 == 0, emb <= 512, vocab * round_up(filters*ksize, 64) * 4 bytes <= 3 GiB, no gate
  * (rbr_conv_bwd_cmat_supported; otherwise use K2b).                                                                     */
 int rbr_conv_bwd_cmat_supported(int64_t vocab, int64_t emb, int64_t filters, int64_t ksize);

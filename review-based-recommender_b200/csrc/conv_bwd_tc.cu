@@ -133,6 +133,7 @@ struct TableGemmArgs {
     int E, NT, nkb;            // nkb = 2 * HJp / 64
     int64_t padding_idx;
     float* table_grad;         // [vocab][E]
+    int overwrite;             // 1: table_grad = tile (every row and column of the gradient is written, padding row = 0); 0: +=
 };
 
 __global__ void __launch_bounds__(CM_THREADS, 2)
@@ -198,7 +199,10 @@ cmat_table_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     } else {
         const int quad = warp & 3;                                   // TMEM lane quadrant this warp may read
         const int64_t row = (int64_t)m0 + quad * 32 + lane;
-        const bool live = row < a.vocab && row != a.padding_idx;
+        const bool in_range = row < a.vocab;
+        const bool pad_row = row == a.padding_idx;
+        const bool live = in_range && (a.overwrite || !pad_row);
+        const float keep = pad_row ? 0.f : 1.f;                      // overwrite mode writes the padding row as zeros
         float* dst_row = a.table_grad + row * a.E;
         mbar_wait(bars + 16 * CM_STAGES_T, 0);
         tc_fence_after();
@@ -213,9 +217,10 @@ cmat_table_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                     const int col = n0 + c0 + q * 4;
                     if (col + 3 < a.E) {
                         float4* p = reinterpret_cast<float4*>(dst_row + col);
-                        float4 o = *p;
-                        o.x += __uint_as_float(v[4 * q]); o.y += __uint_as_float(v[4 * q + 1]);
-                        o.z += __uint_as_float(v[4 * q + 2]); o.w += __uint_as_float(v[4 * q + 3]);
+                        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (!a.overwrite) o = *p;
+                        o.x += keep * __uint_as_float(v[4 * q]); o.y += keep * __uint_as_float(v[4 * q + 1]);
+                        o.z += keep * __uint_as_float(v[4 * q + 2]); o.w += keep * __uint_as_float(v[4 * q + 3]);
                         *p = o;
                     }
                 }
@@ -400,7 +405,8 @@ extern "C" int rbr_conv_bwd_cmat_finish(int what, const void* shadow_bf16, const
                                         int64_t ws_bytes, void* stream) {
     RBR_REQUIRE(ws && packed, RBR_EINVAL, "conv_bwd_cmat_finish: null pointer");
     RBR_REQUIRE(cmat_shape_ok(vocab, emb, filters, ksize), RBR_EUNSUPPORTED, "conv_bwd_cmat: shape outside the dense tensor-core backward");
-    RBR_REQUIRE((what & ~7) == 0 && what != 0, RBR_EINVAL, "conv_bwd_cmat_finish: `what` is a mask of 1 (split), 2 (table), 4 (weight)");
+    RBR_REQUIRE((what & ~15) == 0 && (what & 7) != 0, RBR_EINVAL,
+                "conv_bwd_cmat_finish: `what` is a mask of 1 (split), 2 (table), 4 (weight), 8 (table: overwrite instead of +=)");
     const CmatLayout l = cmat_layout(vocab, emb, filters, ksize);
     RBR_REQUIRE(ws_bytes >= l.total, RBR_EWORKSPACE, "conv_bwd_cmat_finish: workspace too small");
     const PackLayout pl = pack_layout(emb, filters, ksize);
@@ -427,6 +433,7 @@ extern "C" int rbr_conv_bwd_cmat_finish(int what, const void* shadow_bf16, const
         TableGemmArgs a{};
         a.vocab = vocab; a.E = (int)emb; a.NT = (int)pl.NT; a.nkb = (int)(2 * l.HJp / 64); a.padding_idx = padding_idx;
         a.table_grad = table_grad;
+        a.overwrite = (what & 8) ? 1 : 0;
         const int smem = CM_STAGES_T * (16384 + (int)pl.NT * 128) + 8 * (2 * CM_STAGES_T + 1) + 16 + 1024;
         static bool attr = false;
         if (!attr) {

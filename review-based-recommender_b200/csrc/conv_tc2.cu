@@ -32,8 +32,10 @@ constexpr int T2_M = 128;                  // positions per CTA tile (UMMA M = 2
 // per tile relative to the MMA/gather work (many filter chunks, short documents = per-tile finalisation, or a narrow
 // embedding = few K blocks per tile), 8 leave more issue slots to the MMA warp.
 // Warp roles: [0, EW) epilogue, [EW, EW+4) TMA producers (TMA issue is serialised per warp), EW+4 = TMEM owner + MMA issuer.
-constexpr int T2_PROD_WARPS = 4;
-constexpr int t2_threads(int ew) { return (ew + T2_PROD_WARPS + 1) * 32; }
+// Producer warps PW (template parameter): issuing one gather4 costs a warp ~100 cycles (the TMA unit accepts the instruction's
+// uniform-register operands serially per warp), so the 32 + halo gather4s of a K block are spread over PW warps; each
+// stages 128 / PW tile rows.
+constexpr int t2_threads(int ew, int pw) { return (ew + pw + 1) * 32; }
 constexpr int T2_MIN_STAGES = 3;
 
 struct Tc2Plan {
@@ -118,9 +120,10 @@ __device__ __forceinline__ bool t2_row_source(const Tc2Plan& p, int64_t unit, in
     return true;
 }
 
-template <int KT, int EW>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(t2_threads(EW), 1)
+template <int KT, int EW, int PW>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(t2_threads(EW, PW), 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const Tc2Args a) {
+    constexpr int T2_PROD_WARPS = PW, ROWS_PW = T2_M / PW, G4_PW = ROWS_PW / 4;
     constexpr int T2_EPI_WARPS = EW, T2_EPI_SHARES = EW / 4, T2_EPI_THREADS = EW * 32;
     constexpr int MAXC = 1;   // TMEM chunks held in registers at once (2 or 4 with an earlier accumulator release measured slower: 0.34 / 0.38 vs 0.31 ms)
     constexpr int T2_PROD_WARP0 = EW, T2_MMA_WARP = EW + T2_PROD_WARPS;
@@ -243,8 +246,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const Tc2Args a) {
             for (int i = 0; i < 2; ++i) {
                 id_next[i] = -1;
                 ok_next[i] = 0;
-                if (g >= pair_tiles || (i == 1 && !halo_lane)) continue;
-                const int r = (i == 0) ? pw * 32 + lane : T2_M + lane;
+                if (g >= pair_tiles || (i == 1 && !halo_lane) || (i == 0 && lane >= ROWS_PW)) continue;
+                const int r = (i == 0) ? pw * ROWS_PW + lane : T2_M + lane;
                 int64_t doc;
                 int t;
                 if (t2_row_source(p, unit, tt, r, a.n_docs, &doc, &t)) {
@@ -256,7 +259,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const Tc2Args a) {
         int stage = 0;
         uint32_t ph = 0;
         bool w_checked = false;
-        const uint32_t dst0 = ring_s + (uint32_t)(pw * 8) * 512u;
+        const uint32_t dst0 = ring_s + (uint32_t)(pw * G4_PW) * 512u;
         const uint32_t dst_halo = ring_s + 32u * 512u;
         prefetch_ids(0);
         for (int64_t g = 0; g < pair_tiles; ++g) {
@@ -274,9 +277,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const Tc2Args a) {
             // every lane gets all 32 row indices of the warp (and the halo's 8): the issuing lane then has its operands in
             // registers and the gather4s of a stage are straight-line code (a per-lane issue loop serialises on the TMA
             // unit accepting each instruction's uniform registers: ~100 cycles per gather4)
-            int idx[32], hidx[8];
+            int idx[ROWS_PW], hidx[8];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) idx[i] = __shfl_sync(0xffffffffu, mine[0], i);
+            for (int i = 0; i < ROWS_PW; ++i) idx[i] = __shfl_sync(0xffffffffu, mine[0], i);
 #pragma unroll
             for (int i = 0; i < 8; ++i) hidx[i] = __shfl_sync(0xffffffffu, mine[1], i);
             for (int kb = 0; kb < p.nkb; ++kb) {
@@ -293,7 +296,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const Tc2Args a) {
                 const uint32_t so = (uint32_t)(stage * p.stage_bytes);
                 if (elect_one()) {
 #pragma unroll
-                    for (int gi = 0; gi < 8; ++gi)
+                    for (int gi = 0; gi < G4_PW; ++gi)
                         tma_gather4_pair(dst0 + so + (uint32_t)gi * 512u, &tmap, kb * 64, idx[4 * gi], idx[4 * gi + 1], idx[4 * gi + 2],
                                          idx[4 * gi + 3], fb);
                     if (pw == 0) {
@@ -484,11 +487,11 @@ static EncodeTiledFn tc2_encoder() {
     return fn;
 }
 
-template <int KT, int EW>
+template <int KT, int EW, int PW>
 static int tc2_launch(const CUtensorMap& tm, const Tc2Args& a, cudaStream_t s) {
     static int max_clusters = -1;
-    constexpr int T2_THREADS = t2_threads(EW);
-    auto kern = conv_tc2_kernel<KT, EW>;
+    constexpr int T2_THREADS = t2_threads(EW, PW);
+    auto kern = conv_tc2_kernel<KT, EW, PW>;
     if (max_clusters < 0) {
         RBR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM_MAX));
         cudaLaunchConfig_t cfg{};
@@ -547,7 +550,11 @@ int conv_tc2_dispatch(const __nv_bfloat16* shadow, int64_t vocab, int E, IdView 
     a.feat = feat; a.argmax = argmax; a.preact = preact; a.gate = gate; a.gate_mode = gate_mode; a.feat_ld = feat_ld;
     static const char* ew_env = getenv("RBR_TC2_EPI_WARPS");                    // timing experiments: force 8 or 16
     const bool wide = ew_env ? atoi(ew_env) == 16 : (a.p.mode_b || a.p.Nb / 16 >= 9 || a.p.nkb <= 2);
-#define RBR_T2(KT_) return wide ? tc2_launch<KT_, 16>(tm, a, s) : tc2_launch<KT_, 8>(tm, a, s)
+    static const char* pw_env = getenv("RBR_TC2_PROD_WARPS");                   // timing experiments: 4 or 8
+    const bool pw8 = pw_env ? atoi(pw_env) == 8 : false;      // measured: 8 producer warps = 4 (the floor is the TMA unit's row rate, not per-warp issue)
+#define RBR_T2(KT_)                                                                                                   \
+    return wide ? (pw8 ? tc2_launch<KT_, 16, 8>(tm, a, s) : tc2_launch<KT_, 16, 4>(tm, a, s))                          \
+                : (pw8 ? tc2_launch<KT_, 8, 8>(tm, a, s) : tc2_launch<KT_, 8, 4>(tm, a, s))
     switch (K) {
         case 1: RBR_T2(1);
         case 2: RBR_T2(2);

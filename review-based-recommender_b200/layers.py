@@ -176,6 +176,13 @@ class NgramFeat(nn.Module):
             "flags": self.conv_flags,
             "mask_from_ids": True,      # a side passed without a mask: mask = (ids != 0), what collate_fn computes (utils.py:30-42)
         }
+        # one bf16 conv whose dense tensor-core backward (K2c) writes EVERY element of the table gradient: the arena need not
+        # zero-fill that 60 MB slot and the GEMM epilogue stores without reading
+        if (self._arena is not None and len(convs) == 1 and self.precision == "bf16" and table.requires_grad
+                and not (self.conv_flags & ops.CONV_BWD_SPARSE) and torch.is_grad_enabled()
+                and ops.lib.rbr_conv_bwd_cmat_supported(table.shape[0], table.shape[1], convs[0].weight.shape[0], conv.kernel_sizes[0])):
+            cfg["table_overwrite"] = True
+            self._arena.no_zero.add(id(table))
         flat = []
         for ids, m in zip(sides, masks):
             flat += [ids, m]

@@ -107,6 +107,7 @@ class GradArena:
         self.device = None
         self.external: Optional[torch.Tensor] = None
         self.params = named_params
+        self.no_zero: set = set()       # id(param) of slots whose producer OVERWRITES every element (dense table gradient, K2c)
 
     @staticmethod
     def signature_of(named_params) -> tuple:
@@ -145,9 +146,16 @@ class GradArena:
                             "is re-zeroed by every backward: call zero_grad(set_to_none=True) before each step — gradient "
                             "accumulation over micro-batches is not supported with enable_nvls_allreduce")
                 self.flat = ext[:self.total]
-                self.flat.zero_()
             else:
-                self.flat = torch.zeros(self.total, dtype=torch.float32, device=device)
+                self.flat = torch.empty(self.total, dtype=torch.float32, device=device)
+            # zero-fill, except the slots a kernel is going to overwrite completely (the 60 MB word-table gradient)
+            skip = sorted((self.slots[i][0], self.slots[i][0] + (self.slots[i][1].numel() + 63) // 64 * 64)
+                          for i in self.no_zero if i in self.slots)
+            pos = 0
+            for lo, hi in skip + [(self.total, self.total)]:
+                if lo > pos:
+                    self.flat[pos:lo].zero_()
+                pos = max(pos, hi)
 
     def view(self, prm: torch.Tensor) -> Optional[torch.Tensor]:
         slot = self.slots.get(id(prm))
@@ -378,7 +386,15 @@ class EncodeDocsFn(torch.autograd.Function):
                     feats[s].data_ptr() + 4 * cols[i], argmaxes[s].data_ptr() + 4 * cols[i], fgs[s].data_ptr() + 4 * cols[i],
                     h_total, _p(g_b[i]), _p(ws), ws.numel(), ctx.flags_l[s], sh), "rbr_conv_bwd_cmat_scatter")
 
+        # the arena left the table slot un-zeroed because this backward writes every element of it (NgramFeat.encode decided)
+        overwrite = bool(cfg.get("table_overwrite")) and need_table and arena is not None and id(cfg["table_param"]) in arena.no_zero
+        if overwrite and not (all(dense) and n_conv == 1 and live):
+            g_table.zero_()                 # nothing will overwrite it after all
+            overwrite = False
+
         def dense_finish(what):
+            if overwrite and (what & 2):
+                what |= 8
             for i, ws in cm_ws.items():
                 h, _, k = shapes[i]
                 lib.check(lib.rbr_conv_bwd_cmat_finish(what, _p(ctx.shadow), _p(ctx.packed[i]), vocab, emb, h, k, cfg["padding_idx"],
