@@ -216,18 +216,19 @@ int rbr_head_bwd(const float* u_text, const float* i_text, const int64_t* u_id, 
  * convolutions themselves are rbr_conv_act_maxpool_fwd with RBR_ACT_TANH and gate_mode 1 (local, k=1) / 2 (global).
  *   w_local [1,E,window], b_local [1], w_global [1,E,doc_len], b_global [1]  (nn.Conv1d layouts).
  * Backward: gate_*_grad are d loss / d gate (filled by rbr_conv_act_maxpool_bwd's gate_grad); produces the four
- * parameter gradients (+=) and the gates' contribution to the table gradient (+=, padding row skipped).          */
+ * parameter gradients (+=) and the gates' contribution to the table gradient (+=, padding row skipped).
+ * `flags`: RBR_IDS_I32 when `ids` are int32 (D-ATT has no masks).                                                   */
 int64_t rbr_datt_gate_workspace_bytes(int64_t n_docs, int64_t doc_len, int64_t emb, int64_t window, int64_t vocab);
-int rbr_datt_gate_fwd(const float* table, int64_t vocab, int64_t emb, const int64_t* ids, int64_t n_docs,
+int rbr_datt_gate_fwd(const float* table, int64_t vocab, int64_t emb, const void* ids, int64_t n_docs,
                       int64_t doc_len, const float* w_local, const float* b_local, int64_t window,
                       const float* w_global, const float* b_global, float* gate_local, float* gate_global,
-                      void* ws, int64_t ws_bytes, void* stream);
-int rbr_datt_gate_bwd(const float* table, int64_t vocab, int64_t emb, const int64_t* ids, int64_t n_docs,
+                      void* ws, int64_t ws_bytes, int flags, void* stream);
+int rbr_datt_gate_bwd(const float* table, int64_t vocab, int64_t emb, const void* ids, int64_t n_docs,
                       int64_t doc_len, const float* w_local, int64_t window, const float* w_global,
                       const float* gate_local, const float* gate_global, const float* gate_local_grad,
                       const float* gate_global_grad, int64_t padding_idx, float* w_local_grad, float* b_local_grad,
                       float* w_global_grad, float* b_global_grad, float* table_grad, void* ws, int64_t ws_bytes,
-                      void* stream);
+                      int flags, void* stream);
 
 /* ---- K6: data-parallel gradient all-reduce through the NVSwitch (NVLS multimem) ------------------------------
  * Replaces nn.DataParallel's gradient reduce_add (trainer/train_deepconn_pp.py:129-131) for one-process-per-GPU training:

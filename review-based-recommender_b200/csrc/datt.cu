@@ -62,7 +62,7 @@ __global__ void datt_transpose_kernel(const float* __restrict__ w, int E, int Ep
 // one CTA per document: warp w takes tokens w, w+8, ...; lane c owns elements 4c..4c+3 of the row
 template <bool V4, int WIN>
 __global__ void __launch_bounds__(DA_WARPS * 32) datt_gate_fwd_kernel(
-    const float* __restrict__ table, int64_t vocab, int E, const int64_t* __restrict__ ids, int L, const float* __restrict__ waT,
+    const float* __restrict__ table, int64_t vocab, int E, const IdView ids, int L, const float* __restrict__ waT,
     const float* __restrict__ b_local, int win, const float* __restrict__ wgT, const float* __restrict__ b_global,
     float* __restrict__ gate_local, float* __restrict__ gate_global) {
     extern __shared__ __align__(16) float smem[];
@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(DA_WARPS * 32) datt_gate_fwd_kernel(
     // bits (4,3,2) spell j holds d_j.  (The kernel was issue-bound: 242 warp instructions per token, mostly reductions.)
     const int my_j = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
     for (int t = wib; t < L; t += DA_WARPS) {
-        const int64_t id = ids[n * L + t];
+        const int64_t id = ld_id(ids, n * L + t);
         float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
         const bool ok = id >= 0 && id < vocab;
         if (!ok && lane == 0) note_oob();
@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(DA_WARPS * 32) datt_gate_fwd_kernel(
 }
 
 // dz = d gate * gate * (1 - gate); bias grads; sort keys (token id, or -1 for the padding row / bad ids)
-__global__ void __launch_bounds__(256) datt_gate_dz_kernel(const int64_t* __restrict__ ids, int64_t n_docs, int L, int64_t vocab,
+__global__ void __launch_bounds__(256) datt_gate_dz_kernel(const IdView ids, int64_t n_docs, int L, int64_t vocab,
                                                            int64_t padding_idx, const float* __restrict__ gl,
                                                            const float* __restrict__ gg, const float* __restrict__ gl_grad,
                                                            const float* __restrict__ gg_grad, float* __restrict__ dz_l,
@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(256) datt_gate_dz_kernel(const int64_t* __rest
         const float d = gl_grad[q] * g * (1.f - g);
         dz_l[q] = d;
         sl += d;
-        const int64_t id = ids[q];
+        const int64_t id = ld_id(ids, q);
         keys[q] = (id >= 0 && id < vocab && id != padding_idx) ? (int32_t)id : -1;
         if (q < n_docs) {
             const float g2 = gg[q];
@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(256) datt_gate_dz_kernel(const int64_t* __rest
 //   w_local_grad[e, j]  += sum_n dz_l[n, t - j + pad] * x[n, t, e]
 template <int WIN, bool V4>
 __global__ void __launch_bounds__(DA_WARPS * 32) datt_gate_wgrad_kernel(const float* __restrict__ table, int64_t vocab, int E,
-                                                                        const int64_t* __restrict__ ids, int64_t n_docs, int L,
+                                                                        const IdView ids, int64_t n_docs, int L,
                                                                         const float* __restrict__ dz_l, const float* __restrict__ dz_g,
                                                                         float* __restrict__ w_local_grad /*[E][WIN]*/,
                                                                         float* __restrict__ w_global_grad /*[E][L]*/) {
@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(DA_WARPS * 32) datt_gate_wgrad_kernel(const fl
 #pragma unroll
         for (int j = 0; j < WIN; ++j) zl_l[j] = 0.f;
         if (n < n_docs) {
-            const int64_t id = ids[n * L + t];
+            const int64_t id = ld_id(ids, n * L + t);
             if (id >= 0 && id < vocab) id_l = id;
             zg_l = dz_g[n];
 #pragma unroll
@@ -323,14 +323,15 @@ extern "C" int64_t rbr_datt_gate_workspace_bytes(int64_t n_docs, int64_t doc_len
     return datt_ws(nullptr, n_docs, doc_len, emb, window, vocab).total;
 }
 
-extern "C" int rbr_datt_gate_fwd(const float* table, int64_t vocab, int64_t emb, const int64_t* ids, int64_t n_docs,
+extern "C" int rbr_datt_gate_fwd(const float* table, int64_t vocab, int64_t emb, const void* ids_raw, int64_t n_docs,
                                  int64_t doc_len, const float* w_local, const float* b_local, int64_t window,
                                  const float* w_global, const float* b_global, float* gate_local, float* gate_global, void* ws,
-                                 int64_t ws_bytes, void* stream) {
+                                 int64_t ws_bytes, int flags, void* stream) {
     int rc = datt_check(emb, doc_len, window, "rbr_datt_gate_fwd");
     if (rc != RBR_OK) return rc;
     if (n_docs == 0) return RBR_OK;
-    RBR_REQUIRE(table && ids && w_local && b_local && w_global && b_global && gate_local && gate_global && ws, RBR_EINVAL,
+    const IdView ids = id_view(ids_raw, flags);
+    RBR_REQUIRE(table && ids_raw && w_local && b_local && w_global && b_global && gate_local && gate_global && ws, RBR_EINVAL,
                 "rbr_datt_gate_fwd: null pointer");
     RBR_REQUIRE(ws_bytes >= rbr_datt_gate_workspace_bytes(n_docs, doc_len, emb, window, vocab), RBR_EWORKSPACE,
                 "rbr_datt_gate_fwd: workspace too small");
@@ -343,7 +344,7 @@ extern "C" int rbr_datt_gate_fwd(const float* table, int64_t vocab, int64_t emb,
     RBR_LAUNCH_CHECK("datt_transpose(global)");
     const size_t smem = ((size_t)((win * L + 3) & ~3) + (size_t)win * Ep + DA_WARPS) * 4;
     RBR_REQUIRE(smem <= 200 * 1024, RBR_EUNSUPPORTED, "rbr_datt_gate_fwd: doc_len too large for shared memory");
-    void (*kern)(const float*, int64_t, int, const int64_t*, int, const float*, const float*, int, const float*, const float*, float*,
+    void (*kern)(const float*, int64_t, int, IdView, int, const float*, const float*, int, const float*, const float*, float*,
                  float*) = nullptr;
 #define RBR_GF(W_) case W_: kern = (E % 4 == 0) ? datt_gate_fwd_kernel<true, W_> : datt_gate_fwd_kernel<false, W_>; break;
     switch (win) { RBR_GF(1) RBR_GF(3) RBR_GF(5) RBR_GF(7) }
@@ -356,16 +357,17 @@ extern "C" int rbr_datt_gate_fwd(const float* table, int64_t vocab, int64_t emb,
     return RBR_OK;
 }
 
-extern "C" int rbr_datt_gate_bwd(const float* table, int64_t vocab, int64_t emb, const int64_t* ids, int64_t n_docs,
+extern "C" int rbr_datt_gate_bwd(const float* table, int64_t vocab, int64_t emb, const void* ids_raw, int64_t n_docs,
                                  int64_t doc_len, const float* w_local, int64_t window, const float* w_global,
                                  const float* gate_local, const float* gate_global, const float* gate_local_grad,
                                  const float* gate_global_grad, int64_t padding_idx, float* w_local_grad, float* b_local_grad,
                                  float* w_global_grad, float* b_global_grad, float* table_grad, void* ws, int64_t ws_bytes,
-                                 void* stream) {
+                                 int flags, void* stream) {
     int rc = datt_check(emb, doc_len, window, "rbr_datt_gate_bwd");
     if (rc != RBR_OK) return rc;
     if (n_docs == 0) return RBR_OK;
-    RBR_REQUIRE(table && ids && w_local && w_global && gate_local && gate_global && gate_local_grad && gate_global_grad &&
+    const IdView ids = id_view(ids_raw, flags);
+    RBR_REQUIRE(table && ids_raw && w_local && w_global && gate_local && gate_global && gate_local_grad && gate_global_grad &&
                     w_local_grad && b_local_grad && w_global_grad && b_global_grad && ws,
                 RBR_EINVAL, "rbr_datt_gate_bwd: null pointer");
     RBR_REQUIRE(ws_bytes >= rbr_datt_gate_workspace_bytes(n_docs, doc_len, emb, window, vocab), RBR_EWORKSPACE,

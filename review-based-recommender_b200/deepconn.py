@@ -10,6 +10,8 @@ from .layers import FM, HotPathModule, LastFeat, NgramFeat, WordEmbedding, fused
 
 
 class DeepCoNNpp(HotPathModule):
+    staging_spec = dict(tokens=(0, 1), masks=(2, 3))      # which forward() inputs are token-id tensors / their masks (staging.StagedInputs)
+
     def __init__(self, user_size, item_size, vocab_size, kernel_sizes, embedding_dim, hidden_dim, latent_dim, doc_len,
                  pretrained_embeddings, dropout, arch="CNN", precision=None):
         super().__init__()

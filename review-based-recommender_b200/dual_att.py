@@ -43,6 +43,8 @@ class GlobalAttention(nn.Module):
 
 
 class DualAtt(HotPathModule):
+    staging_spec = dict(tokens=(0, 1), masks=())      # which forward() inputs are token-id tensors / their masks (staging.StagedInputs)
+
     def __init__(self, vocab_size, doc_len, l_window_size=5, l_out_size=200, g_out_size=100, emb_size=100,
                  hidden_size_1=500, hidden_size_2=50, dropout=0.5, pretrained_embeddings=None, precision=None):
         super().__init__()

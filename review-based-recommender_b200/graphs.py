@@ -29,14 +29,22 @@ class GraphedTrainStep:
     def __init__(self, model: torch.nn.Module, loss_fn: Callable, example_batch: Sequence[torch.Tensor],
                  example_ratings: torch.Tensor, restage_operands: bool = True, warmup: int = 3,
                  pool=None, device: Optional[torch.device] = None, post_backward: Optional[Callable[[], None]] = None,
-                 fuse_mse: bool = True):
+                 fuse_mse: bool = True, staged: bool = False):
         dev = device or next(model.parameters()).device
         if dev.type != "cuda":
             raise RuntimeError("GraphedTrainStep needs the model on a CUDA device")
         self.model, self.loss_fn, self.restage = model, loss_fn, restage_operands
         self.post_backward = post_backward      # e.g. lambda: parallel.allreduce_gradients(model) — captured with the step
-        self.static_batch = [torch.empty(t.shape, dtype=t.dtype, device=dev) for t in example_batch]
-        self.static_ratings = torch.empty(example_ratings.shape, dtype=example_ratings.dtype, device=dev)
+        # staged=True: the static inputs are typed views of ONE device arena — token ids as int32, masks derived
+        # on the device — filled by a single H2D copy per step (staging.StagedInputs; `load_packed`)
+        self.staged = None
+        if staged:
+            from .staging import StagedInputs
+            self.staged = StagedInputs.for_model(model, example_batch, example_ratings, dev)
+            self.static_batch, self.static_ratings = self.staged.batch, self.staged.ratings
+        else:
+            self.static_batch = [None if t is None else torch.empty(t.shape, dtype=t.dtype, device=dev) for t in example_batch]
+            self.static_ratings = torch.empty(example_ratings.shape, dtype=example_ratings.dtype, device=dev)
         self._fm = getattr(model, "fm", None)
         # FM dropout seed counter: attached to the model only while this object's body runs (warm-up and capture), so eager
         # calls made between replays keep drawing fresh host seeds
@@ -84,9 +92,17 @@ class GraphedTrainStep:
         """Copy a batch into the static input buffers (H2D straight from pinned memory, or D2D), optionally on `stream`."""
         ctx = torch.cuda.stream(stream) if stream is not None else _null()
         with ctx:
+            if self.staged is not None:
+                self.staged.load_device(batch, ratings)
+                return
             for dst, src in zip(self.static_batch, batch):
-                dst.copy_(src, non_blocking=True)
+                if dst is not None:
+                    dst.copy_(src, non_blocking=True)
             self.static_ratings.copy_(ratings, non_blocking=True)
+
+    def load_packed(self, host: torch.Tensor, stream: Optional[torch.cuda.Stream] = None) -> None:
+        """staged=True: ONE cudaMemcpyAsync of a step packed by `self.staged.pack(batch, ratings)` into pinned memory."""
+        self.staged.upload(host, stream)
 
     def replay(self) -> torch.Tensor:
         self.graph.replay()

@@ -10,6 +10,8 @@ from .layers import FM, HotPathModule, LastFeat, LinearAttention, NgramFeat, Wor
 
 
 class NARRE(HotPathModule):
+    staging_spec = dict(tokens=(0, 1), masks=(2, 3))      # which forward() inputs are token-id tensors / their masks (staging.StagedInputs)
+
     def __init__(self, user_size, item_size, vocab_size, kernel_sizes, hidden_dim, embedding_dim, att_dim, latent_dim,
                  max_doc_num, max_doc_len, dropout, word_padding_idx, user_padding_idx, item_padding_idx,
                  pretrained_embeddings, arch, precision=None):

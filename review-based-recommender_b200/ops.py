@@ -648,7 +648,8 @@ class DattEncodeFn(torch.autograd.Function):
         shadow = cfg["shadow_fn"]() if prec == PREC_BF16 else None
         saved, feats, side_ctx = [], [], []
         for s in range(n_sides):
-            ids = _req(rest[s * stride], torch.int64, "token ids")
+            ids = _ids(rest[s * stride], "token ids")
+            idf = IDS_I32 if ids.dtype == torch.int32 else 0
             prm = [_req(t, torch.float32, "D-ATT parameter") for t in rest[s * stride + 1:(s + 1) * stride]]
             la_w, la_b, lc_w, lc_b, ga_w, ga_b = prm[:6]
             g_convs = [(prm[6 + 2 * i], prm[7 + 2 * i]) for i in range(3)]
@@ -659,7 +660,7 @@ class DattEncodeFn(torch.autograd.Function):
             gate_l = torch.empty(n_docs, doc_len, dtype=torch.float32, device=dev)
             gate_g = torch.empty(n_docs, dtype=torch.float32, device=dev)
             lib.check(lib.rbr_datt_gate_fwd(_p(table), vocab, emb, _p(ids), n_docs, doc_len, _p(la_w), _p(la_b), win, _p(ga_w),
-                                            _p(ga_b), _p(gate_l), _p(gate_g), _p(ws), ws_bytes, _stream()), "rbr_datt_gate_fwd")
+                                            _p(ga_b), _p(gate_l), _p(gate_g), _p(ws), ws_bytes, idf, _stream()), "rbr_datt_gate_fwd")
             convs = [(lc_w, lc_b, gate_l, 1)] + [(w, b, gate_g, 2) for w, b in g_convs]
             packed = [conv_pack(w) for w, _, _, _ in convs]
             h_total = sum(w.shape[0] for w, _, _, _ in convs)
@@ -671,7 +672,7 @@ class DattEncodeFn(torch.autograd.Function):
                 h, _, k = w.shape
                 lib.check(lib.rbr_conv_act_maxpool_fwd(prec, ACT_TANH, _p(table), _p(shadow), vocab, emb, _p(ids), None, _p(gate),
                                                        mode, n_docs, doc_len, _p(pk), _p(b), h, k, 0, feat.data_ptr() + 4 * col,
-                                                       amax.data_ptr() + 4 * col, pre.data_ptr() + 4 * col, h_total, 0, _stream()),
+                                                       amax.data_ptr() + 4 * col, pre.data_ptr() + 4 * col, h_total, idf, _stream()),
                           "rbr_conv_act_maxpool_fwd")
                 col += h
             saved += [ids, gate_l, gate_g, feat, amax, pre]
@@ -727,6 +728,7 @@ class DattEncodeFn(torch.autograd.Function):
                        emb, dev):
         if True:
             n_docs, doc_len = ids.shape
+            idf = IDS_I32 if ids.dtype == torch.int32 else 0
             la_w, la_b, lc_w, lc_b, ga_w, ga_b = prm[:6]
             convs = [(lc_w, lc_b, gate_l, 1, 2, 3)] + [(prm[6 + 2 * i], prm[7 + 2 * i], gate_g, 2, 6 + 2 * i, 7 + 2 * i)
                                                        for i in range(3)]
@@ -742,12 +744,12 @@ class DattEncodeFn(torch.autograd.Function):
                     prec, ACT_TANH, _p(table), _p(shadow), vocab, emb, _p(ids), None, _p(gate), mode, n_docs, doc_len, _p(pk),
                     h, k, 0, feat.data_ptr() + 4 * col, amax.data_ptr() + 4 * col, fg.data_ptr() + 4 * col,
                     pre.data_ptr() + 4 * col, h_total, cfg["padding_idx"], _p(grads[wi]), _p(grads[bi]), _p(g_table),
-                    _p(d_gate_l if mode == 1 else d_gate_g), _p(ws), ws_bytes, 0, _stream()), "rbr_conv_act_maxpool_bwd")
+                    _p(d_gate_l if mode == 1 else d_gate_g), _p(ws), ws_bytes, idf, _stream()), "rbr_conv_act_maxpool_bwd")
                 col += h
             win = la_w.shape[2]
             ws_bytes = lib.rbr_datt_gate_workspace_bytes(n_docs, doc_len, emb, win, vocab)
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
             lib.check(lib.rbr_datt_gate_bwd(_p(table), vocab, emb, _p(ids), n_docs, doc_len, _p(la_w), win, _p(ga_w), _p(gate_l),
                                             _p(gate_g), _p(d_gate_l), _p(d_gate_g), cfg["padding_idx"], _p(grads[0]), _p(grads[1]),
-                                            _p(grads[4]), _p(grads[5]), _p(g_table), _p(ws), ws_bytes, _stream()),
+                                            _p(grads[4]), _p(grads[5]), _p(g_table), _p(ws), ws_bytes, idf, _stream()),
                       "rbr_datt_gate_bwd")

@@ -116,3 +116,47 @@ def test_graphed_step_dual_att_matches_eager(precision):
             assert abs(float(loss) - ref_loss) <= 2e-6 * max(1.0, abs(ref_loss))
             for k, p in model.named_parameters():
                 assert rel_err(p.grad.cpu(), ref_grads[k].cpu(), 1e-9) < 2e-6, k
+
+
+@pytest.mark.parametrize("model_name", ["deepconn", "narre", "dual_att"])
+def test_staged_inputs_int32_ids_and_derived_masks_match_the_reference_wire_format(model_name):
+    """one pinned arena per step (token ids int32, masks derived on the device as ids != 0) uploaded with one
+    copy into the graph's static inputs gives the same loss and gradients as int64 ids + bool masks, eager and graphed."""
+    if model_name == "deepconn":
+        model, (U, I, V, L) = _model(0.0, "bf16")
+        mk = lambda seed: synth.deepconn_batch(32, L, V, U, I, seed=seed)
+    elif model_name == "narre":
+        U, I, V, E, H, A, K, R, T = 40, 30, 600, 64, 48, 16, 16, 6, 20
+        model = rbr_b200.NARRE(U, I, V, [3], H, E, A, K, R, T, 0.0, 0, 0, 0, None, "CNN", precision="bf16")
+        model.load_state_dict(synth.narre_params(U, I, V, E, H, A, K, (3,), seed=4))
+        model.cuda().train()
+        mk = lambda seed: synth.narre_batch(24, R, T, V, U, I, seed=seed)
+    else:
+        V, L, E = 500, 64, 32
+        model = rbr_b200.DualAtt(V, L, 5, 24, 16, E, 40, 10, 0.0, None, precision="bf16")
+        model.load_state_dict(synth.dual_att_params(V, L, 5, 24, 16, E, 40, 10, seed=5))
+        model.cuda().train()
+        mk = lambda seed: synth.dual_att_batch(16, L, V, seed=seed)
+    host = [mk(s) for s in (5, 6, 7)]
+    ref = [_eager_step(model, [t.cuda() for t in b], r.cuda()) for b, r in host]
+    step = GraphedTrainStep(model, torch.nn.MSELoss(), [t.cuda() for t in host[0][0]], host[0][1].cuda(), staged=True)
+    st = step.staged
+    ref_bytes = sum(t.numel() * t.element_size() for t in host[0][0]) + host[0][1].numel() * 4
+    assert st.h2d_bytes < 0.52 * ref_bytes + 4096                          # int32 ids, no masks
+    assert all(v is None or v.dtype != torch.bool for v in st.batch)
+    for (b, r), (ref_loss, ref_grads) in zip(host, ref):
+        arena = st.pack(b, r)                                              # pinned host arena in wire format
+        assert arena.is_pinned() and arena.numel() == st.h2d_bytes
+        step.load_packed(arena)
+        loss = step.replay()
+        torch.cuda.synchronize()
+        assert abs(float(loss) - ref_loss) <= 2e-6 * max(1.0, abs(ref_loss))
+        for k, p in model.named_parameters():
+            assert rel_err(p.grad.cpu(), ref_grads[k].cpu(), 1e-9) < 1e-5, k
+    # eager call on the staged views (the public nn.Module API with int32 ids and masks=None)
+    st.upload(st.pack(*host[1]))
+    out = model(*st.batch)
+    pred = out[0] if isinstance(out, tuple) else out
+    ref_out = model(*[t.cuda() for t in host[1][0]])
+    ref_pred = ref_out[0] if isinstance(ref_out, tuple) else ref_out
+    assert torch.equal(pred, ref_pred)
