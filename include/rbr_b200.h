@@ -230,6 +230,21 @@ int rbr_datt_gate_bwd(const float* table, int64_t vocab, int64_t emb, const void
                       float* w_global_grad, float* b_global_grad, float* table_grad, void* ws, int64_t ws_bytes,
                       int flags, void* stream);
 
+/* ---- K7: fused global-norm clip + Adam over flat parameter / gradient buffers -----------------------------
+ * Replaces nn.utils.clip_grad_norm_(model.parameters(), max_norm) + torch.optim.Adam.step()
+ * (trainer/train_deepconn_pp.py:135,167-168).  params / grads / exp_avg / exp_avg_sq: flat fp32 buffers of n_floats elements
+ * with the same layout (every parameter a 256-byte aligned slot; gaps hold zeros and stay zero).
+ *   clip = min(1, max_norm / (||grads||_2 + 1e-6))  (max_norm <= 0: no clipping);  sumsq_dev: 1 double of device scratch
+ *   Adam (no amsgrad, no weight decay) with bias corrections from the DEVICE step counter step_dev[0], which the call
+ *   increments first — a CUDA-graph replay of the trainer step therefore advances the optimizer correctly.
+ *   grad_norm_out (optional, device): the unclipped gradient norm clip_grad_norm_ returns.
+ *   shadow_bf16 (optional): the bf16 shadow of the word table (rows of rbr_emb_pad(emb) elements), rewritten from the updated
+ *   parameters of the slice [table_off, table_off + table_rows*emb) — the next forward needs no rbr_table_to_bf16.        */
+int rbr_clip_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n_floats, float lr,
+                       float beta1, float beta2, float eps, float max_norm, double* sumsq_dev, int64_t* step_dev,
+                       float* grad_norm_out, int64_t table_off, int64_t table_rows, int64_t emb, void* shadow_bf16,
+                       void* stream);
+
 /* ---- K6: data-parallel gradient all-reduce through the NVSwitch (NVLS multimem) ------------------------------
  * Replaces nn.DataParallel's gradient reduce_add (trainer/train_deepconn_pp.py:129-131) for one-process-per-GPU training:
  * `multicast_ptr` is the NVLS multicast address of the flat gradient arena (symmetric memory, same offset on every GPU).

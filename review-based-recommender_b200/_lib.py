@@ -20,6 +20,7 @@ _SCALARS = {
     "int64_t": ctypes.c_int64,
     "uint64_t": ctypes.c_uint64,
     "float": ctypes.c_float,
+    "double": ctypes.c_double,
 }
 
 

@@ -29,12 +29,15 @@ class GraphedTrainStep:
     def __init__(self, model: torch.nn.Module, loss_fn: Callable, example_batch: Sequence[torch.Tensor],
                  example_ratings: torch.Tensor, restage_operands: bool = True, warmup: int = 3,
                  pool=None, device: Optional[torch.device] = None, post_backward: Optional[Callable[[], None]] = None,
-                 fuse_mse: bool = True, staged: bool = False):
+                 fuse_mse: bool = True, staged: bool = False, optimizer=None, max_grad_norm: Optional[float] = None):
         dev = device or next(model.parameters()).device
         if dev.type != "cuda":
             raise RuntimeError("GraphedTrainStep needs the model on a CUDA device")
         self.model, self.loss_fn, self.restage = model, loss_fn, restage_operands
         self.post_backward = post_backward      # e.g. lambda: parallel.allreduce_gradients(model) — captured with the step
+        # optimizer (optim.FusedClipAdam): the update — global-norm clip + Adam, step counter on the device — is captured too:
+        # one replay = the reference's whole loop body, trainer/train_deepconn_pp.py:161-168
+        self.optimizer, self.max_grad_norm = optimizer, max_grad_norm
         # staged=True: the static inputs are typed views of ONE device arena — token ids as int32, masks derived
         # on the device — filled by a single H2D copy per step (staging.StagedInputs; `load_packed`)
         self.staged = None
@@ -72,8 +75,9 @@ class GraphedTrainStep:
             self._fm.__dict__["_rbr_seed_dev"] = self._seed_dev
         try:
             self.model.zero_grad(set_to_none=True)
-            if self.restage and hasattr(self.model, "invalidate_operand_cache"):
+            if self.restage and self.optimizer is None and hasattr(self.model, "invalidate_operand_cache"):
                 self.model.invalidate_operand_cache()    # the parameters change between replays: re-stage bf16 shadow / packed weights
+                # (with a captured optimizer the update itself keeps the shadow current and drops the packed conv weights)
             if self.fused_loss:
                 loss, _ = self.model.forward_loss(*self.static_batch, self.static_ratings)
             else:
@@ -83,6 +87,8 @@ class GraphedTrainStep:
             loss.backward()
             if self.post_backward is not None:
                 self.post_backward()
+            if self.optimizer is not None:
+                self.grad_norm = self.optimizer.clip_and_step(self.max_grad_norm)
         finally:
             if self._fm is not None:
                 self._fm.__dict__.pop("_rbr_seed_dev", None)

@@ -149,8 +149,9 @@ class GradArena:
             else:
                 self.flat = torch.empty(self.total, dtype=torch.float32, device=device)
             # zero-fill, except the slots a kernel is going to overwrite completely (the 60 MB word-table gradient)
-            skip = sorted((self.slots[i][0], self.slots[i][0] + (self.slots[i][1].numel() + 63) // 64 * 64)
-                          for i in self.no_zero if i in self.slots)
+            # (only the slot's own elements are skipped: the alignment gap behind it is zeroed like everything else, so the flat
+            # buffer can be summed / all-reduced / fed to the fused optimizer as it is)
+            skip = sorted((self.slots[i][0], self.slots[i][0] + self.slots[i][1].numel()) for i in self.no_zero if i in self.slots)
             pos = 0
             for lo, hi in skip + [(self.total, self.total)]:
                 if lo > pos:
