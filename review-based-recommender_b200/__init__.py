@@ -21,7 +21,7 @@ def __getattr__(name):          # lazy: model classes import torch.nn and the na
     if name == "DualAtt":
         from .dual_att import DualAtt
         return DualAtt
-    if name in ("layers", "ops", "parallel", "graphs", "deepconn", "narre", "dual_att", "_lib"):
+    if name in ("layers", "ops", "parallel", "graphs", "deepconn", "narre", "dual_att", "_lib", "staging", "optim", "inference"):
         import importlib
         return importlib.import_module(f"{__name__}.{name}")
     raise AttributeError(name)

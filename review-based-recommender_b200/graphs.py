@@ -110,6 +110,13 @@ class GraphedTrainStep:
         """staged=True: ONE cudaMemcpyAsync of a step packed by `self.staged.pack(batch, ratings)` into pinned memory."""
         self.staged.upload(host, stream)
 
+    def refresh_operands(self) -> None:
+        """With a captured optimizer the graph never re-casts the bf16 shadow of the word table (the update keeps it current).
+        Call this after changing parameters OUTSIDE the graph (load_state_dict, manual edits) so the next replay sees them."""
+        we = getattr(self.model, "word_embeddings", None)
+        if we is not None and hasattr(we, "refresh_operand_cache"):
+            we.refresh_operand_cache()
+
     def replay(self) -> torch.Tensor:
         self.graph.replay()
         return self.loss

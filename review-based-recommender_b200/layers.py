@@ -96,6 +96,15 @@ class WordEmbedding(nn.Module):
         """Drop the bf16 shadow (as an optimizer step would, by bumping the table's version)."""
         self._shadow = None
 
+    def refresh_operand_cache(self):
+        """Re-cast the table into the EXISTING shadow buffer (same address: a captured CUDA graph keeps reading it) and mark
+        it current — after parameters were changed outside a graph whose optimizer keeps the shadow up to date itself."""
+        if self._shadow is None:
+            return
+        w = self.embedding.weight
+        self._shadow[1].copy_(ops.table_to_bf16(w.detach()))
+        self._shadow = ((w._version, w.data_ptr()), self._shadow[1])
+
 
 class MyConv1d(nn.Module):
     """Holder of one nn.Conv1d per kernel size; the arithmetic runs inside NgramFeat's fused kernel."""

@@ -47,6 +47,16 @@ def doc_batch(batch: int, doc_len: int, vocab: int, seed: int = SEED_BASE, unifo
     return ids, ids != 0
 
 
+def doc_batch_device(batch: int, doc_len: int, vocab: int, gen: torch.Generator, device, dtype=torch.int64) -> torch.Tensor:
+    """doc_batch's distribution generated ON THE DEVICE (config 5 scores 10 M pairs = 80 GB of int64 ids: produced chunk by
+    chunk, never materialised).  Returns ids only (mask = ids != 0)."""
+    u = torch.rand(batch, doc_len, device=device, generator=gen, dtype=torch.float32)
+    ids = (3 + ((vocab - 3) * u * u * u).floor()).to(torch.int64).clamp_(max=vocab - 1)
+    lens = torch.randint(max(1, doc_len // 2), doc_len + 1, (batch, 1), device=device, generator=gen)
+    pos = torch.arange(doc_len, device=device).unsqueeze(0)
+    return torch.where(pos < lens, ids, torch.zeros((), dtype=torch.int64, device=device)).to(dtype)
+
+
 def deepconn_batch(batch: int, doc_len: int, vocab: int, users: int, items: int, seed: int = SEED_BASE,
                    uniform: bool = False):
     """(u_revs, i_revs, u_masks, i_masks, u_ids, i_ids), ratings — the 7 tensors collate_fn yields

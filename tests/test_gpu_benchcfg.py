@@ -366,3 +366,29 @@ def test_saturated_gate_gives_finite_gate_gradient():
     assert rel_err(pred.cpu(), rp) < FP32_TOL
     for k in rg:
         assert rel_err(grads[k].cpu(), rg[k], 1e-9) < FP32_GRAD_TOL, k
+
+
+def test_feature_cache_scores_are_bit_identical_to_per_pair_scoring():
+    """encode each entity's document once, score pairs with K1 gather + K4 head: same bits as the reference's
+    per-pair data flow (both documents encoded for every pair)."""
+    from rbr_b200.inference import PairScorer
+    U, I, V, E, H, K, L = 300, 200, 5000, 300, 100, 32, 500
+    params = synth.deepconn_params(U, I, V, E, H, K, (3,), seed=4)
+    model = rbr_b200.DeepCoNNpp(U, I, V, [3], E, H, K, L, None, 0.5, precision="bf16")
+    model.load_state_dict(params)
+    scorer = PairScorer(model.cuda())
+    user_docs, _ = synth.doc_batch(U, L, V, seed=1)
+    item_docs, _ = synth.doc_batch(I, L, V, seed=2)
+    user_docs[0] = 0
+    item_docs[0] = 0                                                   # the padding entities
+    user_docs, item_docs = user_docs.cuda(), item_docs.cuda()
+    scorer.build_cache(user_docs, item_docs, chunk=128)
+    gen = torch.Generator().manual_seed(3)
+    u_ids = torch.randint(0, U, (4096,), generator=gen).cuda()
+    i_ids = torch.randint(0, I, (4096,), generator=gen).cuda()
+    cached = scorer.score_cached(u_ids, i_ids)
+    ud, idd = user_docs[u_ids], item_docs[i_ids]
+    direct = scorer.score_pairs(ud, idd, ud != 0, idd != 0, u_ids, i_ids)
+    assert torch.equal(cached, direct)
+    rp = orc.deepconn_forward(_f64(params, round_bf16=True), ud, idd, ud != 0, idd != 0, u_ids, i_ids)
+    assert rel_err(cached.cpu(), rp.cpu()) < 2e-3

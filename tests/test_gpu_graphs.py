@@ -42,7 +42,7 @@ def test_graphed_step_matches_eager_on_every_batch(precision):
         torch.cuda.synchronize()
         assert abs(float(loss) - ref_loss) <= 1e-6 * max(1.0, abs(ref_loss))
         for k, p in model.named_parameters():
-            assert rel_err(p.grad.cpu(), ref_grads[k].cpu()) < 1e-6, k
+            assert rel_err(p.grad.cpu(), ref_grads[k].cpu()) < 1e-5, k        # fp32 atomics land in a different order
 
 
 def test_graphed_step_dropout_mask_changes_between_replays():

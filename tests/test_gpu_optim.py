@@ -77,8 +77,7 @@ def test_whole_trainer_step_captured_in_a_graph_matches_eager():
     # construction ran warm-up + capture steps: rewind parameters and optimizer state, then replay the 4 batches
     ours.load_state_dict(state0)
     opt.exp_avg.zero_(); opt.exp_avg_sq.zero_(); opt.step_dev.zero_()
-    ours.invalidate_operand_cache()
-    ours.word_embeddings.bf16_shadow()                       # stage the shadow of the rewound table (outside the graph)
+    step.refresh_operands()                                  # the graph reads the shadow buffer it was captured with: re-cast in place
     losses = []
     for b, r in batches:
         losses.append(float(step(b, r)))
