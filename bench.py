@@ -628,6 +628,29 @@ def measure(ctx, name, args):
                            "'existing kernels' of SURVEY §2.1")
         del prm
 
+    # ------------------------------ full trainer step: + global-norm clip + Adam in the same graph ------------------------------
+    # (last: the fused optimizer re-homes the parameters into one flat buffer, which invalidates the graphs captured above)
+    full_step = None
+    if train and args.graphs == "auto" and not args.no_full_step:
+        from rbr_b200.optim import FusedClipAdam
+        opt = FusedClipAdam(model, lr=0.002, max_grad_norm=5.0)                # the reference's lr / max_grad_norm (default_*.json)
+        fg, fpool = [], None
+        for j in range(NB):
+            g_ = GraphedTrainStep(model, loss_fn, *dev_batches[j], warmup=1, pool=fpool, post_backward=post, optimizer=opt,
+                                  max_grad_norm=5.0)
+            fpool = g_.pool
+            fg.append(g_)
+        for _ in range(8):
+            for g_ in fg:
+                g_.replay()
+        ms_f, loss_f = time_graph_loop(ctx, [g_.replay for g_ in fg], K)
+        full_step = {"value": world * c["B"] * K / (ms_f * 1e-3), "unit": "samples/s", "ms_per_step": ms_f / K,
+                     "final_loss": float(loss_f.item()),
+                     "what": "zero_grad + forward + MSELoss + backward" + (" + gradient all-reduce" if world > 1 else "") +
+                             " + clip_grad_norm_(5.0) + Adam(lr 0.002) as ONE CUDA-graph replay (rbr_b200.optim.FusedClipAdam: Σg² + "
+                             "clip·Adam over flat arenas, bf16 shadow of the word table rewritten by the update)"}
+        del fg
+
     out = None
     if rank == 0:
         samples, reasons = value_clocks[0] + e2e_clocks[0], value_clocks[1] | e2e_clocks[1]
@@ -663,9 +686,117 @@ def measure(ctx, name, args):
             out["strong"] = strong
         if library is not None:
             out["library_gpu_baseline"] = library
+        if full_step is not None:
+            out["full_trainer_step"] = full_step
     del model, dev_batches, pinned
     torch.cuda.empty_cache()
     return out
+
+
+def measure_infer_pairs(ctx, args):
+    """BASELINE.json configs[4] as written: --pairs (user, item) pairs in total, vocab 200k, each pair carrying its own two
+    500-token documents (the reference's data flow, trainer/train_deepconn_pp.py:274), sharded contiguously over the ranks,
+    NO collective; every rank writes its slice of the score vector.  Ids are generated on the device chunk by chunk (10 M pairs
+    = 80 GB of int64 ids: never materialised).  Also reported: the same pairs scored from the per-entity feature cache
+    (rbr_b200.inference.PairScorer)."""
+    import torch.distributed as dist
+    from rbr_b200 import parallel, synth
+    from rbr_b200._lib import lib
+    from rbr_b200.inference import PairScorer
+    name = "deepconn_infer"
+    c = CFG[name]
+    rank, world, dev = ctx.rank, ctx.world, ctx.dev
+    model = build(name, dev, args.precision)
+    parallel.broadcast_parameters(model)
+    scorer = PairScorer(model)
+    sh = parallel.shard_range(args.pairs, rank, world)
+    n_mine = len(sh)
+    scores = torch.empty(n_mine, dtype=torch.float32, device=dev)
+    Bc = c["B"]
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(synth.SEED_BASE + rank)
+    NBUF = 4                                              # chunk buffers in flight: generation of chunk i+1 queues behind scoring of i
+
+    def make_chunk(n):
+        u = synth.doc_batch_device(n, c["L"], c["V"], gen, dev, dtype=torch.int32)
+        i = synth.doc_batch_device(n, c["L"], c["V"], gen, dev, dtype=torch.int32)
+        uid = torch.randint(1, c["U"], (n,), device=dev, generator=gen)
+        iid = torch.randint(1, c["I"], (n,), device=dev, generator=gen)
+        return u, i, uid, iid
+    # warm-up (clock ramp) on throw-away chunks
+    ctx.sampler.start()
+    for _ in range(max(args.warmup, 3) + 40):
+        u, i, uid, iid = make_chunk(Bc)
+        scorer.score_pairs(u, i, None, None, uid, iid)
+    ctx.sync_all()
+    l0 = lib.rbr_launch_count()
+    ev_score = []
+    ctx.sampler.mark()
+    t0 = time.perf_counter()
+    done = 0
+    while done < n_mine:
+        n = min(Bc, n_mine - done)
+        u, i, uid, iid = make_chunk(n)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        scores[done:done + n] = scorer.score_pairs(u, i, None, None, uid, iid)
+        e1.record()
+        ev_score.append((e0, e1))
+        done += n
+    ctx.sync_all()
+    wall = time.perf_counter() - t0
+    clocks = ctx.sampler.take()
+    launches = lib.rbr_launch_count() - l0
+    score_ms = sum(a.elapsed_time(b) for a, b in ev_score)
+    t = torch.tensor([wall, score_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    wall, score_ms = float(t[0]), float(t[1])
+    checksum = scores.double().sum().reshape(1)
+    if world > 1:
+        dist.all_reduce(checksum)
+    # the same number of pairs from the per-entity feature cache: U + I documents encoded once, then K1 gather + K4 head
+    user_docs = synth.doc_batch_device(c["U"], c["L"], c["V"], gen, dev, dtype=torch.int32)
+    item_docs = synth.doc_batch_device(c["I"], c["L"], c["V"], gen, dev, dtype=torch.int32)
+    torch.cuda.synchronize()
+    tb = time.perf_counter()
+    scorer.build_cache(user_docs, item_docs)
+    torch.cuda.synchronize()
+    build_s = time.perf_counter() - tb
+    big = 1 << 20
+    tc0 = time.perf_counter()
+    done = 0
+    while done < n_mine:
+        n = min(big, n_mine - done)
+        uid = torch.randint(1, c["U"], (n,), device=dev, generator=gen)
+        iid = torch.randint(1, c["I"], (n,), device=dev, generator=gen)
+        scores[done:done + n] = scorer.score_cached(uid, iid)
+        done += n
+    ctx.sync_all()
+    cached_s = time.perf_counter() - tc0
+    tt = torch.tensor([build_s, cached_s], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    if rank != 0:
+        return None
+    return {
+        "metric": METRIC[name], "value": args.pairs / (score_ms * 1e-3), "unit": "pairs/s", "n_gpus": world,
+        "steps": len(ev_score), "warmup": args.warmup, "ms_per_step": score_ms / max(len(ev_score), 1), "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+        "config": {"workload": workload_name(name), "total_pairs": args.pairs, "pairs_per_gpu": n_mine, "parallelism": f"dp{world} (no collective)"},
+        "run": {"value_is": "total pairs / summed CUDA-event time of the scoring calls (max over ranks)",
+                "total_wall_s": wall, "total_wall_includes": "on-device generation of the ids (80 GB of int64-equivalent for 10 M pairs, produced "
+                "per 4096-pair chunk as int32) + scoring + writing each rank's slice of the score vector",
+                "pairs_per_s_wall": args.pairs / wall, "score_checksum": float(checksum.item())},
+        "e2e": {"value": args.pairs / wall, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                "how": "ids are synthesised on the device (config 5 has no host data set); wall clock of the whole job, max over ranks"},
+        "feature_cache": {"build_s": float(tt[0]), "entities": c["U"] + c["I"], "score_s": float(tt[1]),
+                          "pairs_per_s": args.pairs / float(tt[1]), "pairs_per_s_incl_build": args.pairs / float(tt[0] + tt[1]),
+                          "what": "rbr_b200.inference.PairScorer: each entity's document encoded once, pairs scored with K1 gather + K4 head "
+                                  "(bit-identical scores, tests/test_gpu_benchcfg.py)"},
+        "gpu_launches": int(launches), "gpu_launches_per_step": launches / max(len(ev_score), 1),
+        "clocks": ctx.sampler.summarise(*clocks),
+    }
 
 
 def main():
@@ -692,6 +823,10 @@ def main():
     ap.add_argument("--no-library-baseline", action="store_true",
                     help="skip timing the reference's formulation on ATen/cuBLAS kernels on this GPU (library_gpu_baseline)")
     ap.add_argument("--no-extras", action="store_true", help="skip the per-kernel extras (roofline_other)")
+    ap.add_argument("--no-full-step", action="store_true", help="skip the full trainer step (clip + Adam captured with the step)")
+    ap.add_argument("--pairs", type=int, default=0,
+                    help="--mode infer: score this many synthetic (user, item) pairs in total (BASELINE.json configs[4]: 10000000), "
+                         "sharded over the ranks with no collective, ids generated on the device chunk by chunk")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -719,6 +854,15 @@ def main():
             torch.cuda.synchronize()
     ctx.sync_all = sync_all
 
+    if args.mode == "infer" and args.pairs > 0:
+        line = measure_infer_pairs(ctx, args)
+        ctx.sampler.stop()
+        if ctx.rank == 0:
+            print(json.dumps(line), flush=True)
+        if ctx.world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
     if args.mode == "infer":
         models = ["deepconn_infer"]
     elif args.model == "all":
