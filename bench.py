@@ -388,7 +388,13 @@ def measure(ctx, name, args):
     # exposed collective time per step (N > 1): the same graphed step WITHOUT the gradient exchange
     exposed = None
     if post is not None and graphs is not None:
+        ngram = getattr(model, "ngram", None)
+        saved_hook = getattr(ngram, "table_grad_hook", None)
+        if ngram is not None:
+            ngram.table_grad_hook = None               # no early (in-backward) reduction either: nothing would join its stream
         g_local = GraphedTrainStep(model, loss_fn, *dev_batches[0], warmup=1, pool=pool, post_backward=None)
+        if ngram is not None:
+            ngram.table_grad_hook = saved_hook
         ms_local, _ = time_graph_loop(ctx, [g_local.replay], K)
         exposed = {"ms_per_step_without_exchange": ms_local / K, "exposed_collective_ms_per_step": (total_ms - ms_local) / K}
         del g_local
@@ -493,7 +499,13 @@ def measure(ctx, name, args):
         bs = c["B"] // world
         sb = [([t.to(dev) for t in b], r.to(dev)) for b, r in make_batches(name, 2, rank, b=bs)]
         sg = [GraphedTrainStep(model, loss_fn, *sb[j], warmup=2, pool=None, post_backward=post) for j in range(2)]
+        ngram = getattr(model, "ngram", None)
+        saved_hook = getattr(ngram, "table_grad_hook", None)
+        if ngram is not None:
+            ngram.table_grad_hook = None
         sl = GraphedTrainStep(model, loss_fn, *sb[0], warmup=1, pool=sg[0].pool, post_backward=None)
+        if ngram is not None:
+            ngram.table_grad_hook = saved_hook
         for _ in range(20):
             sg[0].replay(); sg[1].replay()
         ms_s, _ = time_graph_loop(ctx, [g.replay for g in sg], K)

@@ -176,6 +176,24 @@ int rbr_narre_attn_bwd(const float* feat, const int64_t* other_id, int64_t batch
                        float* W_rv_grad, float* W_id_grad, float* h_grad, float* b_1_grad, float* b_2_grad,
                        float* ebd_vals_grad, void* stream);
 
+/* ---- K3 on tensor cores: both attention sides in ONE launch (csrc/attn_tc.cu) ---------------------------------------------
+ * Same function as rbr_narre_attn_fwd / _bwd for n_sides (1 or 2) independent LinearAttention modules at once — NARRE's
+ * user_att and item_att (models/narre/narre.py:184-185) — given as arrays of n_sides pointers per argument.  A CTA owns a
+ * tile of samples; feat@W_rv, e@W_id and the four backward contractions run as mma.sync TF32 in the 3xTF32 scheme (fp32-grade
+ * accuracy).  Returns RBR_EUNSUPPORTED for shapes outside it (att > 32, hidden > 512, reviews > 64): use K3 then.       */
+int rbr_narre_attn_pair_supported(int64_t reviews, int64_t hidden, int64_t att);
+int rbr_narre_attn_pair_fwd(int n_sides, const float* const* feat, const int64_t* const* other_id, int64_t batch, int64_t reviews,
+                            int64_t hidden, int64_t att, const float* const* W_rv, const float* const* W_id, const float* const* h,
+                            const float* const* b_1, const float* const* b_2, const float* const* ebd_vals, const int64_t* n_ids,
+                            float* const* out, float* const* scores, void* stream);
+int rbr_narre_attn_pair_bwd(int n_sides, const float* const* feat, const int64_t* const* other_id, int64_t batch, int64_t reviews,
+                            int64_t hidden, int64_t att, const float* const* W_rv, const float* const* W_id, const float* const* h,
+                            const float* const* b_1, const float* const* b_2, const float* const* ebd_vals, const int64_t* n_ids,
+                            const int64_t* padding_idx, const float* const* scores, const float* const* out_grad,
+                            const float* const* scores_grad, float* const* feat_grad, float* const* W_rv_grad,
+                            float* const* W_id_grad, float* const* h_grad, float* const* b_1_grad, float* const* b_2_grad,
+                            float* const* ebd_vals_grad, void* stream);
+
 /* ---- K4: fused LastFeat ×2 + FM head (+ MSE loss) --------------------------------------------------
  * Replaces LastFeat.forward (models/deepconn/layers.py:156-165) for the user and the item side,
  * FM.forward (layers.py:188-209) and nn.MSELoss (trainer/train_deepconn_pp.py:140,164).

@@ -31,6 +31,7 @@ class NARRE(HotPathModule):
         self.fm = FM(user_size, item_size, latent_dim, dropout, user_padding_idx=user_padding_idx,
                      item_padding_idx=item_padding_idx)
         self.last_arena = None
+        self.fused_attention = True     # both attention sides in one tensor-core launch (False: the per-side K3 kernels)
 
     def _new_arena(self):
         arena = ops.GradArena.for_module(self)
@@ -57,8 +58,16 @@ class NARRE(HotPathModule):
         u_feat, i_feat = self.ngram.encode(self.word_embeddings, [u_docs, i_docs], [u_m, i_m])
         u_feat = u_feat.view(bz, self.doc_num, self.hiddem_dim)
         i_feat = i_feat.view(bz, self.doc_num, self.hiddem_dim)
-        # the user-side and item-side attentions are independent, latency-bound kernels: the item side runs on an auxiliary
-        # stream, forward and (because autograd replays each node on its forward stream) backward
+        ua, ia = self.user_att, self.item_att
+        if self.fused_attention and ops.narre_attn_pair_supported(self.doc_num, self.hiddem_dim, ua.W_rv.shape[1]):
+            # both sides in one launch per direction on the tensor cores (csrc/attn_tc.cu); dropout as in LinearAttention.forward
+            pu = [ua.W_rv, ua.W_id, ua.h, ua.b_1, ua.b_2, ua.ebd_vals.weight]
+            pi = [ia.W_rv, ia.W_id, ia.h, ia.b_1, ia.b_2, ia.ebd_vals.weight]
+            u_out, u_att_scores, i_out, i_att_scores = ops.NarreAttnPairFn.apply(
+                u_feat, reuid, i_feat, reiid, *pu, *pi, (ua.padding_idx, ia.padding_idx), self.last_arena, pu + pi)
+            return ua.dropout(u_out), ia.dropout(i_out), u_att_scores, i_att_scores
+        # fallback (att_dim > 32, ...): one warp-per-sample launch per side, the item side on an auxiliary stream — forward and
+        # (because autograd replays each node on its forward stream) backward
         main = torch.cuda.current_stream()
         aux = ops._side_streams(u_feat.device, 1)[0]
         aux.wait_stream(main)

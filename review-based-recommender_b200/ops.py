@@ -480,6 +480,73 @@ class NarreAttnFn(torch.autograd.Function):
         return (g_feat, None, *grads, None, None, None)
 
 
+def _ptr_array(ptrs):
+    import ctypes
+    return (ctypes.c_void_p * len(ptrs))(*[None if p is None else int(p) for p in ptrs])
+
+
+def _i64_array(vals):
+    import ctypes
+    return (ctypes.c_int64 * len(vals))(*[int(v) for v in vals])
+
+
+class NarreAttnPairFn(torch.autograd.Function):
+    """Both LinearAttention modules of NARRE (narre.py:184-185) in ONE launch per direction on the tensor cores
+    (csrc/attn_tc.cu).  Inputs: feat_u, id_u, feat_i, id_i, then the 6 parameters of each side
+    (W_rv, W_id, h, b_1, b_2, ebd_vals).  Returns (out_u, scores_u [B,R,1], out_i, scores_i [B,R,1]), dropout excluded."""
+
+    @staticmethod
+    def forward(ctx, feat_u, id_u, feat_i, id_i, *rest):
+        _stream(refresh=True)
+        prm = [_req(t, torch.float32, "attention parameter") for t in rest[:12]]
+        pads, arena, params = rest[12], rest[13], rest[14]
+        feats = [_req(feat_u, torch.float32, "feat"), _req(feat_i, torch.float32, "feat")]
+        ids = [_req(id_u, torch.int64, "other_id"), _req(id_i, torch.int64, "other_id")]
+        B, R, H = feats[0].shape
+        if feats[1].shape != feats[0].shape:
+            raise ValueError("rbr_b200: the two attention sides must have the same [B, R, H] shape")
+        A = prm[0].shape[1]
+        outs = [torch.empty(B, H, dtype=torch.float32, device=feats[0].device) for _ in range(2)]
+        scores = [torch.empty(B, R, dtype=torch.float32, device=feats[0].device) for _ in range(2)]
+        side = [prm[:6], prm[6:]]
+        lib.check(lib.rbr_narre_attn_pair_fwd(
+            2, _ptr_array([_p(f) for f in feats]), _ptr_array([_p(i) for i in ids]), B, R, H, A,
+            *[_ptr_array([_p(side[0][j]), _p(side[1][j])]) for j in range(6)],
+            _i64_array([side[0][5].shape[0], side[1][5].shape[0]]), _ptr_array([_p(o) for o in outs]),
+            _ptr_array([_p(s) for s in scores]), _stream()), "rbr_narre_attn_pair_fwd")
+        ctx.save_for_backward(*feats, *ids, *scores, *prm)
+        ctx.pads, ctx.arena, ctx.params = pads, arena, params
+        return outs[0], scores[0].view(B, R, 1), outs[1], scores[1].view(B, R, 1)
+
+    @staticmethod
+    def backward(ctx, g_out_u, g_sc_u, g_out_i, g_sc_i):
+        _stream(refresh=True)
+        saved = ctx.saved_tensors
+        feats, ids, scores, prm = saved[0:2], saved[2:4], saved[4:6], saved[6:18]
+        B, R, H = feats[0].shape
+        A = prm[0].shape[1]
+        dev = feats[0].device
+        g_outs = [torch.zeros(B, H, device=dev) if g is None else g.contiguous() for g in (g_out_u, g_out_i)]
+        g_scs = [None if g is None else g.contiguous() for g in (g_sc_u, g_sc_i)]
+        g_feats = [torch.empty_like(feats[0]), torch.empty_like(feats[1])]
+        grads = [_grad_buf(ctx.arena, p, True) for p in ctx.params]             # 12: side u then side i
+        side, gside = [prm[:6], prm[6:]], [grads[:6], grads[6:]]
+        pads = [-1 if x is None else int(x) for x in ctx.pads]
+        any_sc = any(g is not None for g in g_scs)
+        lib.check(lib.rbr_narre_attn_pair_bwd(
+            2, _ptr_array([_p(f) for f in feats]), _ptr_array([_p(i) for i in ids]), B, R, H, A,
+            *[_ptr_array([_p(side[0][j]), _p(side[1][j])]) for j in range(6)],
+            _i64_array([side[0][5].shape[0], side[1][5].shape[0]]), _i64_array(pads), _ptr_array([_p(s) for s in scores]),
+            _ptr_array([_p(g) for g in g_outs]), _ptr_array([_p(g) for g in g_scs]) if any_sc else None,
+            _ptr_array([_p(g) for g in g_feats]),
+            *[_ptr_array([_p(gside[0][j]), _p(gside[1][j])]) for j in range(6)], _stream()), "rbr_narre_attn_pair_bwd")
+        return (g_feats[0], None, g_feats[1], None, *grads, None, None, None)
+
+
+def narre_attn_pair_supported(R: int, H: int, A: int) -> bool:
+    return bool(lib.rbr_narre_attn_pair_supported(R, H, A))
+
+
 # ---------------------------------------------------------------------------------------------------
 # K4: LastFeat x2 + FM head
 # ---------------------------------------------------------------------------------------------------

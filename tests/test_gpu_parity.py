@@ -231,3 +231,49 @@ def test_two_pass_backward_with_table_hook_matches_single_pass():
     for k in grads[0]:
         assert rel_err(grads[1][k], grads[0][k]) < 1e-6, k
     assert rel_err(seen["table"].cpu(), g.grads["word_embeddings.embedding.weight"]) < FP32_GRAD_TOL
+
+
+@pytest.mark.parametrize("shape", [(33, 10, 150, 32), (7, 4, 8, 5), (5, 5, 15, 6), (100, 6, 100, 16), (3, 1, 40, 8), (70, 17, 64, 32),
+                                   (4096, 10, 150, 32)])
+def test_attention_pair_tensor_core_kernels_vs_oracle(shape):
+    """K3 on tensor cores (csrc/attn_tc.cu, 3xTF32 mma.sync, both sides in one launch): outputs, scores and every gradient
+    against the oracle's LinearAttention at the fp32 tolerance; padded reviews (id 0) keep softmax mass and give the padding
+    row no gradient."""
+    B, R, H, A = shape
+    assert ops.narre_attn_pair_supported(R, H, A)
+    gen = torch.Generator().manual_seed(B + R + H)
+    n_ids = (23, 31)
+    sides = []
+    for s in range(2):
+        feat = torch.randn(B, R, H, generator=gen).abs() * 0.5                   # pooled ReLU features are non-negative
+        oid = torch.randint(0, n_ids[s], (B, R), generator=gen)
+        oid[:, -1] = 0                                                           # a padded review per sample
+        prm = [(torch.rand(H, A, generator=gen) * 2 - 1) * 0.1, (torch.rand(A, A, generator=gen) * 2 - 1) * 0.1,
+               (torch.rand(A, 1, generator=gen) * 2 - 1) * 0.1, torch.full((A,), 0.1), torch.full((1,), 0.1),
+               torch.randn(n_ids[s], A, generator=gen)]
+        prm[5][0] = 0
+        sides.append((feat, oid, prm))
+    g_out = [torch.randn(B, H, generator=gen) for _ in range(2)]
+    g_sc = [torch.randn(B, R, 1, generator=gen) * 0.1 for _ in range(2)]
+    # oracle (float64)
+    ref = []
+    for (feat, oid, prm), go, gs in zip(sides, g_out, g_sc):
+        f64 = feat.double().requires_grad_(True)
+        p64 = [p.double().requires_grad_(True) for p in prm]
+        out, sc = orc.linear_attention(f64, oid, *p64)
+        ((out * go.double()).sum() + (sc * gs.double()).sum()).backward()
+        ge = p64[5].grad.clone()
+        ge[0] = 0                                                                # nn.Embedding(padding_idx=0)
+        ref.append((out.detach(), sc.detach(), f64.grad, [p.grad for p in p64[:5]] + [ge]))
+    cu = [(f.cuda().requires_grad_(True), o.cuda(), [p.cuda().requires_grad_(True) for p in prm]) for f, o, prm in sides]
+    params = cu[0][2] + cu[1][2]
+    out_u, sc_u, out_i, sc_i = ops.NarreAttnPairFn.apply(cu[0][0], cu[0][1], cu[1][0], cu[1][1], *params, (0, 0), None, params)
+    loss = (out_u * g_out[0].cuda()).sum() + (sc_u * g_sc[0].cuda()).sum() + (out_i * g_out[1].cuda()).sum() + (sc_i * g_sc[1].cuda()).sum()
+    loss.backward()
+    for s, (o, sc) in enumerate(((out_u, sc_u), (out_i, sc_i))):
+        assert rel_err(o.detach().cpu(), ref[s][0]) < FP32_TOL
+        assert rel_err(sc.detach().cpu(), ref[s][1]) < FP32_TOL
+        assert rel_err(cu[s][0].grad.cpu(), ref[s][2]) < FP32_GRAD_TOL
+        for j, name in enumerate(("W_rv", "W_id", "h", "b_1", "b_2", "ebd_vals")):
+            assert rel_err(cu[s][2][j].grad.cpu(), ref[s][3][j], 1e-3 if name == "b_2" else 1e-12) < FP32_GRAD_TOL, (s, name)
+        assert float(cu[s][2][5].grad[0].abs().max()) == 0.0
