@@ -578,7 +578,7 @@ static bool attn_tc_plan(int64_t B, int R, int H, int A, bool bwd, AttnArgs* a, 
     // dW_rv m-tiles per warp must fit the register budget
     if (((a->Hp8 + 15) / 16 + a->NW - 1) / a->NW > 4) return false;
     *smem_bytes = (size_t)attn_tc_smem(*a, bwd).total * 4;
-    return *smem_bytes <= 200 * 1024;
+    return *smem_bytes <= 227 * 1024;
 }
 
 }  // namespace rbr
@@ -618,7 +618,7 @@ extern "C" int rbr_narre_attn_pair_fwd(int n_sides, const float* const* feat, co
     if (batch == 0) return RBR_OK;
     static bool attr = false;
     if (!attr) {
-        RBR_CUDA(cudaFuncSetAttribute(narre_attn_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        RBR_CUDA(cudaFuncSetAttribute(narre_attn_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr = true;
     }
     const int64_t n_tiles = (batch + a.TS - 1) / a.TS;
@@ -658,7 +658,7 @@ extern "C" int rbr_narre_attn_pair_bwd(int n_sides, const float* const* feat, co
     if (batch == 0) return RBR_OK;
     static bool attr = false;
     if (!attr) {
-        RBR_CUDA(cudaFuncSetAttribute(narre_attn_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        RBR_CUDA(cudaFuncSetAttribute(narre_attn_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr = true;
     }
     const int64_t n_tiles = (batch + a.TS - 1) / a.TS;
