@@ -152,26 +152,72 @@ __device__ __forceinline__ void stage_b_operand(float* hi, float* lo, const floa
     }
 }
 
-// feature rows + gathered id-embedding rows of one tile → shared memory (zero padded rows / columns)
+// async global → shared copies (LDGSTS): a thread issues all its copies of a tile back to back — with one CTA of 5 warps per
+// SM a load-then-store loop exposes a full memory round trip per iteration
+__device__ __forceinline__ void cp_async_f32(float* dst_smem, const float* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_f32x2(float* dst_smem, const float* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_f32x4(float* dst_smem, const float* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all_() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// rows [0, n_rows) x columns [0, H) of a row-major fp32 matrix (row pitch H) → shared tile of pitch PF; the padding
+// (columns >= H, rows >= n_rows up to rows_pad) must already be zero (zero_tile_padding)
+__device__ __forceinline__ void stage_rows_async(float* tile, int PF, const float* __restrict__ src, int n_rows, int H) {
+    if ((H & 1) == 0 && (reinterpret_cast<uintptr_t>(src) & 7) == 0) {
+        const int h2 = H >> 1;
+        for (int i = threadIdx.x; i < n_rows * h2; i += blockDim.x) {
+            const int r = i / h2, c = (i - r * h2) * 2;
+            cp_async_f32x2(tile + r * PF + c, src + (int64_t)r * H + c);
+        }
+    } else {
+        for (int i = threadIdx.x; i < n_rows * H; i += blockDim.x) {
+            const int r = i / H, c = i - r * H;
+            cp_async_f32(tile + r * PF + c, src + (int64_t)r * H + c);
+        }
+    }
+}
+// zero what stage_rows_async does not write: columns [H, PF) of the live rows and the dead rows entirely
+__device__ __forceinline__ void zero_tile_padding(float* tile, int PF, int rows_pad, int n_rows, int H) {
+    const int padc = PF - H;
+    for (int i = threadIdx.x; i < n_rows * padc; i += blockDim.x) tile[(i / padc) * PF + H + i % padc] = 0.f;
+    for (int i = n_rows * PF + threadIdx.x; i < rows_pad * PF; i += blockDim.x) tile[i] = 0.f;
+}
+
+// feature rows + gathered id-embedding rows of one tile → shared memory (zero padded rows / columns); the caller waits
+// (cp_async_wait_all_ + __syncthreads) before reading
 __device__ __forceinline__ void attn_stage_tile(const AttnArgs& a, const AttnSide& sd, int64_t b0, int n_s, float* Fs, float* Es,
                                                 bool count_oob) {
     const int rows_pad = a.NW * 16;
     const int rows_live = n_s * a.R;
-    const float* src = sd.feat + b0 * a.R * a.H;
-    for (int i = threadIdx.x; i < rows_pad * a.PF; i += blockDim.x) {
-        const int r = i / a.PF, c = i - r * a.PF;
-        Fs[i] = (r < rows_live && c < a.H) ? __ldg(src + (int64_t)r * a.H + c) : 0.f;
-    }
-    for (int i = threadIdx.x; i < rows_pad * 32; i += blockDim.x) {
-        const int r = i >> 5, c = i & 31;
-        float v = 0.f;
+    zero_tile_padding(Fs, a.PF, rows_pad, rows_live, a.H);
+    stage_rows_async(Fs, a.PF, sd.feat + b0 * a.R * a.H, rows_live, a.H);
+    const bool v4 = (a.A & 3) == 0;
+    for (int i = threadIdx.x; i < rows_pad * 8; i += blockDim.x) {            // 8 chunks of 4 attention columns per row
+        const int r = i >> 3, c = (i & 7) * 4;
+        float* dst = Es + r * a.PE + c;
+        bool copied = false;
         if (r < rows_live) {
             const int64_t id = __ldg(sd.other_id + b0 * a.R + r);
             const bool ok = id >= 0 && id < sd.n_ids;
             if (!ok && c == 0 && count_oob) note_oob();
-            if (ok && c < a.A) v = __ldg(sd.ebd + id * a.A + c);
+            if (ok && c < a.A) {
+                const float* src = sd.ebd + id * a.A + c;
+                if (v4) {
+                    cp_async_f32x4(dst, src);
+                    copied = true;
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) dst[j] = c + j < a.A ? __ldg(src + j) : 0.f;
+                    copied = true;
+                }
+            }
         }
-        Es[r * a.PE + c] = v;
+        if (!copied) *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
 }
 
@@ -203,6 +249,7 @@ __global__ void __launch_bounds__(AT_MAXW * 32) narre_attn_tc_fwd_kernel(const A
         const int n_s = (int)min((int64_t)a.TS, a.B - b0);
         __syncthreads();                                   // previous tile's readers are done with Fs / Ss
         attn_stage_tile(a, sd, b0, n_s, Fs, Es, true);
+        cp_async_wait_all_();
         __syncthreads();
         {
             float acc[4][4];
@@ -313,11 +360,10 @@ __global__ void __launch_bounds__(AT_MAXW * 32) narre_attn_tc_bwd_kernel(const A
         const int rows_live = n_s * a.R;
         __syncthreads();
         attn_stage_tile(a, sd, b0, n_s, Fs, Es, false);
-        for (int i = threadIdx.x; i < a.TS * a.PF; i += blockDim.x) {
-            const int s = i / a.PF, c = i - s * a.PF;
-            GO[i] = (s < n_s && c < a.H) ? __ldg(sd.out_grad + (b0 + s) * a.H + c) : 0.f;
-        }
+        zero_tile_padding(GO, a.PF, a.TS, n_s, a.H);
+        stage_rows_async(GO, a.PF, sd.out_grad + b0 * a.H, n_s, a.H);
         for (int i = threadIdx.x; i < rows_pad; i += blockDim.x) Ss[i] = i < rows_live ? __ldg(sd.scores + b0 * a.R + i) : 0.f;
+        cp_async_wait_all_();
         __syncthreads();
         // ds[row] = out_grad[s] · feat[row] (+ scores_grad[row])
         for (int r = warp; r < rows_live; r += a.NW) {
