@@ -16,7 +16,7 @@
 
 namespace rbr {
 
-constexpr int AT_MAXW = 8;         // warps per CTA = m-tiles (16 review rows each) per sample tile
+constexpr int AT_MAXW = 6;         // m-tiles (16 review rows each) per sample tile; two warps per m-tile → <= 384 threads
 
 // ---- mma.sync m16n8k8 TF32 ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
@@ -82,7 +82,7 @@ __host__ __device__ inline AttnSmem attn_tc_smem(const AttnArgs& a, bool bwd) {
     s.widT_lo = off; if (bwd) off += 32 * pa;
     s.F = off; off += (a.NW * 16) * a.PF;
     s.E = off; off += (a.NW * 16) * a.PE;
-    s.L = off; off += a.NW * 16;                      // logits / d logits per row
+    s.L = off; off += 2 * a.NW * 16;                  // logit partials of the two column halves / d logits per row
     s.S = off; off += a.NW * 16;                      // scores per row
     s.GO = off; if (bwd) off += a.TS * a.PF;          // out_grad rows of the tile's samples
     s.DHa = off; if (bwd) off += (a.NW * 16) * 36;    // d hid as an A operand (row-major, pitch 36)
@@ -92,32 +92,39 @@ __host__ __device__ inline AttnSmem attn_tc_smem(const AttnArgs& a, bool bwd) {
     return s;
 }
 
-// hid accumulators of this warp's m-tile: acc[nt][.] (4 n-tiles of 8 attention units) = F·W_rv + E·W_id
+// pick this warp's two n-tiles (half nh of the 32 attention columns) out of a 4-n-tile B-fragment load
+__device__ __forceinline__ float sel0(const float4& v, int nh) { return nh ? v.z : v.x; }
+__device__ __forceinline__ float sel1(const float4& v, int nh) { return nh ? v.w : v.y; }
+
+// hid accumulators of this warp: m-tile rows m0..m0+15, n-tiles 2nh and 2nh+1 (16 of the 32 attention units) = F·W_rv + E·W_id
 __device__ __forceinline__ void attn_hidden_mma(const float* Fs, int PF, const float* Es, int PE, const float* wrv_hi, const float* wrv_lo,
-                                                const float* wid_hi, const float* wid_lo, int Hp8, int m0, int lane, float (&acc)[4][4]) {
+                                                const float* wid_hi, const float* wid_lo, int Hp8, int m0, int nh, int lane,
+                                                float (&acc)[2][4]) {
     const int g = lane >> 2, t = lane & 3;
-    const int pa = b_pitch(32);
+    constexpr int pa = b_pitch(32);
 #pragma unroll
-    for (int nt = 0; nt < 4; ++nt)
+    for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
         for (int i = 0; i < 4; ++i) acc[nt][i] = 0.f;
     const float* fa = Fs + (m0 + g) * PF + t;
-    for (int k0 = 0; k0 < Hp8; k0 += 8) {
+    const float* bh = wrv_hi + t * pa + g * 4;
+    const float* bl = wrv_lo + t * pa + g * 4;
+    for (int k0 = 0; k0 < Hp8; k0 += 8, fa += 8, bh += 8 * pa, bl += 8 * pa) {
         uint32_t ahi[4], alo[4];
-        split_hi_lo(fa[k0], ahi[0], alo[0]);
-        split_hi_lo(fa[k0 + 8 * PF], ahi[1], alo[1]);
-        split_hi_lo(fa[k0 + 4], ahi[2], alo[2]);
-        split_hi_lo(fa[k0 + 8 * PF + 4], ahi[3], alo[3]);
-        const float4 bh0 = *reinterpret_cast<const float4*>(wrv_hi + (k0 + t) * pa + g * 4);
-        const float4 bh1 = *reinterpret_cast<const float4*>(wrv_hi + (k0 + t + 4) * pa + g * 4);
-        const float4 bl0 = *reinterpret_cast<const float4*>(wrv_lo + (k0 + t) * pa + g * 4);
-        const float4 bl1 = *reinterpret_cast<const float4*>(wrv_lo + (k0 + t + 4) * pa + g * 4);
-        mma_3x(acc[0], ahi, alo, __float_as_uint(bh0.x), __float_as_uint(bh1.x), __float_as_uint(bl0.x), __float_as_uint(bl1.x));
-        mma_3x(acc[1], ahi, alo, __float_as_uint(bh0.y), __float_as_uint(bh1.y), __float_as_uint(bl0.y), __float_as_uint(bl1.y));
-        mma_3x(acc[2], ahi, alo, __float_as_uint(bh0.z), __float_as_uint(bh1.z), __float_as_uint(bl0.z), __float_as_uint(bl1.z));
-        mma_3x(acc[3], ahi, alo, __float_as_uint(bh0.w), __float_as_uint(bh1.w), __float_as_uint(bl0.w), __float_as_uint(bl1.w));
+        split_hi_lo(fa[0], ahi[0], alo[0]);
+        split_hi_lo(fa[8 * PF], ahi[1], alo[1]);
+        split_hi_lo(fa[4], ahi[2], alo[2]);
+        split_hi_lo(fa[8 * PF + 4], ahi[3], alo[3]);
+        const float4 bh0 = *reinterpret_cast<const float4*>(bh), bh1 = *reinterpret_cast<const float4*>(bh + 4 * pa);
+        const float4 bl0 = *reinterpret_cast<const float4*>(bl), bl1 = *reinterpret_cast<const float4*>(bl + 4 * pa);
+        mma_3x(acc[0], ahi, alo, __float_as_uint(sel0(bh0, nh)), __float_as_uint(sel0(bh1, nh)), __float_as_uint(sel0(bl0, nh)),
+               __float_as_uint(sel0(bl1, nh)));
+        mma_3x(acc[1], ahi, alo, __float_as_uint(sel1(bh0, nh)), __float_as_uint(sel1(bh1, nh)), __float_as_uint(sel1(bl0, nh)),
+               __float_as_uint(sel1(bl1, nh)));
     }
     const float* ea = Es + (m0 + g) * PE + t;
+    const float* ih = wid_hi + t * pa + g * 4;
+    const float* il = wid_lo + t * pa + g * 4;
 #pragma unroll
     for (int k0 = 0; k0 < 32; k0 += 8) {
         uint32_t ahi[4], alo[4];
@@ -125,14 +132,12 @@ __device__ __forceinline__ void attn_hidden_mma(const float* Fs, int PF, const f
         split_hi_lo(ea[k0 + 8 * PE], ahi[1], alo[1]);
         split_hi_lo(ea[k0 + 4], ahi[2], alo[2]);
         split_hi_lo(ea[k0 + 8 * PE + 4], ahi[3], alo[3]);
-        const float4 bh0 = *reinterpret_cast<const float4*>(wid_hi + (k0 + t) * pa + g * 4);
-        const float4 bh1 = *reinterpret_cast<const float4*>(wid_hi + (k0 + t + 4) * pa + g * 4);
-        const float4 bl0 = *reinterpret_cast<const float4*>(wid_lo + (k0 + t) * pa + g * 4);
-        const float4 bl1 = *reinterpret_cast<const float4*>(wid_lo + (k0 + t + 4) * pa + g * 4);
-        mma_3x(acc[0], ahi, alo, __float_as_uint(bh0.x), __float_as_uint(bh1.x), __float_as_uint(bl0.x), __float_as_uint(bl1.x));
-        mma_3x(acc[1], ahi, alo, __float_as_uint(bh0.y), __float_as_uint(bh1.y), __float_as_uint(bl0.y), __float_as_uint(bl1.y));
-        mma_3x(acc[2], ahi, alo, __float_as_uint(bh0.z), __float_as_uint(bh1.z), __float_as_uint(bl0.z), __float_as_uint(bl1.z));
-        mma_3x(acc[3], ahi, alo, __float_as_uint(bh0.w), __float_as_uint(bh1.w), __float_as_uint(bl0.w), __float_as_uint(bl1.w));
+        const float4 bh0 = *reinterpret_cast<const float4*>(ih + k0 * pa), bh1 = *reinterpret_cast<const float4*>(ih + (k0 + 4) * pa);
+        const float4 bl0 = *reinterpret_cast<const float4*>(il + k0 * pa), bl1 = *reinterpret_cast<const float4*>(il + (k0 + 4) * pa);
+        mma_3x(acc[0], ahi, alo, __float_as_uint(sel0(bh0, nh)), __float_as_uint(sel0(bh1, nh)), __float_as_uint(sel0(bl0, nh)),
+               __float_as_uint(sel0(bl1, nh)));
+        mma_3x(acc[1], ahi, alo, __float_as_uint(sel1(bh0, nh)), __float_as_uint(sel1(bh1, nh)), __float_as_uint(sel1(bl0, nh)),
+               __float_as_uint(sel1(bl1, nh)));
     }
 }
 
@@ -165,27 +170,25 @@ __device__ __forceinline__ void cp_async_f32x4(float* dst_smem, const float* src
 }
 __device__ __forceinline__ void cp_async_wait_all_() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-// rows [0, n_rows) x columns [0, H) of a row-major fp32 matrix (row pitch H) → shared tile of pitch PF; the padding
-// (columns >= H, rows >= n_rows up to rows_pad) must already be zero (zero_tile_padding)
-__device__ __forceinline__ void stage_rows_async(float* tile, int PF, const float* __restrict__ src, int n_rows, int H) {
-    if ((H & 1) == 0 && (reinterpret_cast<uintptr_t>(src) & 7) == 0) {
-        const int h2 = H >> 1;
-        for (int i = threadIdx.x; i < n_rows * h2; i += blockDim.x) {
-            const int r = i / h2, c = (i - r * h2) * 2;
-            cp_async_f32x2(tile + r * PF + c, src + (int64_t)r * H + c);
-        }
-    } else {
-        for (int i = threadIdx.x; i < n_rows * H; i += blockDim.x) {
-            const int r = i / H, c = i - r * H;
-            cp_async_f32(tile + r * PF + c, src + (int64_t)r * H + c);
+// rows [0, n_rows) x columns [0, H) of a row-major fp32 matrix (row pitch H) → shared tile of pitch PF, rows n_rows..rows_pad
+// and columns H..PF zero-filled.  One warp per row (no index divisions), lanes across the columns.
+__device__ __forceinline__ void stage_rows_async(float* tile, int PF, int rows_pad, const float* __restrict__ src, int n_rows, int H) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const bool pair = (H & 1) == 0 && (reinterpret_cast<uintptr_t>(src) & 7) == 0;
+    for (int r = warp; r < rows_pad; r += nw) {
+        float* dst = tile + r * PF;
+        if (r < n_rows) {
+            const float* s_ = src + (int64_t)r * H;
+            if (pair) {
+                for (int c = lane * 2; c < H; c += 64) cp_async_f32x2(dst + c, s_ + c);
+            } else {
+                for (int c = lane; c < H; c += 32) cp_async_f32(dst + c, s_ + c);
+            }
+            for (int c = H + lane; c < PF; c += 32) dst[c] = 0.f;
+        } else {
+            for (int c = lane; c < PF; c += 32) dst[c] = 0.f;
         }
     }
-}
-// zero what stage_rows_async does not write: columns [H, PF) of the live rows and the dead rows entirely
-__device__ __forceinline__ void zero_tile_padding(float* tile, int PF, int rows_pad, int n_rows, int H) {
-    const int padc = PF - H;
-    for (int i = threadIdx.x; i < n_rows * padc; i += blockDim.x) tile[(i / padc) * PF + H + i % padc] = 0.f;
-    for (int i = n_rows * PF + threadIdx.x; i < rows_pad * PF; i += blockDim.x) tile[i] = 0.f;
 }
 
 // feature rows + gathered id-embedding rows of one tile → shared memory (zero padded rows / columns); the caller waits
@@ -194,8 +197,7 @@ __device__ __forceinline__ void attn_stage_tile(const AttnArgs& a, const AttnSid
                                                 bool count_oob) {
     const int rows_pad = a.NW * 16;
     const int rows_live = n_s * a.R;
-    zero_tile_padding(Fs, a.PF, rows_pad, rows_live, a.H);
-    stage_rows_async(Fs, a.PF, sd.feat + b0 * a.R * a.H, rows_live, a.H);
+    stage_rows_async(Fs, a.PF, rows_pad, sd.feat + b0 * a.R * a.H, rows_live, a.H);
     const bool v4 = (a.A & 3) == 0;
     for (int i = threadIdx.x; i < rows_pad * 8; i += blockDim.x) {            // 8 chunks of 4 attention columns per row
         const int r = i >> 3, c = (i & 7) * 4;
@@ -221,25 +223,27 @@ __device__ __forceinline__ void attn_stage_tile(const AttnArgs& a, const AttnSid
     }
 }
 
-__global__ void __launch_bounds__(AT_MAXW * 32) narre_attn_tc_fwd_kernel(const AttnArgs a) {
+__global__ void __launch_bounds__(2 * AT_MAXW * 32) narre_attn_tc_fwd_kernel(const AttnArgs a) {
     extern __shared__ __align__(16) float smem[];
     const AttnSide& sd = a.side[blockIdx.y];
     const AttnSmem L = attn_tc_smem(a, false);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+    const int mt = warp >> 1, nh = warp & 1;            // two warps per m-tile of 16 review rows: attention units 16nh .. 16nh+15
     stage_b_operand(smem + L.wrv_hi, smem + L.wrv_lo, sd.W_rv, a.H, a.Hp8, a.A, a.A, false);
     stage_b_operand(smem + L.wid_hi, smem + L.wid_lo, sd.W_id, a.A, 32, a.A, a.A, false);
     float* Fs = smem + L.F;
     float* Es = smem + L.E;
-    float* Ls = smem + L.L;
+    float* Ls = smem + L.L;                              // [2][rows_pad]: logit partials of the two column halves
     float* Ss = smem + L.S;
+    const int rows_pad = a.NW * 16;
     const float b2v = __ldg(sd.b2);
-    // this lane's 8 attention units: columns nt*8 + 2t, +1
-    float b1v[4][2], hv[4][2];
+    // this lane's 4 attention units: columns (2nh + nt) * 8 + 2t, +1
+    float b1v[2][2], hv[2][2];
 #pragma unroll
-    for (int nt = 0; nt < 4; ++nt)
+    for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
-            const int c = nt * 8 + 2 * t + j;
+            const int c = (2 * nh + nt) * 8 + 2 * t + j;
             b1v[nt][j] = c < a.A ? __ldg(sd.b1 + c) : 0.f;
             hv[nt][j] = c < a.A ? __ldg(sd.h + c) : 0.f;
         }
@@ -252,11 +256,11 @@ __global__ void __launch_bounds__(AT_MAXW * 32) narre_attn_tc_fwd_kernel(const A
         cp_async_wait_all_();
         __syncthreads();
         {
-            float acc[4][4];
-            attn_hidden_mma(Fs, a.PF, Es, a.PE, smem + L.wrv_hi, smem + L.wrv_lo, smem + L.wid_hi, smem + L.wid_lo, a.Hp8, warp * 16, lane, acc);
-            float p0 = 0.f, p1 = 0.f;                      // logit partials of rows g and g + 8
+            float acc[2][4];
+            attn_hidden_mma(Fs, a.PF, Es, a.PE, smem + L.wrv_hi, smem + L.wrv_lo, smem + L.wid_hi, smem + L.wid_lo, a.Hp8, mt * 16, nh, lane, acc);
+            float p0 = 0.f, p1 = 0.f;                      // logit partials of rows g and g + 8 over this warp's 16 units
 #pragma unroll
-            for (int nt = 0; nt < 4; ++nt) {
+            for (int nt = 0; nt < 2; ++nt) {
                 p0 = fmaf(fmaxf(acc[nt][0] + b1v[nt][0], 0.f), hv[nt][0], p0);
                 p0 = fmaf(fmaxf(acc[nt][1] + b1v[nt][1], 0.f), hv[nt][1], p0);
                 p1 = fmaf(fmaxf(acc[nt][2] + b1v[nt][0], 0.f), hv[nt][0], p1);
@@ -264,30 +268,37 @@ __global__ void __launch_bounds__(AT_MAXW * 32) narre_attn_tc_fwd_kernel(const A
             }
             p0 += __shfl_xor_sync(0xffffffffu, p0, 1); p0 += __shfl_xor_sync(0xffffffffu, p0, 2);
             p1 += __shfl_xor_sync(0xffffffffu, p1, 1); p1 += __shfl_xor_sync(0xffffffffu, p1, 2);
-            if (t == 0) { Ls[warp * 16 + g] = p0 + b2v; Ls[warp * 16 + g + 8] = p1 + b2v; }
+            if (t == 0) { Ls[nh * rows_pad + mt * 16 + g] = p0; Ls[nh * rows_pad + mt * 16 + g + 8] = p1; }
         }
         __syncthreads();
         // softmax over the R reviews of a sample (max-shifted, the reference's +1e-8 rescaled: finite where it overflows)
         if (threadIdx.x < n_s) {
             const int s = threadIdx.x;
             float m = -INFINITY;
-            for (int r = 0; r < a.R; ++r) m = fmaxf(m, Ls[s * a.R + r]);
-            float sum = 0.f;
-            for (int r = 0; r < a.R; ++r) sum += expf(Ls[s * a.R + r] - m);
-            const float denom = sum + 1e-8f * expf(-m);
             for (int r = 0; r < a.R; ++r) {
-                const float sc = expf(Ls[s * a.R + r] - m) / denom;
+                const float lg = Ls[s * a.R + r] + Ls[rows_pad + s * a.R + r] + b2v;
+                Ls[s * a.R + r] = lg;
+                m = fmaxf(m, lg);
+            }
+            float sum = 0.f;
+            for (int r = 0; r < a.R; ++r) { const float e = expf(Ls[s * a.R + r] - m); Ss[s * a.R + r] = e; sum += e; }
+            const float inv = 1.f / (sum + 1e-8f * expf(-m));
+            for (int r = 0; r < a.R; ++r) {
+                const float sc = Ss[s * a.R + r] * inv;
                 Ss[s * a.R + r] = sc;
                 sd.scores[(b0 + s) * a.R + r] = sc;
             }
         }
         __syncthreads();
-        // out[s, :] = sum_r score[s, r] * feat[s, r, :]
-        for (int i = threadIdx.x; i < n_s * a.H; i += blockDim.x) {
-            const int s = i / a.H, hcol = i - s * a.H;
-            float acc = 0.f;
-            for (int r = 0; r < a.R; ++r) acc = fmaf(Ss[s * a.R + r], Fs[(s * a.R + r) * a.PF + hcol], acc);
-            sd.out[(b0 + s) * a.H + hcol] = acc;
+        // out[s, :] = sum_r score[s, r] * feat[s, r, :]      (one warp per sample, lanes across the features)
+        for (int s = warp; s < n_s; s += (int)(blockDim.x >> 5)) {
+            const float* fr = Fs + s * a.R * a.PF;
+            const float* sc = Ss + s * a.R;
+            for (int hcol = lane; hcol < a.H; hcol += 32) {
+                float acc = 0.f;
+                for (int r = 0; r < a.R; ++r) acc = fmaf(sc[r], fr[r * a.PF + hcol], acc);
+                sd.out[(b0 + s) * a.H + hcol] = acc;
+            }
         }
     }
 }
@@ -295,26 +306,27 @@ __global__ void __launch_bounds__(AT_MAXW * 32) narre_attn_tc_fwd_kernel(const A
 // ---------------------------------------------------------------------------------------------------------------------
 // backward
 // ---------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(AT_MAXW * 32) narre_attn_tc_bwd_kernel(const AttnArgs a) {
+__global__ void __launch_bounds__(2 * AT_MAXW * 32) narre_attn_tc_bwd_kernel(const AttnArgs a) {
     extern __shared__ __align__(16) float smem[];
     const AttnSide& sd = a.side[blockIdx.y];
     const AttnSmem L = attn_tc_smem(a, true);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
-    const int pa = b_pitch(32);
+    const int mt = warp >> 1, nh = warp & 1, n_warps = (int)(blockDim.x >> 5);
+    constexpr int pa = b_pitch(32);
     const int hcols = (a.Hp8 + 31) / 32 * 32, pht = b_pitch(hcols), n_hgroups = hcols / 32;
     stage_b_operand(smem + L.wrv_hi, smem + L.wrv_lo, sd.W_rv, a.H, a.Hp8, a.A, a.A, false);
     stage_b_operand(smem + L.wid_hi, smem + L.wid_lo, sd.W_id, a.A, 32, a.A, a.A, false);
     stage_b_operand(smem + L.widT_hi, smem + L.widT_lo, sd.W_id, a.A, 32, a.A, a.A, true);        // [k = a][n = a2] = W_id[a2][a]
     // W_rvᵀ as a B operand [k = a (32 rows)][n = h (hcols columns)]
-    for (int i = threadIdx.x; i < 32 * hcols; i += blockDim.x) {
-        const int k = i / hcols, n = i - k * hcols;
-        const float v = (k < a.A && n < a.H) ? __ldg(sd.W_rv + n * a.A + k) : 0.f;
-        uint32_t h_, l_;
-        split_hi_lo(v, h_, l_);
-        const int idx = b_index(k, n, pht);
-        smem[L.wrvT_hi + idx] = __uint_as_float(h_);
-        smem[L.wrvT_lo + idx] = __uint_as_float(l_);
-    }
+    for (int k = warp; k < 32; k += n_warps)
+        for (int n = lane; n < hcols; n += 32) {
+            const float v = (k < a.A && n < a.H) ? __ldg(sd.W_rv + n * a.A + k) : 0.f;
+            uint32_t h_, l_;
+            split_hi_lo(v, h_, l_);
+            const int idx = b_index(k, n, pht);
+            smem[L.wrvT_hi + idx] = __uint_as_float(h_);
+            smem[L.wrvT_lo + idx] = __uint_as_float(l_);
+        }
     float* Fs = smem + L.F;
     float* Es = smem + L.E;
     float* Ls = smem + L.L;
@@ -323,32 +335,32 @@ __global__ void __launch_bounds__(AT_MAXW * 32) narre_attn_tc_bwd_kernel(const A
     float* DHa = smem + L.DHa;
     float* DHb = smem + L.DHb;
     float* red = smem + L.red;
-    float b1v[4][2], hv[4][2];
+    float b1v[2][2], hv[2][2];
 #pragma unroll
-    for (int nt = 0; nt < 4; ++nt)
+    for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
-            const int c = nt * 8 + 2 * t + j;
+            const int c = (2 * nh + nt) * 8 + 2 * t + j;
             b1v[nt][j] = c < a.A ? __ldg(sd.b1 + c) : 0.f;
             hv[nt][j] = c < a.A ? __ldg(sd.h + c) : 0.f;
         }
     // persistent partial parameter gradients of this thread
-    float dh_p[4][2], db1_p[4][2], db2_p = 0.f;
+    float dh_p[2][2], db1_p[2][2], db2_p = 0.f;
 #pragma unroll
-    for (int nt = 0; nt < 4; ++nt) { dh_p[nt][0] = dh_p[nt][1] = db1_p[nt][0] = db1_p[nt][1] = 0.f; }
-    // dW_rv: (Hp8 / 16 rounded up) m-tiles x 4 n-tiles shared round-robin by the warps; dW_id: 2 m-tiles x 4 n-tiles
-    const int n_hm = (a.Hp8 + 15) / 16;
-    constexpr int MAX_WT = 4;                                  // m-tiles of dW_rv per warp (<= 256 / 16 / 5 rounded up)
-    float dwrv[MAX_WT][4][4];
-    float dwid[4][4];
+    for (int nt = 0; nt < 2; ++nt) { dh_p[nt][0] = dh_p[nt][1] = db1_p[nt][0] = db1_p[nt][1] = 0.f; }
+    // dW_rv: tasks (m-tile of 16 feature rows h, column half) shared round-robin by the warps; dW_id: 2 m-tiles x 2 halves
+    const int n_hm = (a.Hp8 + 15) / 16, n_tasks = 2 * n_hm;
+    constexpr int MAX_WT = 4;
+    float dwrv[MAX_WT][2][4];
+    float dwid[2][4];
 #pragma unroll
     for (int i = 0; i < MAX_WT; ++i)
 #pragma unroll
-        for (int nt = 0; nt < 4; ++nt)
+        for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
             for (int j = 0; j < 4; ++j) dwrv[i][nt][j] = 0.f;
 #pragma unroll
-    for (int nt = 0; nt < 4; ++nt)
+    for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
         for (int j = 0; j < 4; ++j) dwid[nt][j] = 0.f;
     const int rows_pad = a.NW * 16;
@@ -360,16 +372,16 @@ __global__ void __launch_bounds__(AT_MAXW * 32) narre_attn_tc_bwd_kernel(const A
         const int rows_live = n_s * a.R;
         __syncthreads();
         attn_stage_tile(a, sd, b0, n_s, Fs, Es, false);
-        zero_tile_padding(GO, a.PF, a.TS, n_s, a.H);
-        stage_rows_async(GO, a.PF, sd.out_grad + b0 * a.H, n_s, a.H);
+        stage_rows_async(GO, a.PF, a.TS, sd.out_grad + b0 * a.H, n_s, a.H);
         for (int i = threadIdx.x; i < rows_pad; i += blockDim.x) Ss[i] = i < rows_live ? __ldg(sd.scores + b0 * a.R + i) : 0.f;
         cp_async_wait_all_();
         __syncthreads();
         // ds[row] = out_grad[s] · feat[row] (+ scores_grad[row])
-        for (int r = warp; r < rows_live; r += a.NW) {
-            const int s = r / a.R;
+        for (int r = warp; r < rows_live; r += n_warps) {
+            const float* go = GO + (r / a.R) * a.PF;
+            const float* fr = Fs + r * a.PF;
             float p = 0.f;
-            for (int c = lane; c < a.H; c += 32) p = fmaf(GO[s * a.PF + c], Fs[r * a.PF + c], p);
+            for (int c = lane; c < a.H; c += 32) p = fmaf(go[c], fr[c], p);
             p = warp_sum(p);
             if (lane == 0) Ls[r] = p + (sd.scores_grad ? __ldg(sd.scores_grad + b0 * a.R + r) : 0.f);
         }
@@ -391,15 +403,15 @@ __global__ void __launch_bounds__(AT_MAXW * 32) narre_attn_tc_bwd_kernel(const A
         __syncthreads();
         // recompute hid; d hid = (hid > 0) * dl[row] * h[a]  → DHa (A operand) and DHb (B operand); dh, db1 partials
         {
-            float acc[4][4];
-            const int m0 = warp * 16;
-            attn_hidden_mma(Fs, a.PF, Es, a.PE, smem + L.wrv_hi, smem + L.wrv_lo, smem + L.wid_hi, smem + L.wid_lo, a.Hp8, m0, lane, acc);
+            float acc[2][4];
+            const int m0 = mt * 16;
+            attn_hidden_mma(Fs, a.PF, Es, a.PE, smem + L.wrv_hi, smem + L.wrv_lo, smem + L.wid_hi, smem + L.wid_lo, a.Hp8, m0, nh, lane, acc);
             const float dl0 = Ls[m0 + g], dl1 = Ls[m0 + g + 8];
 #pragma unroll
-            for (int nt = 0; nt < 4; ++nt)
+            for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
                 for (int j = 0; j < 2; ++j) {
-                    const int c = nt * 8 + 2 * t + j;
+                    const int c = (2 * nh + nt) * 8 + 2 * t + j;
                     const float h0 = fmaxf(acc[nt][j] + b1v[nt][j], 0.f), h1 = fmaxf(acc[nt][2 + j] + b1v[nt][j], 0.f);
                     dh_p[nt][j] = fmaf(dl0, h0, fmaf(dl1, h1, dh_p[nt][j]));
                     const float d0 = h0 > 0.f ? dl0 * hv[nt][j] : 0.f, d1 = h1 > 0.f ? dl1 * hv[nt][j] : 0.f;
@@ -411,9 +423,10 @@ __global__ void __launch_bounds__(AT_MAXW * 32) narre_attn_tc_bwd_kernel(const A
                 }
         }
         __syncthreads();
-        // ---- d feat[rows, H] = score[row] * out_grad[s] + DH · W_rvᵀ      (M = this warp's 16 rows, N = H, K = A)
+        // ---- d feat[rows, H] = score[row] * out_grad[s] + DH · W_rvᵀ      (M = the m-tile's 16 rows, N = H: the two warps of an
+        //      m-tile take alternate groups of 32 columns, K = A)
         {
-            const int m0 = warp * 16;
+            const int m0 = mt * 16;
             uint32_t ahi[4][4], alo[4][4];
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {
@@ -425,19 +438,22 @@ __global__ void __launch_bounds__(AT_MAXW * 32) narre_attn_tc_bwd_kernel(const A
             }
             const int r0 = m0 + g, r1 = m0 + g + 8;
             const float sc0 = Ss[r0], sc1 = Ss[r1];
-            const int s0 = r0 / a.R, s1 = r1 / a.R;
-            for (int hg = 0; hg < n_hgroups; ++hg) {
+            const float* go0 = GO + (r0 / a.R) * a.PF;
+            const float* go1 = GO + (r1 / a.R) * a.PF;
+            float* dst0 = sd.feat_grad + (b0 * a.R + r0) * a.H;
+            float* dst1 = sd.feat_grad + (b0 * a.R + r1) * a.H;
+            for (int hg = nh; hg < n_hgroups; hg += 2) {
                 float acc[4][4];
 #pragma unroll
                 for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
                     for (int i = 0; i < 4; ++i) acc[nt][i] = 0.f;
+                const float* bb = smem + L.wrvT_hi + t * pht + hg * 40 + g * 4;
+                const float* bl = smem + L.wrvT_lo + t * pht + hg * 40 + g * 4;
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks) {
-                    const float* bb = smem + L.wrvT_hi + (ks * 8 + t) * pht + hg * 40 + g * 4;
-                    const float* bl = smem + L.wrvT_lo + (ks * 8 + t) * pht + hg * 40 + g * 4;
-                    const float4 bh0 = *reinterpret_cast<const float4*>(bb), bh1 = *reinterpret_cast<const float4*>(bb + 4 * pht);
-                    const float4 bl0 = *reinterpret_cast<const float4*>(bl), bl1 = *reinterpret_cast<const float4*>(bl + 4 * pht);
+                    const float4 bh0 = *reinterpret_cast<const float4*>(bb + ks * 8 * pht), bh1 = *reinterpret_cast<const float4*>(bb + (ks * 8 + 4) * pht);
+                    const float4 bl0 = *reinterpret_cast<const float4*>(bl + ks * 8 * pht), bl1 = *reinterpret_cast<const float4*>(bl + (ks * 8 + 4) * pht);
                     mma_3x(acc[0], ahi[ks], alo[ks], __float_as_uint(bh0.x), __float_as_uint(bh1.x), __float_as_uint(bl0.x), __float_as_uint(bl1.x));
                     mma_3x(acc[1], ahi[ks], alo[ks], __float_as_uint(bh0.y), __float_as_uint(bh1.y), __float_as_uint(bl0.y), __float_as_uint(bl1.y));
                     mma_3x(acc[2], ahi[ks], alo[ks], __float_as_uint(bh0.z), __float_as_uint(bh1.z), __float_as_uint(bl0.z), __float_as_uint(bl1.z));
@@ -448,34 +464,32 @@ __global__ void __launch_bounds__(AT_MAXW * 32) narre_attn_tc_bwd_kernel(const A
                     const int c = hg * 32 + nt * 8 + 2 * t;
                     if (c < a.H) {                                    // H even or odd: the pair is written element-wise
                         if (r0 < rows_live) {
-                            float* dst = sd.feat_grad + (b0 * a.R + r0) * a.H + c;
-                            dst[0] = fmaf(sc0, GO[s0 * a.PF + c], acc[nt][0]);
-                            if (c + 1 < a.H) dst[1] = fmaf(sc0, GO[s0 * a.PF + c + 1], acc[nt][1]);
+                            dst0[c] = fmaf(sc0, go0[c], acc[nt][0]);
+                            if (c + 1 < a.H) dst0[c + 1] = fmaf(sc0, go0[c + 1], acc[nt][1]);
                         }
                         if (r1 < rows_live) {
-                            float* dst = sd.feat_grad + (b0 * a.R + r1) * a.H + c;
-                            dst[0] = fmaf(sc1, GO[s1 * a.PF + c], acc[nt][2]);
-                            if (c + 1 < a.H) dst[1] = fmaf(sc1, GO[s1 * a.PF + c + 1], acc[nt][3]);
+                            dst1[c] = fmaf(sc1, go1[c], acc[nt][2]);
+                            if (c + 1 < a.H) dst1[c + 1] = fmaf(sc1, go1[c + 1], acc[nt][3]);
                         }
                     }
                 }
             }
-            // ---- d e[rows, A] = DH · W_idᵀ  → id-embedding rows (atomics; padding row skipped)
-            float acc[4][4];
+            // ---- d e[rows, A] = DH · W_idᵀ  (this warp's 16 columns) → id-embedding rows (atomics; padding row skipped)
+            float acc[2][4];
 #pragma unroll
-            for (int nt = 0; nt < 4; ++nt)
+            for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
                 for (int i = 0; i < 4; ++i) acc[nt][i] = 0.f;
+            const float* bb = smem + L.widT_hi + t * pa + g * 4;
+            const float* bl = smem + L.widT_lo + t * pa + g * 4;
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {
-                const float* bb = smem + L.widT_hi + (ks * 8 + t) * pa + g * 4;
-                const float* bl = smem + L.widT_lo + (ks * 8 + t) * pa + g * 4;
-                const float4 bh0 = *reinterpret_cast<const float4*>(bb), bh1 = *reinterpret_cast<const float4*>(bb + 4 * pa);
-                const float4 bl0 = *reinterpret_cast<const float4*>(bl), bl1 = *reinterpret_cast<const float4*>(bl + 4 * pa);
-                mma_3x(acc[0], ahi[ks], alo[ks], __float_as_uint(bh0.x), __float_as_uint(bh1.x), __float_as_uint(bl0.x), __float_as_uint(bl1.x));
-                mma_3x(acc[1], ahi[ks], alo[ks], __float_as_uint(bh0.y), __float_as_uint(bh1.y), __float_as_uint(bl0.y), __float_as_uint(bl1.y));
-                mma_3x(acc[2], ahi[ks], alo[ks], __float_as_uint(bh0.z), __float_as_uint(bh1.z), __float_as_uint(bl0.z), __float_as_uint(bl1.z));
-                mma_3x(acc[3], ahi[ks], alo[ks], __float_as_uint(bh0.w), __float_as_uint(bh1.w), __float_as_uint(bl0.w), __float_as_uint(bl1.w));
+                const float4 bh0 = *reinterpret_cast<const float4*>(bb + ks * 8 * pa), bh1 = *reinterpret_cast<const float4*>(bb + (ks * 8 + 4) * pa);
+                const float4 bl0 = *reinterpret_cast<const float4*>(bl + ks * 8 * pa), bl1 = *reinterpret_cast<const float4*>(bl + (ks * 8 + 4) * pa);
+                mma_3x(acc[0], ahi[ks], alo[ks], __float_as_uint(sel0(bh0, nh)), __float_as_uint(sel0(bh1, nh)), __float_as_uint(sel0(bl0, nh)),
+                       __float_as_uint(sel0(bl1, nh)));
+                mma_3x(acc[1], ahi[ks], alo[ks], __float_as_uint(sel1(bh0, nh)), __float_as_uint(sel1(bh1, nh)), __float_as_uint(sel1(bl0, nh)),
+                       __float_as_uint(sel1(bl1, nh)));
             }
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
@@ -484,10 +498,10 @@ __global__ void __launch_bounds__(AT_MAXW * 32) narre_attn_tc_bwd_kernel(const A
                     const int64_t id = __ldg(sd.other_id + b0 * a.R + r);
                     if (id >= 0 && id < sd.n_ids && id != sd.padding_idx) {
 #pragma unroll
-                        for (int nt = 0; nt < 4; ++nt)
+                        for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
                             for (int j = 0; j < 2; ++j) {
-                                const int c = nt * 8 + 2 * t + j;
+                                const int c = (2 * nh + nt) * 8 + 2 * t + j;
                                 const float v = acc[nt][half * 2 + j];
                                 if (c < a.A && v != 0.f) atomicAdd(sd.ebd_grad + id * a.A + c, v);
                             }
@@ -497,81 +511,74 @@ __global__ void __launch_bounds__(AT_MAXW * 32) narre_attn_tc_bwd_kernel(const A
         }
         // ---- dW_rv[h, a] += featᵀ · DH   (M = h, N = A, K = rows);  dW_id[a2, a] += eᵀ · DH
         {
-            int slot = 0;
-            for (int hm = warp; hm < n_hm; hm += a.NW, ++slot) {
-                if (slot >= MAX_WT) break;
-                const int m0 = hm * 16;
-                for (int k0 = 0; k0 < rows_pad; k0 += 8) {
+#pragma unroll
+            for (int sl = 0; sl < MAX_WT; ++sl) {                     // static slot index: dwrv stays in registers
+                const int task = warp + sl * n_warps;
+                if (task >= n_tasks) break;
+                const int m0 = (task >> 1) * 16, th = task & 1;
+                const bool in0 = m0 + g < a.Hp8, in1 = m0 + g + 8 < a.Hp8;
+                const float* fa = Fs + t * a.PF + m0 + g;
+                const float* db = DHb + t * pa + g * 4;
+                for (int k0 = 0; k0 < rows_pad; k0 += 8, fa += 8 * a.PF, db += 8 * pa) {
                     // A[m = h][k = row] = F[row][h]   (transposed read of the feature tile)
                     uint32_t ahi[4], alo[4];
-                    const float* fa = Fs + (k0 + t) * a.PF + m0 + g;
-                    const bool in0 = m0 + g < a.Hp8, in1 = m0 + g + 8 < a.Hp8;
                     split_hi_lo(in0 ? fa[0] : 0.f, ahi[0], alo[0]);
                     split_hi_lo(in1 ? fa[8] : 0.f, ahi[1], alo[1]);
                     split_hi_lo(in0 ? fa[4 * a.PF] : 0.f, ahi[2], alo[2]);
                     split_hi_lo(in1 ? fa[4 * a.PF + 8] : 0.f, ahi[3], alo[3]);
-                    const float4 b0v = *reinterpret_cast<const float4*>(DHb + (k0 + t) * pa + g * 4);
-                    const float4 b1w = *reinterpret_cast<const float4*>(DHb + (k0 + t + 4) * pa + g * 4);
-                    uint32_t bh0[4], bl0[4], bh1[4], bl1[4];
-                    split_hi_lo(b0v.x, bh0[0], bl0[0]); split_hi_lo(b0v.y, bh0[1], bl0[1]);
-                    split_hi_lo(b0v.z, bh0[2], bl0[2]); split_hi_lo(b0v.w, bh0[3], bl0[3]);
-                    split_hi_lo(b1w.x, bh1[0], bl1[0]); split_hi_lo(b1w.y, bh1[1], bl1[1]);
-                    split_hi_lo(b1w.z, bh1[2], bl1[2]); split_hi_lo(b1w.w, bh1[3], bl1[3]);
+                    const float4 b0v = *reinterpret_cast<const float4*>(db);
+                    const float4 b1w = *reinterpret_cast<const float4*>(db + 4 * pa);
+                    uint32_t bh0[2], bl0[2], bh1[2], bl1[2];
+                    split_hi_lo(sel0(b0v, th), bh0[0], bl0[0]); split_hi_lo(sel1(b0v, th), bh0[1], bl0[1]);
+                    split_hi_lo(sel0(b1w, th), bh1[0], bl1[0]); split_hi_lo(sel1(b1w, th), bh1[1], bl1[1]);
 #pragma unroll
-                    for (int nt = 0; nt < 4; ++nt) {
-                        // `slot` is warp-uniform; the static unroll keeps dwrv in registers
-#pragma unroll
-                        for (int sl = 0; sl < MAX_WT; ++sl)
-                            if (sl == slot) mma_3x(dwrv[sl][nt], ahi, alo, bh0[nt], bh1[nt], bl0[nt], bl1[nt]);
-                    }
+                    for (int nt = 0; nt < 2; ++nt) mma_3x(dwrv[sl][nt], ahi, alo, bh0[nt], bh1[nt], bl0[nt], bl1[nt]);
                 }
             }
-            if (warp < 2) {                                           // dW_id: m-tile = warp (a2 rows 16 warp .. +15)
-                const int m0 = warp * 16;
-                for (int k0 = 0; k0 < rows_pad; k0 += 8) {
+            if (warp < 4) {                                           // dW_id: m-tile = warp >> 1 (a2 rows), column half = warp & 1
+                const int m0 = (warp >> 1) * 16, th = warp & 1;
+                const float* ea = Es + t * a.PE + m0 + g;
+                const float* db = DHb + t * pa + g * 4;
+                for (int k0 = 0; k0 < rows_pad; k0 += 8, ea += 8 * a.PE, db += 8 * pa) {
                     uint32_t ahi[4], alo[4];
-                    const float* ea = Es + (k0 + t) * a.PE + m0 + g;
                     split_hi_lo(ea[0], ahi[0], alo[0]);
                     split_hi_lo(ea[8], ahi[1], alo[1]);
                     split_hi_lo(ea[4 * a.PE], ahi[2], alo[2]);
                     split_hi_lo(ea[4 * a.PE + 8], ahi[3], alo[3]);
-                    const float4 b0v = *reinterpret_cast<const float4*>(DHb + (k0 + t) * pa + g * 4);
-                    const float4 b1w = *reinterpret_cast<const float4*>(DHb + (k0 + t + 4) * pa + g * 4);
-                    uint32_t bh0[4], bl0[4], bh1[4], bl1[4];
-                    split_hi_lo(b0v.x, bh0[0], bl0[0]); split_hi_lo(b0v.y, bh0[1], bl0[1]);
-                    split_hi_lo(b0v.z, bh0[2], bl0[2]); split_hi_lo(b0v.w, bh0[3], bl0[3]);
-                    split_hi_lo(b1w.x, bh1[0], bl1[0]); split_hi_lo(b1w.y, bh1[1], bl1[1]);
-                    split_hi_lo(b1w.z, bh1[2], bl1[2]); split_hi_lo(b1w.w, bh1[3], bl1[3]);
+                    const float4 b0v = *reinterpret_cast<const float4*>(db);
+                    const float4 b1w = *reinterpret_cast<const float4*>(db + 4 * pa);
+                    uint32_t bh0[2], bl0[2], bh1[2], bl1[2];
+                    split_hi_lo(sel0(b0v, th), bh0[0], bl0[0]); split_hi_lo(sel1(b0v, th), bh0[1], bl0[1]);
+                    split_hi_lo(sel0(b1w, th), bh1[0], bl1[0]); split_hi_lo(sel1(b1w, th), bh1[1], bl1[1]);
 #pragma unroll
-                    for (int nt = 0; nt < 4; ++nt) mma_3x(dwid[nt], ahi, alo, bh0[nt], bh1[nt], bl0[nt], bl1[nt]);
+                    for (int nt = 0; nt < 2; ++nt) mma_3x(dwid[nt], ahi, alo, bh0[nt], bh1[nt], bl0[nt], bl1[nt]);
                 }
             }
         }
     }
     // ---- flush the CTA's partial parameter gradients
     {
-        int slot = 0;
-        for (int hm = warp; hm < n_hm; hm += a.NW, ++slot) {
-            if (slot >= MAX_WT) break;
 #pragma unroll
-            for (int sl = 0; sl < MAX_WT; ++sl)
-                if (sl == slot) {
+        for (int sl = 0; sl < MAX_WT; ++sl) {
+            const int task = warp + sl * n_warps;
+            if (task >= n_tasks) break;
+            const int hm = task >> 1, th = task & 1;
 #pragma unroll
-                    for (int nt = 0; nt < 4; ++nt)
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const int hrow = hm * 16 + g + (j >> 1) * 8, c = nt * 8 + 2 * t + (j & 1);
-                            const float v = dwrv[sl][nt][j];
-                            if (hrow < a.H && c < a.A && v != 0.f) atomicAdd(sd.W_rv_grad + hrow * a.A + c, v);
-                        }
-                }
-        }
-        if (warp < 2) {
-#pragma unroll
-            for (int nt = 0; nt < 4; ++nt)
+            for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const int arow = warp * 16 + g + (j >> 1) * 8, c = nt * 8 + 2 * t + (j & 1);
+                    const int hrow = hm * 16 + g + (j >> 1) * 8, c = (2 * th + nt) * 8 + 2 * t + (j & 1);
+                    const float v = dwrv[sl][nt][j];
+                    if (hrow < a.H && c < a.A && v != 0.f) atomicAdd(sd.W_rv_grad + hrow * a.A + c, v);
+                }
+        }
+        if (warp < 4) {
+            const int th = warp & 1;
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int arow = (warp >> 1) * 16 + g + (j >> 1) * 8, c = (2 * th + nt) * 8 + 2 * t + (j & 1);
                     const float v = dwid[nt][j];
                     if (arow < a.A && c < a.A && v != 0.f) atomicAdd(sd.W_id_grad + arow * a.A + c, v);
                 }
@@ -583,14 +590,14 @@ __global__ void __launch_bounds__(AT_MAXW * 32) narre_attn_tc_bwd_kernel(const A
     if (threadIdx.x == 0) red[64] = 0.f;
     __syncthreads();
 #pragma unroll
-    for (int nt = 0; nt < 4; ++nt)
+    for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
             float vh = dh_p[nt][j], vb = db1_p[nt][j];
 #pragma unroll
             for (int o = 4; o < 32; o <<= 1) { vh += __shfl_xor_sync(0xffffffffu, vh, o); vb += __shfl_xor_sync(0xffffffffu, vb, o); }
             if (g == 0) {
-                const int c = nt * 8 + 2 * t + j;
+                const int c = (2 * nh + nt) * 8 + 2 * t + j;
                 atomicAdd(red + c, vh);
                 atomicAdd(red + 32 + c, vb);
             }
@@ -671,7 +678,7 @@ extern "C" int rbr_narre_attn_pair_fwd(int n_sides, const float* const* feat, co
     const int64_t per_side = (2 * 148) / n_sides / (smem > 112 * 1024 ? 2 : 1);   // persistent CTAs: all co-resident
     int64_t gx = n_tiles < per_side ? n_tiles : per_side;
     dim3 grid((unsigned)gx, (unsigned)n_sides);
-    narre_attn_tc_fwd_kernel<<<grid, a.NW * 32, smem, as_stream(stream)>>>(a);
+    narre_attn_tc_fwd_kernel<<<grid, 2 * a.NW * 32, smem, as_stream(stream)>>>(a);
     RBR_LAUNCH_CHECK("narre_attn_tc_fwd_kernel");
     return RBR_OK;
 }
@@ -711,7 +718,7 @@ extern "C" int rbr_narre_attn_pair_bwd(int n_sides, const float* const* feat, co
     const int64_t per_side = 148 / n_sides;                           // one CTA per SM (232 registers per thread), all co-resident
     int64_t gx = n_tiles < per_side ? n_tiles : per_side;
     dim3 grid((unsigned)gx, (unsigned)n_sides);
-    narre_attn_tc_bwd_kernel<<<grid, a.NW * 32, smem, as_stream(stream)>>>(a);
+    narre_attn_tc_bwd_kernel<<<grid, 2 * a.NW * 32, smem, as_stream(stream)>>>(a);
     RBR_LAUNCH_CHECK("narre_attn_tc_bwd_kernel");
     return RBR_OK;
 }
