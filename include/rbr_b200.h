@@ -160,6 +160,18 @@ int rbr_conv_bwd_cmat_finish(int what, const void* shadow_bf16, const void* pack
                              int64_t ksize, int64_t padding_idx, float* table_grad, float* weight_grad, void* ws,
                              int64_t ws_bytes, void* stream);
 
+/* ---- K8: the alternate encoder arch="HierPooling" ---------------------------------------------------------------------
+ * Replaces HierPooling.forward (models/deepconn/layers.py:81-98: F.avg_pool1d(kernel k, stride 1) over time, then F.max_pool1d
+ * over the whole pooled length) applied to the masked, transposed embeddings (NgramFeat.forward, layers.py:131-133), together
+ * with the embedding gather: pooled[n,e] = max_t mean_{j<k} x[n,t+j,e], argmax = the FIRST window start attaining it.  The
+ * optional Linear(E → out) and the ReLU that follow stay library ops.  Backward: table_grad[ids[n,t*+j], e] += grad[n,e] / k
+ * for the k rows of the arg-max window (mask true, id != padding_idx).  1 <= k <= 8.                                   */
+int rbr_hier_pool_fwd(const float* table, int64_t vocab, int64_t emb, const void* ids, const uint8_t* mask, int64_t n_docs,
+                      int64_t doc_len, int64_t ksize, float* pooled, int32_t* argmax, int flags, void* stream);
+int rbr_hier_pool_bwd(const void* ids, const uint8_t* mask, int64_t n_docs, int64_t doc_len, int64_t vocab, int64_t emb,
+                      int64_t ksize, int64_t padding_idx, const int32_t* argmax, const float* pooled_grad, float* table_grad,
+                      int flags, void* stream);
+
 /* ---- K3: fused NARRE review-level attention --------------------------------------------------------
  * Replaces LinearAttention.forward, models/narre/narre.py:40-64 (dropout excluded: applied by the caller).
  *   feat [B,R,H], other_id [B,R] int64, W_rv [H,A], W_id [A,A], h [A], b_1 [A], b_2 [1], ebd_vals [n_ids, A]

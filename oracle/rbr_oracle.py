@@ -159,6 +159,25 @@ def ngram_feat(x: Tensor, mask: Optional[Tensor], conv_weights: Sequence[Tensor]
     return feat
 
 
+def hier_pooling(x: Tensor, mask: Optional[Tensor], kernel_size: int, proj_w: Optional[Tensor] = None,
+                 proj_b: Optional[Tensor] = None) -> Tensor:
+    """NgramFeat.forward with arch="HierPooling" (layers.py:110-114, 123-136; HierPooling.forward :81-98):
+    mask → avg_pool1d(kernel, stride 1) over time → max over time (first arg-max) → [Linear] → ReLU.  x [N,L,E] → [N,out]."""
+    if mask is not None:
+        x = mask_rows(x, mask)
+    n, l, e = x.shape
+    lout = l - kernel_size + 1
+    y = torch.zeros(n, lout, e, dtype=x.dtype, device=x.device)
+    for j in range(kernel_size):
+        y = y + x[:, j:j + lout]
+    y = y / kernel_size
+    idx = (y == y.max(dim=1, keepdim=True).values).to(torch.uint8).argmax(dim=1)
+    v = torch.gather(y, 1, idx.unsqueeze(1)).squeeze(1)
+    if proj_w is not None:
+        v = v @ proj_w.t() + proj_b
+    return torch.relu(v)
+
+
 # --------------------------------------------------------------------------------------
 # a6: LinearAttention  (models/narre/narre.py:26-64)
 # --------------------------------------------------------------------------------------
@@ -219,7 +238,7 @@ def _conv_params(p: Params, prefix: str) -> Tuple[List[Tensor], List[Tensor]]:
 
 def deepconn_forward(p: Params, u_revs: Tensor, i_revs: Tensor, u_masks: Tensor, i_masks: Tensor, u_ids: Tensor,
                      i_ids: Tensor, return_aux: bool = False, fm_drop_mask: Optional[Tensor] = None,
-                     argmax_override: Optional[Tuple[Tensor, Tensor]] = None):
+                     argmax_override: Optional[Tuple[Tensor, Tensor]] = None, hier_kernel: Optional[int] = None):
     """DeepCoNNpp.forward, deepconn.py:28-53.  Embedding + conv weights are SHARED between the
     user and the item side (deepconn.py:20-22, 43-47)."""
     table = p["word_embeddings.embedding.weight"]
@@ -227,8 +246,13 @@ def deepconn_forward(p: Params, u_revs: Tensor, i_revs: Tensor, u_masks: Tensor,
     u_x = embedding_gather(table, u_revs)                                        # deepconn.py:43
     i_x = embedding_gather(table, i_revs)                                        # deepconn.py:44
     ao = argmax_override or (None, None)
-    u_rev, u_arg = ngram_feat(u_x, u_masks, ws, bs, return_argmax=True, argmax_override=ao[0])   # deepconn.py:46
-    i_rev, i_arg = ngram_feat(i_x, i_masks, ws, bs, return_argmax=True, argmax_override=ao[1])   # deepconn.py:47
+    if hier_kernel is not None:                                                  # arch="HierPooling" (layers.py:110-114)
+        pw, pb = p.get("ngram.feature_layer.0.proj_layer.weight"), p.get("ngram.feature_layer.0.proj_layer.bias")
+        u_rev, i_rev = hier_pooling(u_x, u_masks, hier_kernel, pw, pb), hier_pooling(i_x, i_masks, hier_kernel, pw, pb)
+        u_arg = i_arg = None
+    else:
+        u_rev, u_arg = ngram_feat(u_x, u_masks, ws, bs, return_argmax=True, argmax_override=ao[0])   # deepconn.py:46
+        i_rev, i_arg = ngram_feat(i_x, i_masks, ws, bs, return_argmax=True, argmax_override=ao[1])   # deepconn.py:47
     u_f = last_feat(u_rev, u_ids, p["user_feat.W"], p["user_feat.b"], p["user_feat.ebd.weight"])   # :48
     i_f = last_feat(i_rev, i_ids, p["item_feat.W"], p["item_feat.b"], p["item_feat.ebd.weight"])   # :49
     pred = fm_head(u_f, i_f, u_ids, i_ids, p["fm.h"], p["fm.g_bias"], p["fm.user_bias.weight"],

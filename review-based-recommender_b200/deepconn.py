@@ -38,7 +38,8 @@ class DeepCoNNpp(HotPathModule):
         after every optimizer step in training (parameter version counters change).  bench.py calls this every
         step so that the operand staging kernels are inside the timed region."""
         self.word_embeddings.invalidate_operand_cache()
-        self.ngram.conv.invalidate_operand_cache()
+        if hasattr(self.ngram.conv, "invalidate_operand_cache"):           # (arch="HierPooling" has no conv weights to re-pack)
+            self.ngram.conv.invalidate_operand_cache()
 
     def forward(self, u_revs, i_revs, u_rev_masks, i_rev_masks, u_ids, i_ids):
         """u_revs/i_revs [bz, doc_len] int64 (or int32: the staged input pipeline), masks [bz, doc_len] bool (None: derived on

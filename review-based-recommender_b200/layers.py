@@ -139,6 +139,20 @@ class MyConv1d(nn.Module):
                            "call NgramFeat (conv + ReLU + max-over-time fused)")
 
 
+class HierPooling(nn.Module):
+    """Holder of the optional projection of the reference's HierPooling (models/deepconn/layers.py:62-98): avg-pool with the
+    given kernel (stride 1) then max-pool over time run in K8 (ops.HierPoolFn) fused with the embedding gather; the
+    Linear(in → out), present only when the sizes differ, is a library GEMM."""
+
+    def __init__(self, in_features, out_features, kernel_size):
+        super().__init__()
+        self.kernel_size = kernel_size
+        self.proj_layer = nn.Linear(in_features, out_features) if in_features != out_features else None
+
+    def forward(self, inputs):
+        raise RuntimeError("rbr_b200.HierPooling is a parameter holder: call NgramFeat (gather + avg-pool + max-pool fused)")
+
+
 class NgramFeat(nn.Module):
     def __init__(self, kernel_sizes, in_features, out_features, seq_len, dropout=0., arch="CNN", precision=None):
         super().__init__()
@@ -147,7 +161,10 @@ class NgramFeat(nn.Module):
             self.feature_layer = nn.Sequential(MyConv1d(kernel_sizes, in_features, out_features), nn.ReLU(),
                                                nn.MaxPool1d(seq_len))
         elif arch == "HierPooling":
-            raise NotImplementedError("rbr_b200: arch='HierPooling' is outside the accelerated hot path (SURVEY.md §2)")
+            if type(kernel_sizes) is str:
+                kernel_sizes = [int(x) for x in kernel_sizes.split(",")]
+            assert len(kernel_sizes) == 1                           # layers.py:112
+            self.feature_layer = nn.Sequential(HierPooling(in_features, out_features, kernel_sizes[0]), nn.ReLU())
         else:
             raise ValueError(f"{arch} is not predefined.")
         self.seq_len = seq_len
@@ -159,13 +176,24 @@ class NgramFeat(nn.Module):
         self.conv_flags = 0             # ops.CONV_* kernel-selection flags passed with every call (tests, A/B timing)
 
     @property
-    def conv(self) -> MyConv1d:
+    def conv(self):
         return self.feature_layer[0]
+
+    def _hier(self, table, table_param, ids, mask, padding_idx, mask_from_ids):
+        hp = self.feature_layer[0]
+        pooled = ops.HierPoolFn.apply(table, ids, mask, hp.kernel_size, padding_idx, self._arena, table_param, mask_from_ids)
+        if hp.proj_layer is not None:
+            pooled = hp.proj_layer(pooled)
+        return torch.relu(pooled)
 
     def encode(self, word_embeddings: WordEmbedding, sides: Sequence[torch.Tensor],
                masks: Sequence[Optional[torch.Tensor]], return_argmax: bool = False) -> List[torch.Tensor]:
         """Fused path used by the models: token ids → pooled features, [n_docs, H] per side (with return_argmax: followed by
         the int32 [n_docs, H] first-arg-max positions per side)."""
+        if self.arch == "HierPooling":
+            table = word_embeddings.embedding.weight
+            pidx = -1 if word_embeddings.padding_idx is None else word_embeddings.padding_idx
+            return [self._hier(table, table, ids, m, pidx, True) for ids, m in zip(sides, masks)]
         conv = self.conv
         convs = list(conv.list_of_conv1d)
         table = word_embeddings.embedding.weight
@@ -206,6 +234,8 @@ class NgramFeat(nn.Module):
         bz, seq_len, emb = inputs.shape
         x = inputs.contiguous().view(bz * seq_len, emb)
         ids = torch.arange(bz * seq_len, device=inputs.device, dtype=torch.int64).view(bz, seq_len)
+        if self.arch == "HierPooling":
+            return self._hier(x, x, ids, input_masks, -1, False)        # [bz, out_features], as the reference returns it
         conv = self.conv
         convs = list(conv.list_of_conv1d)
         cfg = {

@@ -46,7 +46,8 @@ class NARRE(HotPathModule):
         after every optimizer step in training (parameter version counters change).  bench.py calls this every
         step so that the operand staging kernels are inside the timed region."""
         self.word_embeddings.invalidate_operand_cache()
-        self.ngram.conv.invalidate_operand_cache()
+        if hasattr(self.ngram.conv, "invalidate_operand_cache"):           # (arch="HierPooling" has no conv weights to re-pack)
+            self.ngram.conv.invalidate_operand_cache()
 
     def _encode_attend(self, u_text, i_text, u_text_masks, i_text_masks, reuid, reiid):
         bz = u_text.shape[0]

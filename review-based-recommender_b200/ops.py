@@ -441,6 +441,43 @@ def _cmat_workspace(table: torch.Tensor, conv_index: int, vocab: int, emb: int, 
     return ws
 
 
+class HierPoolFn(torch.autograd.Function):
+    """pooled = max_t mean_{j<k} mask(table[ids])[t+j]  per document and embedding channel — HierPooling.forward
+    (reference models/deepconn/layers.py:81-98) on the masked embeddings (layers.py:131-133).  → [n_docs, E]."""
+
+    @staticmethod
+    def forward(ctx, table, ids, mask, ksize, padding_idx, arena, table_param, mask_from_ids):
+        _stream(refresh=True)
+        table = _req(table, torch.float32, "embedding table")
+        ids = _ids(ids, "token ids")
+        mask = _mask_u8(mask, "token mask")
+        flags = _id_flags(ids, mask, mask_from_ids)
+        doc_len = ids.shape[-1]
+        n_docs = ids.numel() // doc_len
+        vocab, emb = table.shape
+        pooled = torch.empty(n_docs, emb, dtype=torch.float32, device=table.device)
+        amax = torch.empty(n_docs, emb, dtype=torch.int32, device=table.device)
+        lib.check(lib.rbr_hier_pool_fwd(_p(table), vocab, emb, _p(ids), _p(mask), n_docs, doc_len, ksize, _p(pooled), _p(amax), flags,
+                                        _stream()), "rbr_hier_pool_fwd")
+        ctx.save_for_backward(ids, amax, *([mask] if mask is not None else []))
+        ctx.meta = (vocab, emb, ksize, -1 if padding_idx is None else padding_idx, flags, arena, table_param, mask is not None)
+        return pooled
+
+    @staticmethod
+    def backward(ctx, g):
+        _stream(refresh=True)
+        vocab, emb, ksize, pad, flags, arena, table_param, has_mask = ctx.meta
+        ids, amax = ctx.saved_tensors[:2]
+        mask = ctx.saved_tensors[2] if has_mask else None
+        if not ctx.needs_input_grad[0]:
+            return (None,) * 8
+        g_table = _grad_buf(arena, table_param, True)
+        doc_len = ids.shape[-1]
+        lib.check(lib.rbr_hier_pool_bwd(_p(ids), _p(mask), ids.numel() // doc_len, doc_len, vocab, emb, ksize, pad, _p(amax),
+                                        _p(g.contiguous()), _p(g_table), flags, _stream()), "rbr_hier_pool_bwd")
+        return (g_table, None, None, None, None, None, None, None)
+
+
 # ---------------------------------------------------------------------------------------------------
 # K3: NARRE attention
 # ---------------------------------------------------------------------------------------------------

@@ -151,6 +151,19 @@ def deepconn_params(users: int, items: int, vocab: int, emb: int, hidden: int, l
     return p
 
 
+def deepconn_hier_params(users: int, items: int, vocab: int, emb: int, hidden: int, latent: int, seed: int = 0):
+    """DeepCoNNpp(arch="HierPooling"): no conv weights; a Linear(emb → hidden) projection when the sizes differ
+    (models/deepconn/layers.py:72-76)."""
+    g = _gen(seed)
+    p: Dict[str, torch.Tensor] = {"word_embeddings.embedding.weight": _embedding_init(g, vocab, emb)}
+    if emb != hidden:
+        b = 1.0 / emb ** 0.5
+        p["ngram.feature_layer.0.proj_layer.weight"] = _uniform(g, (hidden, emb), b)
+        p["ngram.feature_layer.0.proj_layer.bias"] = _uniform(g, (hidden,), b)
+    _head_params(g, p, users, items, hidden, latent)
+    return p
+
+
 def narre_params(users: int, items: int, vocab: int, emb: int, hidden: int, att: int, latent: int,
                  kernel_sizes=(3,), seed: int = 0) -> Dict[str, torch.Tensor]:
     g = _gen(seed)

@@ -93,6 +93,16 @@ def deepconn_case(name, B, L, V, U, I, E, H, K, ks, seed, tweak=None):
           dict(model="deepconn", B=B, L=L, V=V, U=U, I=I, E=E, H=H, K=K, ks=list(ks)))
 
 
+def deepconn_hier_case(name, B, L, V, U, I, E, H, K, k, seed):
+    """DeepCoNNpp(arch="HierPooling") — the reference's alternate encoder (models/deepconn/layers.py:62-98, 110-114)."""
+    params = synth.deepconn_hier_params(U, I, V, E, H, K, seed=seed)
+    batch, ratings = synth.deepconn_batch(B, L, V, U, I, seed=synth.SEED_BASE + seed)
+    batch = list(batch)
+    model = DeepCoNNpp(U, I, V, [k], E, H, K, L, None, 0.0, arch="HierPooling")
+    outs = _run(model, params, batch, ratings)
+    _save(name, model, params, batch, ratings, outs, dict(model="deepconn_hier", B=B, L=L, V=V, U=U, I=I, E=E, H=H, K=K, k=k))
+
+
 def narre_case(name, B, R, T, V, U, I, E, H, A, K, seed):
     params = synth.narre_params(U, I, V, E, H, A, K, (3,), seed=seed)
     batch, ratings = synth.narre_batch(B, R, T, V, U, I, seed=synth.SEED_BASE + seed)
@@ -151,6 +161,8 @@ if __name__ == "__main__":
     deepconn_case("deepconn_edge", B=4, L=16, V=40, U=9, I=7, E=10, H=6, K=5, ks=(3,), seed=2, tweak=edge_tweak)
     deepconn_case("deepconn_multik", B=3, L=18, V=50, U=6, I=6, E=9, H=12, K=4, ks=(3, 5), seed=3)
     deepconn_case("deepconn_odd", B=5, L=37, V=80, U=11, I=13, E=20, H=10, K=7, ks=(3,), seed=4)
+    deepconn_hier_case("deepconn_hier", B=5, L=24, V=70, U=9, I=7, E=12, H=8, K=6, k=3, seed=8)
+    deepconn_hier_case("deepconn_hier_noproj", B=4, L=17, V=50, U=6, I=5, E=8, H=8, K=4, k=5, seed=9)
     narre_case("narre_small", B=3, R=4, T=10, V=60, U=9, I=7, E=12, H=8, A=5, K=6, seed=5)
     narre_case("narre_h150ish", B=2, R=5, T=12, V=70, U=8, I=9, E=16, H=15, A=6, K=4, seed=6)
     dual_att_case("dual_att_small", B=3, L=16, V=50, E=10, lw=5, lo=8, go=6, h1=20, h2=5, seed=7)

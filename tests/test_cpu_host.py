@@ -49,6 +49,10 @@ def test_state_dict_keys_match_reference_goldens():
     assert set(model.state_dict()) == set(n.params)
     with pytest.raises(ValueError):
         rbr_b200.layers.NgramFeat([3], 8, 8, 10, arch="nope")
+    h = Golden("deepconn_hier")
+    m = h.meta
+    model = rbr_b200.DeepCoNNpp(m["U"], m["I"], m["V"], [m["k"]], m["E"], m["H"], m["K"], m["L"], None, 0.0, arch="HierPooling")
+    assert set(model.state_dict()) == set(h.params)                  # incl. ngram.feature_layer.0.proj_layer.{weight,bias}
     with pytest.raises(AssertionError):
         rbr_b200.layers.MyConv1d([2], 8, 8)              # even kernel sizes are rejected, layers.py:39
 

@@ -233,7 +233,7 @@ def test_two_pass_backward_with_table_hook_matches_single_pass():
     assert rel_err(seen["table"].cpu(), g.grads["word_embeddings.embedding.weight"]) < FP32_GRAD_TOL
 
 
-@pytest.mark.parametrize("shape", [(33, 10, 150, 32), (7, 4, 8, 5), (5, 5, 15, 6), (100, 6, 100, 16), (3, 1, 40, 8), (70, 17, 64, 32),
+@pytest.mark.parametrize("shape", [(33, 10, 150, 32), (7, 4, 8, 5), (5, 5, 15, 6), (100, 6, 100, 16), (3, 2, 40, 8), (70, 17, 64, 32),
                                    (4096, 10, 150, 32)])
 def test_attention_pair_tensor_core_kernels_vs_oracle(shape):
     """K3 on tensor cores (csrc/attn_tc.cu, 3xTF32 mma.sync, both sides in one launch): outputs, scores and every gradient
@@ -280,3 +280,52 @@ def test_attention_pair_tensor_core_kernels_vs_oracle(shape):
             floor = float(B * R) ** 0.5 * 0.1 if name == "b_2" else 1e-6      # (R = 1: softmax of one review, gradients ~1e-8)
             assert rel_err(cu[s][2][j].grad.cpu(), ref[s][3][j], floor) < FP32_GRAD_TOL, (s, name)
         assert float(cu[s][2][5].grad[0].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("case", ["deepconn_hier", "deepconn_hier_noproj"])
+def test_golden_hier_pooling_fp32(case):
+    """DeepCoNNpp(arch="HierPooling") — K8 (gather + avg-pool + max-pool fused) against the reference's numbers."""
+    g = Golden(case)
+    m = g.meta
+    model = rbr_b200.DeepCoNNpp(m["U"], m["I"], m["V"], [m["k"]], m["E"], m["H"], m["K"], m["L"], None, 0.0, arch="HierPooling")
+    assert set(model.state_dict()) == set(g.params)
+    model.load_state_dict(g.params)
+    model.cuda()
+    out, loss, grads = run_step(model, g.batch, g.ratings)
+    assert rel_err(out.detach().cpu(), g.out["pred"]) < FP32_TOL
+    assert rel_err(loss, g.out["loss"]) < FP32_TOL
+    for k, ref in g.grads.items():
+        assert rel_err(grads[k], ref) < FP32_GRAD_TOL, k
+    assert float(grads["word_embeddings.embedding.weight"][0].abs().max()) == 0.0
+
+
+def test_hier_pooling_midsize_and_standalone_vs_oracle():
+    B, L, V, U, I, E, H, K, k = 16, 500, 3000, 50, 40, 300, 100, 32, 3
+    params = synth.deepconn_hier_params(U, I, V, E, H, K, seed=1)
+    batch, ratings = synth.deepconn_batch(B, L, V, U, I, seed=123)
+    model = rbr_b200.DeepCoNNpp(U, I, V, [k], E, H, K, L, None, 0.0, arch="HierPooling")
+    model.load_state_dict(params)
+    model.cuda()
+    out, loss, grads = run_step(model, batch, ratings)
+    rp, rl, rg = orc.loss_and_grads("deepconn", params, batch, ratings, hier_kernel=k)
+    assert rel_err(out.detach().cpu(), rp) < FP32_TOL and rel_err(loss, rl) < FP32_TOL
+    for kk in rg:
+        assert rel_err(grads[kk], rg[kk]) < FP32_GRAD_TOL, kk
+    # int32 ids + derived masks give the same bits
+    with torch.no_grad():
+        b = [t.cuda() for t in batch]
+        assert torch.equal(model(b[0].int(), b[1].int(), None, None, b[4], b[5]), model(*b))
+    # reference-signature NgramFeat.forward on dense inputs (odd width → scalar kernel path), gradient w.r.t. the inputs
+    gen = torch.Generator().manual_seed(4)
+    x = torch.randn(5, 21, 10, generator=gen)
+    mask = torch.rand(5, 21, generator=gen) > 0.2
+    layer = rbr_b200.layers.NgramFeat([5], 10, 10, 21, arch="HierPooling").cuda()
+    xg = x.cuda().requires_grad_(True)
+    y = layer(xg, mask.cuda())
+    xo = x.clone().requires_grad_(True)
+    ref = orc.hier_pooling(xo, mask, 5)
+    assert y.shape == (5, 10) and rel_err(y.detach().cpu(), ref.detach()) < FP32_TOL
+    go = torch.randn(5, 10, generator=gen)
+    y.backward(go.cuda())
+    ref.backward(go)
+    assert rel_err(xg.grad.cpu(), xo.grad) < FP32_GRAD_TOL

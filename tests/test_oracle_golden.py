@@ -1,5 +1,6 @@
 """Pins the CPU oracle (oracle/rbr_oracle.py) to outputs of the unmodified reference modules
 (tests/golden/*.npz, written by tests/golden/make_golden.py in the build container)."""
+import pytest
 import torch
 
 from conftest import Golden, grad_floor, rel_err
@@ -87,3 +88,15 @@ def test_vendored_reference_is_byte_identical_and_agrees_with_the_oracle():
     assert rel_err(pred.detach(), rp) < 1e-6 and rel_err(loss.detach(), rl) < 1e-6
     for k, p in ref.named_parameters():
         assert rel_err(p.grad, rg[k]) < 1e-5, k
+
+
+@pytest.mark.parametrize("case", ["deepconn_hier", "deepconn_hier_noproj"])
+def test_oracle_hier_pooling_matches_reference_golden(case):
+    """arch="HierPooling" (models/deepconn/layers.py:62-98, 110-114): the oracle's avg-pool → max-pool → [Linear] → ReLU
+    against the numbers the unmodified reference produced (with and without the projection)."""
+    g = Golden(case)
+    rp, rl, rg = orc.loss_and_grads("deepconn", g.params, g.batch, g.ratings, hier_kernel=g.meta["k"])
+    assert rel_err(rp, g.out["pred"]) < 1e-5 and rel_err(rl, g.out["loss"]) < 1e-5
+    assert set(rg) == set(g.grads)
+    for k, ref in g.grads.items():
+        assert rel_err(rg[k], ref) < 1e-5, k
