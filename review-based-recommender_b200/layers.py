@@ -179,12 +179,19 @@ class NgramFeat(nn.Module):
     def conv(self):
         return self.feature_layer[0]
 
-    def _hier(self, table, table_param, ids, mask, padding_idx, mask_from_ids):
+    def _hier(self, table, sides, masks, padding_idx, mask_from_ids):
         hp = self.feature_layer[0]
-        pooled = ops.HierPoolFn.apply(table, ids, mask, hp.kernel_size, padding_idx, self._arena, table_param, mask_from_ids)
-        if hp.proj_layer is not None:
-            pooled = hp.proj_layer(pooled)
-        return torch.relu(pooled)
+        cfg = {"ksize": hp.kernel_size, "padding_idx": padding_idx, "arena": self._arena, "table_param": table,
+               "mask_from_ids": mask_from_ids}
+        flat = []
+        for ids, m in zip(sides, masks):
+            flat += [ids, m]
+        outs = []
+        for pooled in ops.HierPoolFn.apply(table, cfg, *flat):
+            if hp.proj_layer is not None:
+                pooled = hp.proj_layer(pooled)
+            outs.append(torch.relu(pooled))
+        return outs
 
     def encode(self, word_embeddings: WordEmbedding, sides: Sequence[torch.Tensor],
                masks: Sequence[Optional[torch.Tensor]], return_argmax: bool = False) -> List[torch.Tensor]:
@@ -193,7 +200,7 @@ class NgramFeat(nn.Module):
         if self.arch == "HierPooling":
             table = word_embeddings.embedding.weight
             pidx = -1 if word_embeddings.padding_idx is None else word_embeddings.padding_idx
-            return [self._hier(table, table, ids, m, pidx, True) for ids, m in zip(sides, masks)]
+            return self._hier(table, sides, masks, pidx, True)
         conv = self.conv
         convs = list(conv.list_of_conv1d)
         table = word_embeddings.embedding.weight
@@ -235,7 +242,7 @@ class NgramFeat(nn.Module):
         x = inputs.contiguous().view(bz * seq_len, emb)
         ids = torch.arange(bz * seq_len, device=inputs.device, dtype=torch.int64).view(bz, seq_len)
         if self.arch == "HierPooling":
-            return self._hier(x, x, ids, input_masks, -1, False)        # [bz, out_features], as the reference returns it
+            return self._hier(x, [ids], [input_masks], -1, False)[0]     # [bz, out_features], as the reference returns it
         conv = self.conv
         convs = list(conv.list_of_conv1d)
         cfg = {

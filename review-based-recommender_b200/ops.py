@@ -442,40 +442,54 @@ def _cmat_workspace(table: torch.Tensor, conv_index: int, vocab: int, emb: int, 
 
 
 class HierPoolFn(torch.autograd.Function):
-    """pooled = max_t mean_{j<k} mask(table[ids])[t+j]  per document and embedding channel — HierPooling.forward
-    (reference models/deepconn/layers.py:81-98) on the masked embeddings (layers.py:131-133).  → [n_docs, E]."""
+    """pooled[s] = max_t mean_{j<k} mask(table[ids[s]])[t+j]  per document and embedding channel, for every side s —
+    HierPooling.forward (reference models/deepconn/layers.py:81-98) on the masked embeddings (layers.py:131-133).
+    All sides go through ONE autograd node: they share the table, whose gradient buffer is accumulated into by every side and
+    handed to autograd once.  Inputs after (table, cfg): per side (ids, mask-or-None).  → [n_docs, E] per side."""
 
     @staticmethod
-    def forward(ctx, table, ids, mask, ksize, padding_idx, arena, table_param, mask_from_ids):
+    def forward(ctx, table, cfg, *flat):
         _stream(refresh=True)
         table = _req(table, torch.float32, "embedding table")
-        ids = _ids(ids, "token ids")
-        mask = _mask_u8(mask, "token mask")
-        flags = _id_flags(ids, mask, mask_from_ids)
-        doc_len = ids.shape[-1]
-        n_docs = ids.numel() // doc_len
         vocab, emb = table.shape
-        pooled = torch.empty(n_docs, emb, dtype=torch.float32, device=table.device)
-        amax = torch.empty(n_docs, emb, dtype=torch.int32, device=table.device)
-        lib.check(lib.rbr_hier_pool_fwd(_p(table), vocab, emb, _p(ids), _p(mask), n_docs, doc_len, ksize, _p(pooled), _p(amax), flags,
-                                        _stream()), "rbr_hier_pool_fwd")
-        ctx.save_for_backward(ids, amax, *([mask] if mask is not None else []))
-        ctx.meta = (vocab, emb, ksize, -1 if padding_idx is None else padding_idx, flags, arena, table_param, mask is not None)
-        return pooled
+        ids_l = [_ids(t, "token ids") for t in flat[0::2]]
+        mask_l = [_mask_u8(m, "token mask") for m in flat[1::2]]
+        flags_l = [_id_flags(i, m, bool(cfg.get("mask_from_ids", False))) for i, m in zip(ids_l, mask_l)]
+        outs, amaxes = [], []
+        for ids, mask, fl in zip(ids_l, mask_l, flags_l):
+            doc_len = ids.shape[-1]
+            n_docs = ids.numel() // doc_len
+            pooled = torch.empty(n_docs, emb, dtype=torch.float32, device=table.device)
+            amax = torch.empty(n_docs, emb, dtype=torch.int32, device=table.device)
+            lib.check(lib.rbr_hier_pool_fwd(_p(table), vocab, emb, _p(ids), _p(mask), n_docs, doc_len, cfg["ksize"], _p(pooled), _p(amax),
+                                            fl, _stream()), "rbr_hier_pool_fwd")
+            outs.append(pooled)
+            amaxes.append(amax)
+        ctx.save_for_backward(*ids_l, *amaxes, *[m for m in mask_l if m is not None])
+        ctx.cfg, ctx.flags_l, ctx.mask_present, ctx.shape = cfg, flags_l, [m is not None for m in mask_l], (vocab, emb)
+        return tuple(outs)
 
     @staticmethod
-    def backward(ctx, g):
+    def backward(ctx, *grads):
         _stream(refresh=True)
-        vocab, emb, ksize, pad, flags, arena, table_param, has_mask = ctx.meta
-        ids, amax = ctx.saved_tensors[:2]
-        mask = ctx.saved_tensors[2] if has_mask else None
+        cfg = ctx.cfg
+        ns = len(ctx.flags_l)
+        vocab, emb = ctx.shape
         if not ctx.needs_input_grad[0]:
-            return (None,) * 8
-        g_table = _grad_buf(arena, table_param, True)
-        doc_len = ids.shape[-1]
-        lib.check(lib.rbr_hier_pool_bwd(_p(ids), _p(mask), ids.numel() // doc_len, doc_len, vocab, emb, ksize, pad, _p(amax),
-                                        _p(g.contiguous()), _p(g_table), flags, _stream()), "rbr_hier_pool_bwd")
-        return (g_table, None, None, None, None, None, None, None)
+            return (None,) * (2 + 2 * ns)
+        saved = ctx.saved_tensors
+        ids_l, amaxes, masks = saved[:ns], saved[ns:2 * ns], list(saved[2 * ns:])
+        g_table = _grad_buf(cfg.get("arena"), cfg["table_param"], True)
+        for s in range(ns):
+            mask = masks.pop(0) if ctx.mask_present[s] else None
+            if grads[s] is None:
+                continue
+            ids = ids_l[s]
+            doc_len = ids.shape[-1]
+            lib.check(lib.rbr_hier_pool_bwd(_p(ids), _p(mask), ids.numel() // doc_len, doc_len, vocab, emb, cfg["ksize"], cfg["padding_idx"],
+                                            _p(amaxes[s]), _p(grads[s].contiguous()), _p(g_table), ctx.flags_l[s], _stream()),
+                      "rbr_hier_pool_bwd")
+        return (g_table, None, *([None] * (2 * ns)))
 
 
 # ---------------------------------------------------------------------------------------------------
