@@ -172,6 +172,15 @@ int rbr_hier_pool_bwd(const void* ids, const uint8_t* mask, int64_t n_docs, int6
                       int64_t ksize, int64_t padding_idx, const int32_t* argmax, const float* pooled_grad, float* table_grad,
                       int flags, void* stream);
 
+/* ---- K9: SimpleSiamese's masked average pooling fused with the embedding gather ------------------------------------------
+ * Replaces word_embedding → transpose → MaskedAvgPooling1d.forward (models/simple_siamese/layers.py:90-110, called at
+ * simple_siamese.py:59-64): out[n,:] = sum_t mask[n,t] * table[ids[n,t],:] / (sum_t mask[n,t] + 1e-8).
+ * Backward: table_grad[ids[n,t],:] += mask[n,t] * out_grad[n,:] / (len + 1e-8), padding row skipped.  emb % 4 == 0.     */
+int rbr_masked_avg_pool_fwd(const float* table, int64_t vocab, int64_t emb, const void* ids, const uint8_t* mask, int64_t n_docs,
+                            int64_t doc_len, float* out, int flags, void* stream);
+int rbr_masked_avg_pool_bwd(const void* ids, const uint8_t* mask, int64_t n_docs, int64_t doc_len, int64_t vocab, int64_t emb,
+                            int64_t padding_idx, const float* out_grad, float* table_grad, int flags, void* stream);
+
 /* ---- K3: fused NARRE review-level attention --------------------------------------------------------
  * Replaces LinearAttention.forward, models/narre/narre.py:40-64 (dropout excluded: applied by the caller).
  *   feat [B,R,H], other_id [B,R] int64, W_rv [H,A], W_id [A,A], h [A], b_1 [A], b_2 [1], ebd_vals [n_ids, A]

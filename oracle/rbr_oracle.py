@@ -342,10 +342,42 @@ def dual_att_forward(p: Params, u_docs: Tensor, i_docs: Tensor, return_aux: bool
 
 
 # --------------------------------------------------------------------------------------
+# SimpleSiamese  (models/simple_siamese/simple_siamese.py:38-88, layers.py:90-110, 171-197)
+# --------------------------------------------------------------------------------------
+def masked_avg_pool(x: Tensor, mask: Tensor) -> Tensor:
+    """MaskedAvgPooling1d (simple_siamese/layers.py:94-110) in token-major layout: x [N,T,E], mask [N,T] → [N,E]."""
+    m = mask.to(x.dtype).unsqueeze(-1)
+    return (x * m).sum(dim=1) / (m.sum(dim=1) + 1e-8)
+
+
+def simple_siamese_forward(p: Params, u_revs: Tensor, i_revs: Tensor, u_wm: Tensor, i_wm: Tensor, u_rm: Tensor, i_rm: Tensor,
+                           u_ids: Tensor, i_ids: Tensor) -> Tensor:
+    """SimpleSiamese.forward with every dropout at 0 / eval (simple_siamese.py:55-88)."""
+    table = p["word_embedding.embedding.weight"]
+    b, r, t = u_revs.shape
+
+    def side(revs, wm, rm):
+        pooled = masked_avg_pool(embedding_gather(table, revs).view(-1, t, table.shape[1]), wm.reshape(-1, t)).view(revs.shape[0], revs.shape[1], -1)
+        if "latent_transform_layer.0.weight" in p:
+            pooled = torch.tanh(pooled @ p["latent_transform_layer.0.weight"].t() + p["latent_transform_layer.0.bias"])
+        hid = torch.tanh(pooled @ p["review_att_layer.proj_layer.0.weight"].t() + p["review_att_layer.proj_layer.0.bias"])
+        logits = hid @ p["review_att_layer.inner_product.weight"].t()
+        logits = torch.where(rm.unsqueeze(2), logits, torch.full((), -1e8, dtype=logits.dtype, device=logits.device))
+        return (torch.softmax(logits, dim=1) * pooled).sum(dim=1)
+
+    u_f = last_feat(side(u_revs, u_wm, u_rm), u_ids, p["user_last_feat_layer.W"], p["user_last_feat_layer.b"], p["user_last_feat_layer.ebd.weight"])
+    i_f = last_feat(side(i_revs, i_wm, i_rm), i_ids, p["item_last_feat_layer.W"], p["item_last_feat_layer.b"], p["item_last_feat_layer.ebd.weight"])
+    if "fm.user_bias.weight" in p:
+        return fm_head(u_f, i_f, u_ids, i_ids, p["fm.h"], p["fm.g_bias"], p["fm.user_bias.weight"], p["fm.item_bias.weight"]).view(-1)
+    return (torch.relu(u_f * i_f) @ p["fm.h"] + p["fm.g_bias"]).view(-1)
+
+
+# --------------------------------------------------------------------------------------
 # loss + all parameter gradients (what `loss.backward()` leaves in `.grad`,
 # trainer/train_deepconn_pp.py:161-165)
 # --------------------------------------------------------------------------------------
-_PADDED_TABLES = ("word_embeddings.embedding.weight", "user_feat.ebd.weight", "item_feat.ebd.weight",
+_PADDED_TABLES = ("word_embeddings.embedding.weight", "word_embedding.embedding.weight", "user_last_feat_layer.ebd.weight",
+                  "item_last_feat_layer.ebd.weight", "user_feat.ebd.weight", "item_feat.ebd.weight",
                   "fm.user_bias.weight", "fm.item_bias.weight", "user_att.ebd_vals.weight",
                   "item_att.ebd_vals.weight")
 
@@ -364,6 +396,8 @@ def loss_and_grads(model: str, p: Params, batch: Sequence[Tensor], ratings: Tens
         pred = narre_forward(leaves, *batch, **fwd_kw)[0]
     elif model == "dual_att":
         pred = dual_att_forward(leaves, *batch)
+    elif model == "simple_siamese":
+        pred = simple_siamese_forward(leaves, *batch)
     else:
         raise ValueError(model)
     loss = mse_loss(pred, ratings)

@@ -18,10 +18,13 @@ def __getattr__(name):          # lazy: model classes import torch.nn and the na
     if name == "NARRE":
         from .narre import NARRE
         return NARRE
+    if name == "SimpleSiamese":
+        from .simple_siamese import SimpleSiamese
+        return SimpleSiamese
     if name == "DualAtt":
         from .dual_att import DualAtt
         return DualAtt
-    if name in ("layers", "ops", "parallel", "graphs", "deepconn", "narre", "dual_att", "_lib", "staging", "optim", "inference"):
+    if name in ("layers", "ops", "parallel", "graphs", "deepconn", "narre", "dual_att", "_lib", "staging", "optim", "inference", "simple_siamese"):
         import importlib
         return importlib.import_module(f"{__name__}.{name}")
     raise AttributeError(name)

@@ -45,6 +45,7 @@ int oob_consume_head(cudaStream_t, unsigned int*);
 int oob_consume_attn(cudaStream_t, unsigned int*);
 int oob_consume_attn_tc(cudaStream_t, unsigned int*);
 int oob_consume_hierpool(cudaStream_t, unsigned int*);
+int oob_consume_avgpool(cudaStream_t, unsigned int*);
 int oob_consume_datt(cudaStream_t, unsigned int*);
 
 }  // namespace rbr
@@ -61,7 +62,7 @@ extern "C" int rbr_consume_oob_count(void* stream) {
     cudaStream_t s = as_stream(stream);
     unsigned long long total = 0;
     int (*const fns[])(cudaStream_t, unsigned int*) = {oob_consume_embed, oob_consume_conv_fp32, oob_consume_conv_tc, oob_consume_conv_tc2,
-                                                       oob_consume_head, oob_consume_attn, oob_consume_attn_tc, oob_consume_hierpool, oob_consume_datt};
+                                                       oob_consume_head, oob_consume_attn, oob_consume_attn_tc, oob_consume_hierpool, oob_consume_avgpool, oob_consume_datt};
     for (auto fn : fns) {
         unsigned int h = 0;
         if (fn(s, &h) != RBR_OK) return cuda_fail(cudaGetLastError(), "rbr_consume_oob_count");

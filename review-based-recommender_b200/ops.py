@@ -492,6 +492,54 @@ class HierPoolFn(torch.autograd.Function):
         return (g_table, None, *([None] * (2 * ns)))
 
 
+class MaskedAvgPoolFn(torch.autograd.Function):
+    """out[s][n, :] = sum_t mask * table[ids[s][n, t]] / (sum_t mask + 1e-8) for every side s (K9) — the SimpleSiamese encoder
+    (reference models/simple_siamese/layers.py:90-110 on the gathered embeddings).  One autograd node for all sides (shared
+    table gradient).  Inputs after (table, cfg): per side (ids [n_docs, T], mask-or-None)."""
+
+    @staticmethod
+    def forward(ctx, table, cfg, *flat):
+        _stream(refresh=True)
+        table = _req(table, torch.float32, "embedding table")
+        vocab, emb = table.shape
+        ids_l = [_ids(t, "token ids") for t in flat[0::2]]
+        mask_l = [_mask_u8(m, "token mask") for m in flat[1::2]]
+        flags_l = [_id_flags(i, m, bool(cfg.get("mask_from_ids", False))) for i, m in zip(ids_l, mask_l)]
+        outs = []
+        for ids, mask, fl in zip(ids_l, mask_l, flags_l):
+            doc_len = ids.shape[-1]
+            n_docs = ids.numel() // doc_len
+            out = torch.empty(n_docs, emb, dtype=torch.float32, device=table.device)
+            lib.check(lib.rbr_masked_avg_pool_fwd(_p(table), vocab, emb, _p(ids), _p(mask), n_docs, doc_len, _p(out), fl, _stream()),
+                      "rbr_masked_avg_pool_fwd")
+            outs.append(out)
+        ctx.save_for_backward(*ids_l, *[m for m in mask_l if m is not None])
+        ctx.cfg, ctx.flags_l, ctx.mask_present, ctx.shape = cfg, flags_l, [m is not None for m in mask_l], (vocab, emb)
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        _stream(refresh=True)
+        cfg = ctx.cfg
+        ns = len(ctx.flags_l)
+        vocab, emb = ctx.shape
+        if not ctx.needs_input_grad[0]:
+            return (None,) * (2 + 2 * ns)
+        saved = ctx.saved_tensors
+        ids_l, masks = saved[:ns], list(saved[ns:])
+        g_table = _grad_buf(cfg.get("arena"), cfg["table_param"], True)
+        for s in range(ns):
+            mask = masks.pop(0) if ctx.mask_present[s] else None
+            if grads[s] is None:
+                continue
+            ids = ids_l[s]
+            doc_len = ids.shape[-1]
+            lib.check(lib.rbr_masked_avg_pool_bwd(_p(ids), _p(mask), ids.numel() // doc_len, doc_len, vocab, emb, cfg["padding_idx"],
+                                                  _p(grads[s].contiguous()), _p(g_table), ctx.flags_l[s], _stream()),
+                      "rbr_masked_avg_pool_bwd")
+        return (g_table, None, *([None] * (2 * ns)))
+
+
 # ---------------------------------------------------------------------------------------------------
 # K3: NARRE attention
 # ---------------------------------------------------------------------------------------------------

@@ -196,3 +196,35 @@ def dual_att_params(vocab: int, doc_len: int, l_window: int = 5, l_out: int = 20
     b3 = 1.0 / hidden1 ** 0.5
     p["fc.3.weight"], p["fc.3.bias"] = _uniform(g, (hidden2, hidden1), b3), _uniform(g, (hidden2,), b3)
     return p
+
+
+def simple_siamese_params(users: int, items: int, vocab: int, emb: int, latent: int, use_ui_bias: bool = True,
+                          latent_transform: bool = False, seed: int = 0) -> Dict[str, torch.Tensor]:
+    """Parameter set of the reference's SimpleSiamese (models/simple_siamese/simple_siamese.py:9-36), keyed by its state_dict."""
+    g = _gen(seed)
+    p: Dict[str, torch.Tensor] = {"word_embedding.embedding.weight": _embedding_init(g, vocab, emb)}
+    feat = latent if latent_transform else emb
+    if latent_transform:
+        b = 1.0 / emb ** 0.5
+        p["latent_transform_layer.0.weight"], p["latent_transform_layer.0.bias"] = _uniform(g, (latent, emb), b), _uniform(g, (latent,), b)
+    for side, size in (("user", users), ("item", items)):
+        p[f"{side}_last_feat_layer.W"] = _uniform(g, (feat, latent), 0.1)
+        p[f"{side}_last_feat_layer.b"] = torch.full((latent,), 0.1)
+        p[f"{side}_last_feat_layer.ebd.weight"] = _uniform(g, (size, latent), 0.1)
+    b = 1.0 / feat ** 0.5
+    p["review_att_layer.proj_layer.0.weight"], p["review_att_layer.proj_layer.0.bias"] = _uniform(g, (latent, feat), b), _uniform(g, (latent,), b)
+    p["review_att_layer.inner_product.weight"] = _uniform(g, (1, latent), 1.0 / latent ** 0.5)
+    p["fm.h"] = _uniform(g, (latent, 1), 0.1)
+    p["fm.g_bias"] = torch.full((1,), 4.0)
+    if use_ui_bias:
+        p["fm.user_bias.weight"] = _uniform(g, (users, 1), 0.1)
+        p["fm.item_bias.weight"] = _uniform(g, (items, 1), 0.1)
+    return p
+
+
+def simple_siamese_batch(batch: int, reviews: int, rev_len: int, vocab: int, users: int, items: int, seed: int = SEED_BASE):
+    """(u_revs, i_revs, u_word_masks, i_word_masks, u_rev_masks, i_rev_masks, u_ids, i_ids), ratings
+    (trainer/train_simple_siamese.py collate): NARRE-shaped review tensors plus review-level masks (a review is real when it
+    has at least one token, models/simple_siamese/utils.py get_rev_mask)."""
+    (u_text, i_text, u_m, i_m, u_id, i_id, _, _), ratings = narre_batch(batch, reviews, rev_len, vocab, users, items, seed)
+    return (u_text, i_text, u_m, i_m, u_m.any(dim=-1), i_m.any(dim=-1), u_id, i_id), ratings

@@ -35,6 +35,7 @@ from rbr_b200 import synth  # noqa: E402
 from models.deepconn.deepconn import DeepCoNNpp  # noqa: E402
 from models.narre.narre import NARRE  # noqa: E402
 from models.dual_att.dual_att import DualAtt  # noqa: E402
+from models.simple_siamese.simple_siamese import SimpleSiamese  # noqa: E402
 
 torch.set_num_threads(1)
 torch.use_deterministic_algorithms(True)
@@ -103,6 +104,22 @@ def deepconn_hier_case(name, B, L, V, U, I, E, H, K, k, seed):
     _save(name, model, params, batch, ratings, outs, dict(model="deepconn_hier", B=B, L=L, V=V, U=U, I=I, E=E, H=H, K=K, k=k))
 
 
+def simple_siamese_case(name, B, R, T, V, U, I, E, K, use_ui_bias, latent_transform, seed):
+    """The reference's SimpleSiamese (models/simple_siamese/simple_siamese.py) with every dropout at 0."""
+    params = synth.simple_siamese_params(U, I, V, E, K, use_ui_bias, latent_transform, seed=seed)
+    batch, ratings = synth.simple_siamese_batch(B, R, T, V, U, I, seed=synth.SEED_BASE + seed)
+    model = SimpleSiamese(E, K, V, U, I, None, False, 0.0, 0.0, 0.0, use_ui_bias, latent_transform)
+    sd = model.state_dict()
+    assert set(sd) == set(params), (set(sd) ^ set(params))
+    model.load_state_dict(params)
+    model.train()
+    pred, _, _ = model(*batch)
+    loss = torch.nn.MSELoss()(pred, ratings)
+    loss.backward()
+    _save(name, model, params, batch, ratings, {"pred": pred, "loss": loss},
+          dict(model="simple_siamese", B=B, R=R, T=T, V=V, U=U, I=I, E=E, K=K, ui=int(use_ui_bias), lt=int(latent_transform)))
+
+
 def narre_case(name, B, R, T, V, U, I, E, H, A, K, seed):
     params = synth.narre_params(U, I, V, E, H, A, K, (3,), seed=seed)
     batch, ratings = synth.narre_batch(B, R, T, V, U, I, seed=synth.SEED_BASE + seed)
@@ -163,6 +180,8 @@ if __name__ == "__main__":
     deepconn_case("deepconn_odd", B=5, L=37, V=80, U=11, I=13, E=20, H=10, K=7, ks=(3,), seed=4)
     deepconn_hier_case("deepconn_hier", B=5, L=24, V=70, U=9, I=7, E=12, H=8, K=6, k=3, seed=8)
     deepconn_hier_case("deepconn_hier_noproj", B=4, L=17, V=50, U=6, I=5, E=8, H=8, K=4, k=5, seed=9)
+    simple_siamese_case("simple_siamese_small", B=4, R=5, T=11, V=60, U=9, I=7, E=12, K=6, use_ui_bias=True, latent_transform=False, seed=10)
+    simple_siamese_case("simple_siamese_lt", B=3, R=4, T=9, V=50, U=6, I=8, E=8, K=5, use_ui_bias=False, latent_transform=True, seed=11)
     narre_case("narre_small", B=3, R=4, T=10, V=60, U=9, I=7, E=12, H=8, A=5, K=6, seed=5)
     narre_case("narre_h150ish", B=2, R=5, T=12, V=70, U=8, I=9, E=16, H=15, A=6, K=4, seed=6)
     dual_att_case("dual_att_small", B=3, L=16, V=50, E=10, lw=5, lo=8, go=6, h1=20, h2=5, seed=7)

@@ -329,3 +329,38 @@ def test_hier_pooling_midsize_and_standalone_vs_oracle():
     y.backward(go.cuda())
     ref.backward(go)
     assert rel_err(xg.grad.cpu(), xo.grad) < FP32_GRAD_TOL
+
+
+@pytest.mark.parametrize("case", ["simple_siamese_small", "simple_siamese_lt"])
+def test_golden_simple_siamese(case):
+    """the SimpleSiamese drop-in (K9 masked average pooling fused with the gather + the fused head) against the
+    reference's own numbers: pred, loss and every parameter gradient."""
+    g = Golden(case)
+    m = g.meta
+    model = rbr_b200.SimpleSiamese(m["E"], m["K"], m["V"], m["U"], m["I"], None, False, 0.0, 0.0, 0.0, bool(m["ui"]), bool(m["lt"]))
+    assert set(model.state_dict()) == set(g.params)
+    model.load_state_dict(g.params)
+    model.cuda()
+    out, loss, grads = run_step(model, g.batch, g.ratings)
+    assert rel_err(out[0].detach().cpu(), g.out["pred"]) < FP32_TOL
+    assert rel_err(loss, g.out["loss"]) < FP32_TOL
+    for k, ref in g.grads.items():
+        assert rel_err(grads[k], ref, 1e-9) < FP32_GRAD_TOL, k
+    assert float(grads["word_embedding.embedding.weight"][0].abs().max()) == 0.0
+
+
+def test_simple_siamese_midsize_vs_oracle():
+    B, R, T, V, U, I, E, K = 48, 10, 60, 3000, 50, 40, 300, 32
+    params = synth.simple_siamese_params(U, I, V, E, K, True, False, seed=1)
+    batch, ratings = synth.simple_siamese_batch(B, R, T, V, U, I, seed=123)
+    model = rbr_b200.SimpleSiamese(E, K, V, U, I, None, False, 0.0, 0.0, 0.0, True, False)
+    model.load_state_dict(params)
+    model.cuda()
+    out, loss, grads = run_step(model, batch, ratings)
+    rp, rl, rg = orc.loss_and_grads("simple_siamese", params, batch, ratings)
+    assert rel_err(out[0].detach().cpu(), rp) < FP32_TOL and rel_err(loss, rl) < FP32_TOL
+    for k in rg:
+        assert rel_err(grads[k], rg[k], 1e-9) < FP32_GRAD_TOL, k
+    with torch.no_grad():                                    # int32 ids + derived word masks: same bits
+        b = [t.cuda() for t in batch]
+        assert torch.equal(model(b[0].int(), b[1].int(), None, None, *b[4:])[0], model(*b)[0])

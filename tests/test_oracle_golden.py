@@ -100,3 +100,15 @@ def test_oracle_hier_pooling_matches_reference_golden(case):
     assert set(rg) == set(g.grads)
     for k, ref in g.grads.items():
         assert rel_err(rg[k], ref) < 1e-5, k
+
+
+@pytest.mark.parametrize("case", ["simple_siamese_small", "simple_siamese_lt"])
+def test_oracle_simple_siamese_matches_reference_golden(case):
+    """SimpleSiamese (models/simple_siamese/simple_siamese.py:55-88): masked average pooling + additive review attention +
+    LastFeat + FM, with and without user/item biases and the latent transform."""
+    g = Golden(case)
+    rp, rl, rg = orc.loss_and_grads("simple_siamese", g.params, g.batch, g.ratings)
+    assert rel_err(rp, g.out["pred"]) < 1e-5 and rel_err(rl, g.out["loss"]) < 1e-5
+    assert set(rg) == set(g.grads)
+    for k, ref in g.grads.items():
+        assert rel_err(rg[k], ref, 1e-9) < 1e-5, k
