@@ -749,6 +749,13 @@ class HeadLossFn(torch.autograd.Function):
         return (g_ut, g_it, None, None, None, *grads, None, None, None, None, None, None)
 
 
+def head_supported(hidden: int, latent: int) -> bool:
+    """Whether the fused head kernels (K4) take this shape: both LastFeat weights, their CTA-partial gradients and a 32-sample
+    tile must fit shared memory (csrc/head.cu)."""
+    bwd = (2 * hidden * (latent + 1) + 2 * hidden * latent + 2 * 32 * hidden + 2 * 32 * latent) * 4
+    return latent <= 128 and bwd <= 200 * 1024
+
+
 def head_dropout_mask(batch: int, latent: int, drop_p: float, drop_seed: int, seed_dev: Optional[torch.Tensor],
                       device=None) -> torch.Tensor:
     """The FM dropout keep-scale [B, K] (values 0 or 1/(1-p)) the head kernels apply for this (p, seed, device counter) — a

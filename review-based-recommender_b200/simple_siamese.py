@@ -108,9 +108,11 @@ class SimpleSiamese(HotPathModule):
         u, i = self.review_dropout(u), self.review_dropout(i)
         u_feat, _ = self.review_att_layer(u, u_rev_masks)
         i_feat, _ = self.review_att_layer(i, i_rev_masks)
-        if self.use_ui_bias:
+        if self.use_ui_bias and ops.head_supported(u_feat.shape[1], self.fm.h.shape[0]):
             out = fused_head(self.user_last_feat_layer, self.item_last_feat_layer, self.fm, u_feat.contiguous(), i_feat.contiguous(),
                              u_ids, i_ids, self.training, arena)
+        elif self.use_ui_bias:                   # feature width beyond the fused head's shared-memory budget: the layers' own forwards
+            out = self.fm(self.user_last_feat_layer(u_feat, u_ids), self.item_last_feat_layer(i_feat, i_ids), u_ids, i_ids)
         else:
             out = self.fm(self.user_last_feat_layer(u_feat, u_ids), self.item_last_feat_layer(i_feat, i_ids))
         self._after_forward()
