@@ -99,7 +99,12 @@ int rbr_conv_pack(const float* weight, int64_t emb, int64_t filters, int64_t ksi
  *         the pooled value before bias and activation, gate included (gate * conv_nobias(x) at the arg-max;
  *         needed by the backward of a gated conv).
  *   ids   int64 (torch.LongTensor) or, with RBR_IDS_I32 in `flags`, int32; RBR_MASK_FROM_IDS: see above.
- *   RBR_PREC_BF16 shapes outside both tensor-core kernels fall back to the fp32 kernel when `table` is given. */
+ *   RBR_PREC_BF16 shapes outside both tensor-core kernels fall back to the fp32 kernel when `table` is given.
+ *   ws / ws_bytes: optional scratch of rbr_conv_fwd_workspace_bytes(n_docs) bytes (NULL: none).  With it, short-document
+ *   batches (NARRE pads every user / item to 10 reviews: all-padding "documents") are first scanned for documents without
+ *   any unmasked token; those get act(bias) / arg-max 0 directly — exactly what the conv over their all-zero rows yields —
+ *   and only the others are tiled onto the tensor cores.                                                               */
+int64_t rbr_conv_fwd_workspace_bytes(int64_t n_docs);
 /* Tiling plan of the CTA-pair kernel for a shape (host-only, launches nothing; used by the CPU tests of the tiling logic):
  * out[0..15] = {available, passes, filters/pass, filters/CTA, 64-wide K blocks, K steps, gather4 groups per stage, stage bytes,
  * ring stages, resident weight bytes per CTA, short-document mode, documents per tile, document row stride, tiles per document,
@@ -110,7 +115,7 @@ int rbr_conv_act_maxpool_fwd(int precision, int activation, const void* table, c
                              const float* gate, int gate_mode, int64_t n_docs, int64_t doc_len,
                              const void* packed, const float* bias, int64_t filters, int64_t ksize,
                              int64_t pad, float* feat, int32_t* argmax, float* pool_raw, int64_t feat_ld,
-                             int flags, void* stream);
+                             void* ws, int64_t ws_bytes, int flags, void* stream);
 
 /* ---- K2b: arg-max-sparse backward of K2 ------------------------------------------------------------
  * Replaces aten::convolution_backward + max_pool1d backward + relu backward + masked_fill backward +

@@ -35,7 +35,9 @@ int conv_tc_dispatch(const __nv_bfloat16* shadow, int64_t vocab, int E, IdView i
 
 int conv_tc2_dispatch(const __nv_bfloat16* shadow, int64_t vocab, int E, IdView ids, const uint8_t* mask,
                       const float* gate, int gate_mode, int64_t n_docs, int L, const __nv_bfloat16* umma_w2, const float* bias,
-                      int H, int K, int pad, int act, float* feat, int32_t* argmax, float* preact, int feat_ld, cudaStream_t s);
+                      int H, int K, int pad, int act, float* feat, int32_t* argmax, float* preact, int feat_ld, void* ws, int64_t ws_bytes,
+                      cudaStream_t s);
+int64_t conv_tc2_select_bytes(int64_t n_docs);
 
 int oob_consume_embed(cudaStream_t, unsigned int*);
 int oob_consume_conv_fp32(cudaStream_t, unsigned int*);
@@ -51,6 +53,8 @@ int oob_consume_datt(cudaStream_t, unsigned int*);
 }  // namespace rbr
 
 using namespace rbr;
+
+extern "C" int64_t rbr_conv_fwd_workspace_bytes(int64_t n_docs) { return conv_tc2_select_bytes(n_docs); }
 
 extern "C" int rbr_version(void) { return 100; }   // 0.1.0
 
@@ -75,7 +79,7 @@ extern "C" int rbr_conv_act_maxpool_fwd(int precision, int activation, const voi
                                         int64_t vocab, int64_t emb, const void* ids_raw, const uint8_t* mask, const float* gate,
                                         int gate_mode, int64_t n_docs, int64_t doc_len, const void* packed, const float* bias,
                                         int64_t filters, int64_t ksize, int64_t pad, float* feat, int32_t* argmax,
-                                        float* preact, int64_t feat_ld, int flags, void* stream) {
+                                        float* preact, int64_t feat_ld, void* ws, int64_t ws_bytes, int flags, void* stream) {
     const IdView ids = id_view(ids_raw, flags);
     RBR_REQUIRE(ids_raw && packed && bias && feat && argmax, RBR_EINVAL, "conv_fwd: null pointer");
     RBR_REQUIRE(n_docs >= 0 && doc_len > 0 && filters > 0 && ksize > 0 && emb > 0 && vocab > 0 && pad >= 0, RBR_EINVAL,
@@ -104,7 +108,7 @@ extern "C" int rbr_conv_act_maxpool_fwd(int precision, int activation, const voi
             const int rc2 = conv_tc2_dispatch(reinterpret_cast<const __nv_bfloat16*>(shadow_bf16), vocab, (int)emb, ids, mask, gate,
                                               gate_mode, n_docs, (int)doc_len,
                                               reinterpret_cast<const __nv_bfloat16*>(pk + pl.off_umma2), bias, (int)filters,
-                                              (int)ksize, (int)pad, activation, feat, argmax, preact, (int)feat_ld, s);
+                                              (int)ksize, (int)pad, activation, feat, argmax, preact, (int)feat_ld, ws, ws_bytes, s);
             if (rc2 != RBR_EUNSUPPORTED) return rc2;
         }
         RBR_REQUIRE(!pair_only, RBR_EUNSUPPORTED, "conv_fwd[bf16]: shape outside the CTA-pair variant");

@@ -93,29 +93,37 @@ struct Tc2Args {
     const float* gate;
     int gate_mode;
     int feat_ld;
+    // optional document selection (conv_doc_select_kernel): live[0] = number of documents with at least one unmasked token,
+    // live[1 + i] = their indices.  The kernel then tiles only those; the all-padding documents (NARRE pads every user / item
+    // to 10 reviews: ~45 % of the "documents" are empty) were given act(bias) / arg-max 0 by the selection pass.
+    const int32_t* live;
     Tc2Plan p;
 };
 
+// list slot li (unit * D + slot) → document index
+__device__ __forceinline__ int64_t t2_doc_of(const int32_t* live, int64_t li) { return live ? (int64_t)__ldg(live + 1 + li) : li; }
+
 // row r of the staged tile → (document, input position), or false = "reads as zeros"
-__device__ __forceinline__ bool t2_row_source(const Tc2Plan& p, int64_t unit, int tt, int r, int64_t n_docs, int64_t* doc, int* t_in) {
-    if (r >= p.rows || unit >= p.n_units) return false;
-    int64_t d;
+__device__ __forceinline__ bool t2_row_source(const Tc2Plan& p, int64_t n_units, int64_t n_live, const int32_t* live, int64_t unit, int tt,
+                                              int r, int64_t* doc, int* t_in) {
+    if (r >= p.rows || unit >= n_units) return false;
+    int64_t li;
     int ext;
     if (p.mode_b) {
         const int q = r / p.S;
         if (q >= p.D) return false;
-        d = unit * p.D + q;
+        li = unit * p.D + q;
         ext = r - q * p.S;
         if (ext >= p.Lext) return false;
     } else {
-        d = unit;
+        li = unit;
         ext = tt * T2_M + r;
         if (ext >= p.Lext) return false;
     }
-    if (d >= n_docs) return false;
+    if (li >= n_live) return false;
     const int t = ext - p.pad;
     if (t < 0 || t >= p.L) return false;
-    *doc = d;
+    *doc = t2_doc_of(live, li);
     *t_in = t;
     return true;
 }
@@ -150,7 +158,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const Tc2Args a) {
     const int h0 = pass * p.Nb;
     // units this CTA owns: ci, ci + ctas_per_pass, ...; the pair runs as many tiles as its even CTA (never fewer than the odd one)
     const int ci_even = ci & ~1;
-    const int64_t pair_units = (p.n_units > ci_even) ? (p.n_units - ci_even + ctas_per_pass - 1) / ctas_per_pass : 0;
+    const int64_t n_live = a.live ? (int64_t)__ldg(a.live) : a.n_docs;
+    const int64_t n_units = p.mode_b ? (n_live + p.D - 1) / p.D : n_live;
+    const int64_t pair_units = (n_units > ci_even) ? (n_units - ci_even + ctas_per_pass - 1) / ctas_per_pass : 0;
     const int64_t pair_tiles = pair_units * p.tpu;
 
     if (threadIdx.x == 0) {
@@ -250,7 +260,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const Tc2Args a) {
                 const int r = (i == 0) ? pw * ROWS_PW + lane : T2_M + lane;
                 int64_t doc;
                 int t;
-                if (t2_row_source(p, unit, tt, r, a.n_docs, &doc, &t)) {
+                if (t2_row_source(p, n_units, n_live, a.live, unit, tt, r, &doc, &t)) {
                     id_next[i] = ld_id(a.ids, doc * p.L + t);
                     ok_next[i] = ld_mask(a.ids, a.mask, doc * p.L + t, id_next[i]) ? (uint8_t)1 : (uint8_t)0;
                 }
@@ -330,10 +340,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const Tc2Args a) {
             // mode B packs documents on 32-row (warp) boundaries: a warp's rows all belong to one document slot
             const int slot = p.mode_b ? (quad * 32) / p.S : 0;
             const int t = p.mode_b ? m - slot * p.S : tt * T2_M + m;
-            const int64_t my_doc = p.mode_b ? unit * p.D + slot : unit;
-            const bool valid = (t < p.Lout) && (slot < p.D) && (unit < p.n_units) && (my_doc < a.n_docs);
+            const int64_t my_li = p.mode_b ? unit * p.D + slot : unit;
+            const bool valid = (t < p.Lout) && (slot < p.D) && (unit < n_units) && (my_li < n_live);
             float row_gate = 1.f;
-            if (a.gate_mode == 1 && valid) row_gate = a.gate[my_doc * p.L + t];
+            if (a.gate_mode == 1 && valid) row_gate = a.gate[t2_doc_of(a.live, my_li) * p.L + t];
 
             mbar_wait(bar_accf + 8 * buf, (uint32_t)((g >> 1) & 1));
             tc_fence_after();
@@ -385,14 +395,15 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const Tc2Args a) {
                 const int qps = p.mode_b ? p.S / 32 : 4;      // quadrants per document slot
                 for (int o = threadIdx.x; o < p.D * p.Nb; o += T2_EPI_THREADS) {
                     const int sl = o / p.Nb, c = o - sl * p.Nb;
-                    const int64_t doc = p.mode_b ? unit * p.D + sl : unit;
+                    const int64_t li = p.mode_b ? unit * p.D + sl : unit;
                     unsigned long long key = 0ull;
                     for (int q = sl * qps; q < sl * qps + qps && q < 4; ++q) {
                         const unsigned long long k2 = keys_u[q * p.Nb + c];
                         keys_u[q * p.Nb + c] = 0ull;
                         key = k2 > key ? k2 : key;
                     }
-                    if (unit < p.n_units && doc < a.n_docs && h0 + c < p.H) {
+                    if (unit < n_units && li < n_live && h0 + c < p.H) {
+                        const int64_t doc = t2_doc_of(a.live, li);
                         const float raw_v = __uint_as_float(ord2f((uint32_t)(key >> 32)));
                         const int tbest = (int)(0xFFFFFFFFu - (uint32_t)key);
                         const float gated = a.gate_mode == 2 ? raw_v * a.gate[doc] : raw_v;                 // per-doc gate > 0: monotone
@@ -409,6 +420,35 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const Tc2Args a) {
     cluster_sync_all();
     if (warp == T2_MMA_WARP) tmem_dealloc2(tmem_base, (uint32_t)p.tmem_cols);
 }
+
+// Document selection: one warp per document.  A document none of whose tokens is unmasked reads as all zeros, so its conv
+// output is the bias at every position: pooled value act(bias), first arg-max 0 — written here; the others are appended to
+// the list the conv kernel tiles (live[0] = count, zeroed by the caller).
+__global__ void __launch_bounds__(256) conv_doc_select_kernel(const IdView ids, const uint8_t* __restrict__ mask, int64_t n_docs, int L,
+                                                              int32_t* __restrict__ live, const float* __restrict__ bias, int H, int act,
+                                                              float* __restrict__ feat, int32_t* __restrict__ argmax,
+                                                              float* __restrict__ pool_raw, int feat_ld) {
+    const int lane = threadIdx.x & 31;
+    const int64_t d = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (d >= n_docs) return;
+    bool any = false;
+    for (int t = lane; t < L && !any; t += 32) {
+        const int64_t i = d * L + t;
+        any = mask ? (__ldg(mask + i) != 0) : (ld_id(ids, i) != 0);
+    }
+    any = __any_sync(0xffffffffu, any);
+    if (any) {
+        if (lane == 0) live[1 + atomicAdd(live, 1)] = (int32_t)d;
+    } else {
+        for (int h = lane; h < H; h += 32) {
+            feat[d * feat_ld + h] = act_apply(act, __ldg(bias + h));
+            argmax[d * feat_ld + h] = 0;
+            if (pool_raw) pool_raw[d * feat_ld + h] = 0.f;
+        }
+    }
+}
+
+int64_t conv_tc2_select_bytes(int64_t n_docs) { return round_up((n_docs + 1) * 4, 256); }
 
 static bool tc2_make_plan(int E, int H, int K, int L, int pad, int act, int64_t n_docs, Tc2Plan* out) {
     Tc2Plan p{};
@@ -523,7 +563,8 @@ static int tc2_launch(const CUtensorMap& tm, const Tc2Args& a, cudaStream_t s) {
 // returns RBR_EUNSUPPORTED (without setting an error message the caller must surface) when the shape is outside this variant
 int conv_tc2_dispatch(const __nv_bfloat16* shadow, int64_t vocab, int E, IdView ids, const uint8_t* mask,
                       const float* gate, int gate_mode, int64_t n_docs, int L, const __nv_bfloat16* umma_w2, const float* bias,
-                      int H, int K, int pad, int act, float* feat, int32_t* argmax, float* preact, int feat_ld, cudaStream_t s) {
+                      int H, int K, int pad, int act, float* feat, int32_t* argmax, float* preact, int feat_ld, void* ws,
+                      int64_t ws_bytes, cudaStream_t s) {
     Tc2Args a{};
     if (vocab >= (1ll << 31) || !tc2_make_plan(E, H, K, L, pad, act, n_docs, &a.p)) return RBR_EUNSUPPORTED;
     {
@@ -546,6 +587,17 @@ int conv_tc2_dispatch(const __nv_bfloat16* shadow, int64_t vocab, int E, IdView 
     const CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(shadow), gdim, gstr, box, estr,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, l2p, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     RBR_REQUIRE(r == CUDA_SUCCESS, RBR_ECUDA, "conv_fwd[bf16]: cuTensorMapEncodeTiled failed (%d)", (int)r);
+    // all-padding documents are cheap to find and need no tensor-core work (short documents only: NARRE's padded review slots)
+    a.live = nullptr;
+    if (ws && ws_bytes >= conv_tc2_select_bytes(n_docs) && (mask || ids.mask_ids) && a.p.mode_b && gate_mode == 0 && n_docs >= 64 &&
+        n_docs < (1ll << 31)) {
+        int32_t* live = reinterpret_cast<int32_t*>(ws);
+        RBR_CUDA(cudaMemsetAsync(live, 0, 4, s));
+        conv_doc_select_kernel<<<(unsigned)((n_docs * 32 + 255) / 256), 256, 0, s>>>(ids, mask, n_docs, L, live, bias, H, act, feat, argmax,
+                                                                                 preact, feat_ld);
+        RBR_LAUNCH_CHECK("conv_doc_select_kernel");
+        a.live = live;
+    }
     a.vocab = vocab; a.ids = ids; a.mask = mask; a.n_docs = n_docs; a.wpack = umma_w2; a.bias = bias;
     a.feat = feat; a.argmax = argmax; a.preact = preact; a.gate = gate; a.gate_mode = gate_mode; a.feat_ld = feat_ld;
     static const char* ew_env = getenv("RBR_TC2_EPI_WARPS");                    // timing experiments: force 8 or 16

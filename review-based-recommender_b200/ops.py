@@ -280,12 +280,14 @@ class EncodeDocsFn(torch.autograd.Function):
             feat = torch.empty(n_docs, h_total, dtype=torch.float32, device=table.device)
             amax = torch.empty(n_docs, h_total, dtype=torch.int32, device=table.device)
             col = 0
+            ws_bytes = lib.rbr_conv_fwd_workspace_bytes(n_docs) if prec == PREC_BF16 else 0
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=table.device) if ws_bytes else None
             for w, b, pk, pad in zip(weights, biases, packed, pads):
                 h, _, k = w.shape
                 lib.check(lib.rbr_conv_act_maxpool_fwd(
                     prec, act, _p(table), _p(shadow), vocab, emb, _p(ids), _p(mask), None, 0, n_docs, doc_len, _p(pk),
                     _p(_req(b, torch.float32, "conv bias")), h, k, pad, feat.data_ptr() + 4 * col, amax.data_ptr() + 4 * col,
-                    None, h_total, fl, _stream()), "rbr_conv_act_maxpool_fwd")
+                    None, h_total, _p(ws), ws_bytes, fl, _stream()), "rbr_conv_act_maxpool_fwd")
                 col += h
             feats.append(feat)
             argmaxes.append(amax)
@@ -774,7 +776,7 @@ def head_dropout_mask(batch: int, latent: int, drop_p: float, drop_seed: int, se
 def conv_act_maxpool(table: torch.Tensor, ids: torch.Tensor, mask: Optional[torch.Tensor], weight: torch.Tensor,
                      bias: torch.Tensor, pad: int, act: int = ACT_RELU, precision: str = "bf16",
                      shadow: Optional[torch.Tensor] = None, packed: Optional[torch.Tensor] = None, flags: int = 0,
-                     mask_from_ids: bool = False):
+                     mask_from_ids: bool = False, select_docs: bool = True):
     """One K2 launch: returns (feat [n_docs, H] fp32, argmax [n_docs, H] int32).  `flags`: CONV_TC_* kernel selection."""
     table = _req(table, torch.float32, "table")
     ids = _ids(ids, "ids")
@@ -790,9 +792,12 @@ def conv_act_maxpool(table: torch.Tensor, ids: torch.Tensor, mask: Optional[torc
     n_docs = ids.numel() // doc_len
     feat = torch.empty(n_docs, h, dtype=torch.float32, device=table.device)
     amax = torch.empty(n_docs, h, dtype=torch.int32, device=table.device)
+    ws_bytes = lib.rbr_conv_fwd_workspace_bytes(n_docs) if (prec == PREC_BF16 and select_docs) else 0
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=table.device) if ws_bytes else None
     lib.check(lib.rbr_conv_act_maxpool_fwd(prec, act, _p(table), _p(shadow), table.shape[0], emb, _p(ids), _p(mask), None, 0,
                                            n_docs, doc_len, _p(packed), _p(_req(bias, torch.float32, "bias")), h, k, pad,
-                                           _p(feat), _p(amax), None, h, flags, _stream(True)), "rbr_conv_act_maxpool_fwd")
+                                           _p(feat), _p(amax), None, h, _p(ws), ws_bytes, flags, _stream(True)),
+              "rbr_conv_act_maxpool_fwd")
     return feat, amax
 
 
@@ -846,8 +851,8 @@ class DattEncodeFn(torch.autograd.Function):
                 h, _, k = w.shape
                 lib.check(lib.rbr_conv_act_maxpool_fwd(prec, ACT_TANH, _p(table), _p(shadow), vocab, emb, _p(ids), None, _p(gate),
                                                        mode, n_docs, doc_len, _p(pk), _p(b), h, k, 0, feat.data_ptr() + 4 * col,
-                                                       amax.data_ptr() + 4 * col, pre.data_ptr() + 4 * col, h_total, idf, _stream()),
-                          "rbr_conv_act_maxpool_fwd")
+                                                       amax.data_ptr() + 4 * col, pre.data_ptr() + 4 * col, h_total, None, 0, idf,
+                                                       _stream()), "rbr_conv_act_maxpool_fwd")
                 col += h
             saved += [ids, gate_l, gate_g, feat, amax, pre]
             feats.append(feat)
