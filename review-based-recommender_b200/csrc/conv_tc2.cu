@@ -97,6 +97,10 @@ struct Tc2Args {
     // live[1 + i] = their indices.  The kernel then tiles only those; the all-padding documents (NARRE pads every user / item
     // to 10 reviews: ~45 % of the "documents" are empty) were given act(bias) / arg-max 0 by the selection pass.
     const int32_t* live;
+    // optional (long documents): ntl[i] = number of 128-position tiles document live[1 + i] needs — the tiles that lie entirely
+    // in its padding tail are skipped (conv_doc_tiles_* kernels; the list is sorted by tile count so that the two CTAs of a
+    // pair, which advance in lockstep, get documents of equal length)
+    const int32_t* ntl;
     Tc2Plan p;
 };
 
@@ -161,7 +165,20 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const Tc2Args a) {
     const int64_t n_live = a.live ? (int64_t)__ldg(a.live) : a.n_docs;
     const int64_t n_units = p.mode_b ? (n_live + p.D - 1) / p.D : n_live;
     const int64_t pair_units = (n_units > ci_even) ? (n_units - ci_even + ctas_per_pass - 1) / ctas_per_pass : 0;
-    const int64_t pair_tiles = pair_units * p.tpu;
+    // tiles of the pair's j-th unit step: fixed (tiles per unit), or — with a tile-count list — what the longer of the pair's
+    // two documents needs (the shorter one then runs over padding rows, which changes neither its max nor its first arg-max)
+    auto step_tiles = [&](int64_t j) -> int {
+        if (!a.ntl) return p.tpu;
+        const int64_t li0 = ci_even + j * ctas_per_pass;
+        const int n0 = li0 < n_live ? __ldg(a.ntl + li0) : 0, n1 = li0 + 1 < n_live ? __ldg(a.ntl + li0 + 1) : 0;
+        const int n = n0 > n1 ? n0 : n1;
+        return n < 1 ? 1 : n;
+    };
+    int64_t pair_tiles = pair_units * p.tpu;
+    if (a.ntl) {
+        pair_tiles = 0;
+        for (int64_t j = 0; j < pair_units; ++j) pair_tiles += step_tiles(j);
+    }
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < p.nst; ++i) { mbar_init(bar_full + 8 * i, 2); mbar_init(bar_empty + 8 * i, 1); }
@@ -249,14 +266,13 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const Tc2Args a) {
         const bool halo_lane = (pw == 0) && (lane < 4 * halo_groups);
         int64_t id_next[2];
         uint8_t ok_next[2];
-        auto prefetch_ids = [&](int64_t g) {
-            const int64_t unit = ci + (g / p.tpu) * ctas_per_pass;
-            const int tt = (int)(g % p.tpu);
+        auto prefetch_ids = [&](int64_t j, int tt) {
+            const int64_t unit = ci + j * ctas_per_pass;
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
                 id_next[i] = -1;
                 ok_next[i] = 0;
-                if (g >= pair_tiles || (i == 1 && !halo_lane) || (i == 0 && lane >= ROWS_PW)) continue;
+                if (j >= pair_units || (i == 1 && !halo_lane) || (i == 0 && lane >= ROWS_PW)) continue;
                 const int r = (i == 0) ? pw * ROWS_PW + lane : T2_M + lane;
                 int64_t doc;
                 int t;
@@ -271,7 +287,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const Tc2Args a) {
         bool w_checked = false;
         const uint32_t dst0 = ring_s + (uint32_t)(pw * G4_PW) * 512u;
         const uint32_t dst_halo = ring_s + 32u * 512u;
-        prefetch_ids(0);
+        int64_t uj = 0;                     // unit step, tile within it, tiles of the step
+        int utt = 0, unt = pair_units > 0 ? step_tiles(0) : 0;
+        prefetch_ids(0, 0);
         for (int64_t g = 0; g < pair_tiles; ++g) {
             int mine[2];
 #pragma unroll
@@ -283,7 +301,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const Tc2Args a) {
                     else note_oob();
                 }
             }
-            prefetch_ids(g + 1);
+            if (++utt >= unt) { ++uj; utt = 0; unt = uj < pair_units ? step_tiles(uj) : 0; }
+            prefetch_ids(uj, utt);
             // every lane gets all 32 row indices of the warp (and the halo's 8): the issuing lane then has its operands in
             // registers and the gather4s of a stage are straight-line code (a per-lane issue loop serialises on the TMA
             // unit accepting each instruction's uniform registers: ~100 cycles per gather4)
@@ -327,16 +346,18 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const Tc2Args a) {
         const int n_chunks = p.Nb / 16;
         const int chunk_lo = n_chunks * share / T2_EPI_SHARES;
         const int chunk_hi = n_chunks * (share + 1) / T2_EPI_SHARES;
+        int64_t uj = 0;
+        int tt = -1, unt = pair_units > 0 ? step_tiles(0) : 0;
         for (int64_t g = 0; g < pair_tiles; ++g) {
-            const int64_t unit = ci + (g / p.tpu) * ctas_per_pass;
-            const int tt = (int)(g % p.tpu);
+            if (++tt >= unt) { ++uj; tt = 0; unt = step_tiles(uj); }
+            const int64_t unit = ci + uj * ctas_per_pass;
             const int buf = (int)(g & 1);
             // Pooled keys (value, ~position) live in shared memory per TMEM lane quadrant: entry [quad][column] is owned by exactly
             // one warp (quad = warp & 3, column chunk by share), so the running max over the tiles of a document is a plain
             // read-modify-write — no atomics (a 64-bit shared atomicMax is a CAS loop, and four quadrants contended for every
             // column).  Double buffered by unit parity: ONE named barrier per unit (the buffer is next written two units
             // later, i.e. after the following unit's barrier, which every thread passes only once it has finalised this unit).
-            unsigned long long* keys_u = keys_s + ((g / p.tpu) & 1) * (4 * p.Nb);
+            unsigned long long* keys_u = keys_s + (uj & 1) * (4 * p.Nb);
             // mode B packs documents on 32-row (warp) boundaries: a warp's rows all belong to one document slot
             const int slot = p.mode_b ? (quad * 32) / p.S : 0;
             const int t = p.mode_b ? m - slot * p.S : tt * T2_M + m;
@@ -390,7 +411,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const Tc2Args a) {
                 __syncwarp();
                 if (lane == 0) mbar_arrive_cluster(bar_acce + 8 * buf, 0);
             }
-            if (tt == p.tpu - 1) {
+            if (tt == unt - 1) {
                 asm volatile("bar.sync 1, %0;" ::"n"(T2_EPI_THREADS) : "memory");
                 const int qps = p.mode_b ? p.S / 32 : 4;      // quadrants per document slot
                 for (int o = threadIdx.x; o < p.D * p.Nb; o += T2_EPI_THREADS) {
@@ -448,7 +469,52 @@ __global__ void __launch_bounds__(256) conv_doc_select_kernel(const IdView ids, 
     }
 }
 
-int64_t conv_tc2_select_bytes(int64_t n_docs) { return round_up((n_docs + 1) * 4, 256); }
+// ---- long documents: tiles per document and a list sorted by tile count (descending) ------------------------------------
+// A position t > len (len = last unmasked token + 1) sees only zero rows: its conv output is the bias, the same value as at
+// position len + 1.  Covering positions 0 .. len + 1 therefore yields the same max and the same FIRST arg-max as covering all of
+// them: tiles beyond ceil(min(Lout, len + 2) / 128) are skipped.  ws layout (int32): [0] count, [16..80) bucket counts,
+// [80..144) bucket cursors, [256 ..) list, then tiles-per-entry, then tiles-per-document.
+constexpr int T2_WS_HDR = 256;
+__global__ void __launch_bounds__(256) conv_doc_tiles_count_kernel(const IdView ids, const uint8_t* __restrict__ mask, int64_t n_docs, int L,
+                                                                   int Lout, int32_t* __restrict__ ws) {
+    const int lane = threadIdx.x & 31;
+    const int64_t d = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (d >= n_docs) return;
+    int len = 0;
+    for (int t0 = ((L - 1) / 32) * 32; t0 >= 0 && len == 0; t0 -= 32) {
+        const int t = t0 + lane;
+        bool on = false;
+        if (t < L) {
+            const int64_t i = d * L + t;
+            on = mask ? (__ldg(mask + i) != 0) : (ld_id(ids, i) != 0);
+        }
+        const unsigned b = __ballot_sync(0xffffffffu, on);
+        if (b) len = t0 + (32 - __clz(b));
+    }
+    const int covered = min(Lout, len + 2);
+    const int nt = max(1, (covered + T2_M - 1) / T2_M);
+    if (lane == 0) {
+        ws[T2_WS_HDR + 2 * n_docs + d] = nt;
+        atomicAdd(ws + 16 + min(nt, 63), 1);
+    }
+}
+__global__ void conv_doc_tiles_scan_kernel(int32_t* __restrict__ ws, int64_t n_docs) {
+    if (threadIdx.x == 0) {
+        int off = 0;
+        for (int b = 63; b >= 0; --b) { ws[80 + b] = off; off += ws[16 + b]; }       // longest documents first
+        ws[0] = (int32_t)n_docs;
+    }
+}
+__global__ void __launch_bounds__(256) conv_doc_tiles_fill_kernel(int32_t* __restrict__ ws, int64_t n_docs) {
+    const int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= n_docs) return;
+    const int nt = ws[T2_WS_HDR + 2 * n_docs + d];
+    const int pos = atomicAdd(ws + 80 + min(nt, 63), 1);
+    ws[T2_WS_HDR + pos] = (int32_t)d;
+    ws[T2_WS_HDR + n_docs + pos] = nt;
+}
+
+int64_t conv_tc2_select_bytes(int64_t n_docs) { return round_up((T2_WS_HDR + 3 * n_docs) * 4, 256); }
 
 static bool tc2_make_plan(int E, int H, int K, int L, int pad, int act, int64_t n_docs, Tc2Plan* out) {
     Tc2Plan p{};
@@ -589,14 +655,34 @@ int conv_tc2_dispatch(const __nv_bfloat16* shadow, int64_t vocab, int E, IdView 
     RBR_REQUIRE(r == CUDA_SUCCESS, RBR_ECUDA, "conv_fwd[bf16]: cuTensorMapEncodeTiled failed (%d)", (int)r);
     // all-padding documents are cheap to find and need no tensor-core work (short documents only: NARRE's padded review slots)
     a.live = nullptr;
-    if (ws && ws_bytes >= conv_tc2_select_bytes(n_docs) && (mask || ids.mask_ids) && a.p.mode_b && gate_mode == 0 && n_docs >= 64 &&
-        n_docs < (1ll << 31)) {
-        int32_t* live = reinterpret_cast<int32_t*>(ws);
-        RBR_CUDA(cudaMemsetAsync(live, 0, 4, s));
-        conv_doc_select_kernel<<<(unsigned)((n_docs * 32 + 255) / 256), 256, 0, s>>>(ids, mask, n_docs, L, live, bias, H, act, feat, argmax,
-                                                                                 preact, feat_ld);
-        RBR_LAUNCH_CHECK("conv_doc_select_kernel");
-        a.live = live;
+    a.ntl = nullptr;
+    static const char* sel_env = getenv("RBR_TC2_SELECT");                      // timing experiments: 0 disables both selections
+    const bool sel_on = !(sel_env && atoi(sel_env) == 0);
+    if (sel_on && ws && ws_bytes >= conv_tc2_select_bytes(n_docs) && (mask || ids.mask_ids) && gate_mode == 0 && n_docs >= 64 &&
+        n_docs < (1ll << 30)) {
+        int32_t* w32 = reinterpret_cast<int32_t*>(ws);
+        if (a.p.mode_b) {
+            // short documents: drop the all-padding ones.  The list (count at [T2_WS_HDR - 1]) is read as live[0], live[1 + i]
+            int32_t* live = w32 + T2_WS_HDR - 1;
+            RBR_CUDA(cudaMemsetAsync(live, 0, 4, s));
+            conv_doc_select_kernel<<<(unsigned)((n_docs * 32 + 255) / 256), 256, 0, s>>>(ids, mask, n_docs, L, live, bias, H, act, feat,
+                                                                                     argmax, preact, feat_ld);
+            RBR_LAUNCH_CHECK("conv_doc_select_kernel");
+            a.live = live;
+        } else if (a.p.tpu > 1) {
+            // long documents: skip the tiles that lie entirely in a document's padding tail
+            RBR_CUDA(cudaMemsetAsync(w32, 0, T2_WS_HDR * 4, s));
+            conv_doc_tiles_count_kernel<<<(unsigned)((n_docs * 32 + 255) / 256), 256, 0, s>>>(ids, mask, n_docs, L, a.p.Lout, w32);
+            RBR_LAUNCH_CHECK("conv_doc_tiles_count_kernel");
+            conv_doc_tiles_scan_kernel<<<1, 32, 0, s>>>(w32, n_docs);
+            RBR_LAUNCH_CHECK("conv_doc_tiles_scan_kernel");
+            conv_doc_tiles_fill_kernel<<<(unsigned)((n_docs + 255) / 256), 256, 0, s>>>(w32, n_docs);
+            RBR_LAUNCH_CHECK("conv_doc_tiles_fill_kernel");
+            // live[0] must be the count and live[1 + i] the list: the count is duplicated just below the list
+            RBR_CUDA(cudaMemcpyAsync(w32 + T2_WS_HDR - 1, w32, 4, cudaMemcpyDeviceToDevice, s));
+            a.live = w32 + T2_WS_HDR - 1;
+            a.ntl = w32 + T2_WS_HDR + n_docs;
+        }
     }
     a.vocab = vocab; a.ids = ids; a.mask = mask; a.n_docs = n_docs; a.wpack = umma_w2; a.bias = bias;
     a.feat = feat; a.argmax = argmax; a.preact = preact; a.gate = gate; a.gate_mode = gate_mode; a.feat_ld = feat_ld;

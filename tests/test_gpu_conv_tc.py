@@ -184,6 +184,41 @@ def test_variants_agree_bitwise_on_values():
     assert torch.equal(outs[0][1], outs[1][1])
 
 
+@pytest.mark.parametrize("L,k", [(500, 3), (1000, 5), (257, 3)])
+def test_padding_tail_tiles_skipped_bitwise(L, k):
+    """Long documents: the CTA-pair kernel runs only the 128-position tiles up to one position past each document's last
+    token (conv_doc_tiles_* pre-pass, documents sorted by tile count).  Values AND arg-max must equal the single-CTA
+    kernel's, which visits every tile — lengths sit on the tile boundaries, include empty and full documents, and one
+    document has a masked-out hole followed by a late token."""
+    gen = torch.Generator().manual_seed(L)
+    V, E, H, n = 3000, 300, 100, 333
+    table = torch.randn(V, E, generator=gen)
+    w = (torch.rand(H, E, k, generator=gen) * 2 - 1) / (E * k) ** 0.5
+    b = (torch.rand(H, generator=gen) * 2 - 1) * 0.1
+    b[:H // 2] -= 1.0                                              # many units whose max is the padding value relu(bias) = 0
+    lens = torch.randint(0, L + 1, (n,), generator=gen)
+    edge = [0, 1, 2, 125, 126, 127, 128, 129, 130, 254, 255, 256, 257, L - 2, L - 1, L]
+    lens[:len(edge)] = torch.tensor([min(e, L) for e in edge])
+    ids = torch.randint(1, V, (n, L), generator=gen)
+    mask = torch.arange(L).unsqueeze(0) < lens.unsqueeze(1)
+    mask[20, :] = False
+    mask[20, min(L - 1, 200)] = True                               # a lone late token
+    ids = ids * mask
+    outs = []
+    for fl in (ops.CONV_TC_SINGLE_CTA, ops.CONV_TC_PAIR_ONLY):
+        outs.append(ops.conv_act_maxpool(table.cuda(), ids.cuda(), mask.cuda(), w.cuda(), b.cuda(), (k - 1) // 2, precision="bf16",
+                                         flags=fl))
+    assert torch.equal(outs[0][0], outs[1][0])
+    assert torch.equal(outs[0][1], outs[1][1])
+    # and with the mask derived from the ids (id != 0), the int32 staging path
+    f3, a3 = ops.conv_act_maxpool(table.cuda(), ids.int().cuda(), None, w.cuda(), b.cuda(), (k - 1) // 2, precision="bf16",
+                                  flags=ops.CONV_TC_PAIR_ONLY, mask_from_ids=True)
+    assert torch.equal(f3, outs[0][0]) and torch.equal(a3, outs[0][1])
+    x = orc.mask_rows(orc.embedding_gather(_bf16_round(table), ids), mask)
+    ref, _ = orc.first_argmax_pool(torch.relu(orc.conv1d_same(x, _bf16_round(w), b)))
+    assert rel_err(outs[1][0].cpu(), ref) < 1e-3
+
+
 # ----------------------------------------------------------------------------------------------------------------------
 # K2c: dense tensor-core backward (coefficient matrix + two tcgen05 GEMMs, conv_bwd_tc.cu) against the arg-max-sparse
 # CUDA-core kernels (K2b) and the oracle.  (n_docs per side, L, V, E, H, k)
