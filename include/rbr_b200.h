@@ -103,7 +103,9 @@ int rbr_conv_pack(const float* weight, int64_t emb, int64_t filters, int64_t ksi
  *   ws / ws_bytes: optional scratch of rbr_conv_fwd_workspace_bytes(n_docs) bytes (NULL: none).  With it, short-document
  *   batches (NARRE pads every user / item to 10 reviews: all-padding "documents") are first scanned for documents without
  *   any unmasked token; those get act(bias) / arg-max 0 directly — exactly what the conv over their all-zero rows yields —
- *   and only the others are tiled onto the tensor cores.                                                               */
+ *   and only the others are tiled onto the tensor cores.  Long-document batches (DeepCoNN) are scanned for each document's
+ *   last unmasked token, and the 128-position tiles lying entirely in the padding tail are skipped (a position past the
+ *   last token + 1 yields the bias again: neither the max nor its first position changes).                                */
 int64_t rbr_conv_fwd_workspace_bytes(int64_t n_docs);
 /* Tiling plan of the CTA-pair kernel for a shape (host-only, launches nothing; used by the CPU tests of the tiling logic):
  * out[0..15] = {available, passes, filters/pass, filters/CTA, 64-wide K blocks, K steps, gather4 groups per stage, stage bytes,
@@ -116,6 +118,11 @@ int rbr_conv_act_maxpool_fwd(int precision, int activation, const void* table, c
                              const void* packed, const float* bias, int64_t filters, int64_t ksize,
                              int64_t pad, float* feat, int32_t* argmax, float* pool_raw, int64_t feat_ld,
                              void* ws, int64_t ws_bytes, int flags, void* stream);
+/* Timing experiments only.  With RBR_TC2_DEBUG=4 in the environment the CTA-pair conv kernel accumulates per-CTA cycle
+ * counters; this copies out[cta][8] = {MMA warp total, its wait for operands, its wait for a free accumulator, producer warp 0
+ * total, its wait for a free ring slot, epilogue warp 0 total, its wait for a finished accumulator, tiles} of the last launch
+ * (synchronises the device). */
+int rbr_debug_conv_tc2_prof(int64_t* out, int n_ctas);
 
 /* ---- K2b: arg-max-sparse backward of K2 ------------------------------------------------------------
  * Replaces aten::convolution_backward + max_pool1d backward + relu backward + masked_fill backward +
@@ -159,8 +166,8 @@ int rbr_conv_bwd_cmat_supported(int64_t vocab, int64_t emb, int64_t filters, int
 int64_t rbr_conv_bwd_cmat_workspace_bytes(int64_t vocab, int64_t emb, int64_t filters, int64_t ksize);
 int rbr_conv_bwd_cmat_scatter(const void* ids, const uint8_t* mask, int64_t n_docs, int64_t doc_len, int64_t vocab, int64_t emb,
                               int64_t filters, int64_t ksize, int64_t pad, int activation, const float* feat,
-                              const int32_t* argmax, const float* feat_grad, int64_t feat_ld, float* bias_grad, void* ws,
-                              int64_t ws_bytes, int flags, void* stream);
+                              const int32_t* argmax, const float* feat_grad, int64_t feat_ld, float* bias_grad,
+                              int64_t row_lo, int64_t row_hi, void* ws, int64_t ws_bytes, int flags, void* stream);
 int rbr_conv_bwd_cmat_finish(int what, const void* shadow_bf16, const void* packed, int64_t vocab, int64_t emb, int64_t filters,
                              int64_t ksize, int64_t padding_idx, float* table_grad, float* weight_grad, void* ws,
                              int64_t ws_bytes, void* stream);

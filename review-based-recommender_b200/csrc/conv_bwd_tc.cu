@@ -58,31 +58,68 @@ static CmatLayout cmat_layout(int64_t vocab, int64_t emb, int64_t filters, int64
 // ------------------------------------------------------------------------------------------------------------------
 // scatter: one thread per (doc, filter)
 // ------------------------------------------------------------------------------------------------------------------
+// The chain per (doc, filter) is two dependent memory round trips — {feat, feat_grad, arg-max} → {the k token ids (and mask
+// bytes) under the window} → k fire-and-forget REDs — and nearly every load misses L2 (the operands of a whole step stream
+// through it), so the kernel is bound by how many of those loads are in flight: the inputs of an item are fetched together, the
+// tap loop is unrolled (KT = k, or 0 = runtime loop) so its k id / mask loads issue back to back, and each thread works on two
+// items at once.  (With the arg-max read after the g == 0 test and a rolled tap loop it was 6 round trips: 2.5x slower.)
+template <int KT>
 __global__ void __launch_bounds__(256) cmat_scatter_kernel(const IdView ids, const uint8_t* __restrict__ mask, int64_t n_docs, int L, int H,
-                                                           int K, int pad, int64_t vocab, const float* __restrict__ feat,
+                                                           int K, int pad, int64_t v_lo, int64_t v_hi, const float* __restrict__ feat,
                                                            const int32_t* __restrict__ argmax, const float* __restrict__ feat_grad,
                                                            int feat_ld, int act, float* __restrict__ c32, int HJp,
                                                            float* __restrict__ bias_grad) {
     extern __shared__ float bsum[];            // [H] CTA-partial bias gradient
     for (int i = threadIdx.x; i < H; i += blockDim.x) bsum[i] = 0.f;
     __syncthreads();
+    constexpr int KU = KT > 0 ? KT : 1;        // unrolled taps per pass of the tap loop
+    constexpr int IT = 2;                      // items in flight per thread
+    const int taps = KT > 0 ? KT : K;
     const int64_t total = n_docs * H;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += stride) {
-        const int64_t n = q / H;
-        const int h = (int)(q - n * H);
-        const float y = __ldg(feat + n * feat_ld + h);
-        const float g = __ldg(feat_grad + n * feat_ld + h) * act_grad_from_out(act, y);
-        if (g == 0.f) continue;
-        if (bias_grad) atomicAdd(bsum + h, g);
-        const int ts = __ldg(argmax + n * feat_ld + h) - pad;
-#pragma unroll 1
-        for (int j = 0; j < K; ++j) {
-            const int t = ts + j;
-            if (t < 0 || t >= L) continue;
-            const int64_t id = ld_id(ids, n * L + t);
-            if (!ld_mask(ids, mask, n * L + t, id) || id < 0 || id >= vocab) continue;
-            atomicAdd(c32 + id * HJp + h * K + j, g);              // no return value: compiles to RED.E.ADD.F32
+    for (int64_t q0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q0 < total; q0 += IT * stride) {
+        int64_t n[IT];
+        int h[IT], ts[IT];
+        float g[IT];
+#pragma unroll
+        for (int u = 0; u < IT; ++u) {
+            const int64_t q = q0 + u * stride;
+            g[u] = 0.f;
+            n[u] = 0; h[u] = 0; ts[u] = 0;
+            if (q < total) {
+                n[u] = q / H;
+                h[u] = (int)(q - n[u] * H);
+                const int64_t o = n[u] * feat_ld + h[u];
+                const float y = __ldg(feat + o), gr = __ldg(feat_grad + o);
+                ts[u] = __ldg(argmax + o) - pad;
+                g[u] = gr * act_grad_from_out(act, y);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < IT; ++u)
+            if (g[u] != 0.f && bias_grad) atomicAdd(bsum + h[u], g[u]);
+        for (int j0 = 0; j0 < taps; j0 += KU) {
+            int64_t id[IT][KU];
+            bool ok[IT][KU];
+#pragma unroll
+            for (int u = 0; u < IT; ++u)
+#pragma unroll
+                for (int jj = 0; jj < KU; ++jj) {
+                    const int t = ts[u] + j0 + jj;
+                    ok[u][jj] = g[u] != 0.f && t >= 0 && t < L;
+                    id[u][jj] = 0;
+                    if (ok[u][jj]) {
+                        const int64_t i = n[u] * L + t;
+                        id[u][jj] = ld_id(ids, i);
+                        ok[u][jj] = ld_mask(ids, mask, i, id[u][jj]);
+                    }
+                }
+#pragma unroll
+            for (int u = 0; u < IT; ++u)
+#pragma unroll
+                for (int jj = 0; jj < KU; ++jj)
+                    if (ok[u][jj] && id[u][jj] >= v_lo && id[u][jj] < v_hi)
+                        atomicAdd(c32 + id[u][jj] * HJp + h[u] * K + j0 + jj, g[u]);      // no return value: compiles to RED.E.ADD.F32
         }
     }
     __syncthreads();
@@ -382,20 +419,30 @@ extern "C" int64_t rbr_conv_bwd_cmat_workspace_bytes(int64_t vocab, int64_t emb,
 
 extern "C" int rbr_conv_bwd_cmat_scatter(const void* ids_raw, const uint8_t* mask, int64_t n_docs, int64_t doc_len, int64_t vocab,
                                          int64_t emb, int64_t filters, int64_t ksize, int64_t pad, int activation, const float* feat,
-                                         const int32_t* argmax, const float* feat_grad, int64_t feat_ld, float* bias_grad, void* ws,
-                                         int64_t ws_bytes, int flags, void* stream) {
+                                         const int32_t* argmax, const float* feat_grad, int64_t feat_ld, float* bias_grad,
+                                         int64_t row_lo, int64_t row_hi, void* ws, int64_t ws_bytes, int flags, void* stream) {
     RBR_REQUIRE(ids_raw && feat && argmax && feat_grad && ws, RBR_EINVAL, "conv_bwd_cmat_scatter: null pointer");
+    if (row_lo == 0 && row_hi == 0) row_hi = vocab;
+    RBR_REQUIRE(row_lo >= 0 && row_lo <= row_hi && row_hi <= vocab, RBR_EINVAL, "conv_bwd_cmat_scatter: bad row range");
     RBR_REQUIRE(cmat_shape_ok(vocab, emb, filters, ksize), RBR_EUNSUPPORTED, "conv_bwd_cmat: shape outside the dense tensor-core backward");
     RBR_REQUIRE(n_docs >= 0 && doc_len > 0 && pad >= 0 && feat_ld >= filters, RBR_EINVAL, "conv_bwd_cmat_scatter: bad sizes");
     const CmatLayout l = cmat_layout(vocab, emb, filters, ksize);
     RBR_REQUIRE(ws_bytes >= l.total, RBR_EWORKSPACE, "conv_bwd_cmat_scatter: workspace too small");
     if (n_docs == 0) return RBR_OK;
     const int64_t total = n_docs * filters;
-    int64_t blocks = (total + 255) / 256;
+    int64_t blocks = (total + 511) / 512;            // two items per thread
     if (blocks > 148 * 16) blocks = 148 * 16;
-    cmat_scatter_kernel<<<(unsigned)blocks, 256, (size_t)filters * 4, as_stream(stream)>>>(
-        id_view(ids_raw, flags), mask, n_docs, (int)doc_len, (int)filters, (int)ksize, (int)pad, vocab, feat, argmax, feat_grad, (int)feat_ld,
-        activation, reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + l.off_c32), (int)l.HJp, bias_grad);
+#define RBR_SCATTER(KT)                                                                                                                   \
+    cmat_scatter_kernel<KT><<<(unsigned)blocks, 256, (size_t)filters * 4, as_stream(stream)>>>(                                           \
+        id_view(ids_raw, flags), mask, n_docs, (int)doc_len, (int)filters, (int)ksize, (int)pad, row_lo, row_hi, feat, argmax, feat_grad, (int)feat_ld, \
+        activation, reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + l.off_c32), (int)l.HJp, bias_grad)
+    switch (ksize) {
+        case 1: RBR_SCATTER(1); break;
+        case 3: RBR_SCATTER(3); break;
+        case 5: RBR_SCATTER(5); break;
+        default: RBR_SCATTER(0); break;
+    }
+#undef RBR_SCATTER
     RBR_LAUNCH_CHECK("cmat_scatter_kernel");
     return RBR_OK;
 }

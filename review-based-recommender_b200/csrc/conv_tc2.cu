@@ -104,6 +104,11 @@ struct Tc2Args {
     Tc2Plan p;
 };
 
+// RBR_TC2_DEBUG bit 4: per-CTA cycle counters (timing experiments): [0] MMA warp total, [1] its wait on the ring (full), [2] its wait on
+// the accumulators (acc_empty), [3] producer warp 0 total, [4] its wait on the ring (empty), [5] epilogue warp 0 total, [6] its wait
+// on the accumulators (acc_full), [7] tiles
+__device__ long long g_tc2_prof[1024][8];
+
 // list slot li (unit * D + slot) → document index
 __device__ __forceinline__ int64_t t2_doc_of(const int32_t* live, int64_t li) { return live ? (int64_t)__ldg(live + 1 + li) : li; }
 
@@ -220,15 +225,21 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const Tc2Args a) {
                 uint32_t ph = 0;
                 uint32_t full_bar = bar_full, empty_bar = bar_empty;
                 uint64_t ad = a_desc0;
+                const bool prof = (p.dbg & 4) != 0;
+                long long pt0 = prof ? clock64() : 0, pw_full = 0, pw_acce = 0, pt;
                 for (int64_t g = 0; g < pair_tiles; ++g) {
                     const int buf = (int)(g & 1);
+                    if (prof) pt = clock64();
                     mbar_wait(bar_acce + 8 * buf, (uint32_t)(((g >> 1) & 1) ^ 1));        // both CTAs' epilogues drained this buffer
+                    if (prof) pw_acce += clock64() - pt;
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + (uint32_t)(buf * p.acc_stride);
                     uint64_t bd = b_desc0;
                     int ks_left = p.ksteps;
                     for (int kb = 0; kb < p.nkb; ++kb) {
+                        if (prof) pt = clock64();
                         mbar_wait(full_bar, ph);                                           // both CTAs' TMA bytes have landed
+                        if (prof) pw_full += clock64() - pt;
                         tc_fence_after();
                         if (leader_lane) {
 #pragma unroll
@@ -251,6 +262,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const Tc2Args a) {
                         empty_bar += 8;
                         if (++stage == p.nst) { stage = 0; ph ^= 1; ad = a_desc0; full_bar = bar_full; empty_bar = bar_empty; }
                     }
+                }
+                if (prof && lane == 0 && blockIdx.x < 1024) {
+                    g_tc2_prof[blockIdx.x][0] = clock64() - pt0; g_tc2_prof[blockIdx.x][1] = pw_full; g_tc2_prof[blockIdx.x][2] = pw_acce;
+                    g_tc2_prof[blockIdx.x][7] = pair_tiles;
                 }
             }
         }
@@ -290,6 +305,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const Tc2Args a) {
         int64_t uj = 0;                     // unit step, tile within it, tiles of the step
         int utt = 0, unt = pair_units > 0 ? step_tiles(0) : 0;
         prefetch_ids(0, 0);
+        const bool prof = (p.dbg & 4) != 0 && pw == 0;
+        long long pt0 = prof ? clock64() : 0, pw_empty = 0, pt;
         for (int64_t g = 0; g < pair_tiles; ++g) {
             int mine[2];
 #pragma unroll
@@ -312,7 +329,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const Tc2Args a) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) hidx[i] = __shfl_sync(0xffffffffu, mine[1], i);
             for (int kb = 0; kb < p.nkb; ++kb) {
+                if (prof) pt = clock64();
                 mbar_wait(bar_empty + 8 * stage, ph ^ 1);
+                if (prof) pw_empty += clock64() - pt;
                 const uint32_t fb = bar_full + 8 * stage;
                 if (pw == 0 && lane == 0) {
                     if (rank == 0) {
@@ -337,6 +356,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const Tc2Args a) {
                 if (++stage == p.nst) { stage = 0; ph ^= 1; }
             }
         }
+        if (prof && lane == 0 && blockIdx.x < 1024) { g_tc2_prof[blockIdx.x][3] = clock64() - pt0; g_tc2_prof[blockIdx.x][4] = pw_empty; }
     } else {
         // =========================== epilogue (16 warps; warp w reads TMEM lanes 32(w&3)..+31 and reduces 1/4 of the column chunks:
         // the reduction is a chain of fixed-latency warp ops, so it is latency- not issue-bound and more warps hide it) ===========================
@@ -348,6 +368,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const Tc2Args a) {
         const int chunk_hi = n_chunks * (share + 1) / T2_EPI_SHARES;
         int64_t uj = 0;
         int tt = -1, unt = pair_units > 0 ? step_tiles(0) : 0;
+        const bool prof = (p.dbg & 4) != 0 && warp == 0;
+        long long pt0 = prof ? clock64() : 0, pw_accf = 0, pt;
         for (int64_t g = 0; g < pair_tiles; ++g) {
             if (++tt >= unt) { ++uj; tt = 0; unt = step_tiles(uj); }
             const int64_t unit = ci + uj * ctas_per_pass;
@@ -366,7 +388,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const Tc2Args a) {
             float row_gate = 1.f;
             if (a.gate_mode == 1 && valid) row_gate = a.gate[t2_doc_of(a.live, my_li) * p.L + t];
 
+            if (prof) pt = clock64();
             mbar_wait(bar_accf + 8 * buf, (uint32_t)((g >> 1) & 1));
+            if (prof) pw_accf += clock64() - pt;
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * p.acc_stride);
             // Chunks are pulled out of TMEM MAXC at a time; the accumulator is handed back to the MMA warp as soon as the warp's
@@ -435,6 +459,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const Tc2Args a) {
                 }
             }
         }
+        if (prof && lane == 0 && blockIdx.x < 1024) { g_tc2_prof[blockIdx.x][5] = clock64() - pt0; g_tc2_prof[blockIdx.x][6] = pw_accf; }
     }
     // teardown: neither CTA may free TMEM / exit while the pair's MMAs can still touch its shared or tensor memory
     tc_fence_before();
@@ -721,3 +746,11 @@ extern "C" int rbr_conv_tc2_plan(int64_t emb, int64_t filters, int64_t ksize, in
 }
 
 RBR_DEFINE_OOB_ACCESSOR(conv_tc2)
+
+// timing experiments (RBR_TC2_DEBUG=4): copies the per-CTA cycle counters of the last conv_tc2 launch to the host
+extern "C" int rbr_debug_conv_tc2_prof(int64_t* out, int n_ctas) {
+    if (!out || n_ctas < 1 || n_ctas > 1024) return RBR_EINVAL;
+    RBR_CUDA(cudaDeviceSynchronize());
+    RBR_CUDA(cudaMemcpyFromSymbol(out, rbr::g_tc2_prof, sizeof(long long) * 8 * (size_t)n_ctas));
+    return RBR_OK;
+}

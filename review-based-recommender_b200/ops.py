@@ -6,6 +6,8 @@ int64 / bool — anything else raises (there is no CPU path).
 """
 from __future__ import annotations
 
+import os
+
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -378,16 +380,19 @@ class EncodeDocsFn(torch.autograd.Function):
                         ws_bytes, ctx.flags_l[s], sh), "rbr_conv_act_maxpool_bwd")
             return run
 
-        def dense_scatter(s, sh):
-            ids, mask = ids_l[s], mask_l[s]
-            doc_len = ids.shape[-1]
-            n_docs = ids.numel() // doc_len
-            for i, ws in cm_ws.items():
-                h, _, k = shapes[i]
-                lib.check(lib.rbr_conv_bwd_cmat_scatter(
-                    _p(ids), _p(mask), n_docs, doc_len, vocab, emb, h, k, cfg["pads"][i], cfg["act"],
-                    feats[s].data_ptr() + 4 * cols[i], argmaxes[s].data_ptr() + 4 * cols[i], fgs[s].data_ptr() + 4 * cols[i],
-                    h_total, _p(g_b[i]), _p(ws), ws.numel(), ctx.flags_l[s], sh), "rbr_conv_bwd_cmat_scatter")
+        def dense_scatter_rows(lo, hi, with_bias):
+            def run(s, sh):
+                ids, mask = ids_l[s], mask_l[s]
+                doc_len = ids.shape[-1]
+                n_docs = ids.numel() // doc_len
+                for i, ws in cm_ws.items():
+                    h, _, k = shapes[i]
+                    lib.check(lib.rbr_conv_bwd_cmat_scatter(
+                        _p(ids), _p(mask), n_docs, doc_len, vocab, emb, h, k, cfg["pads"][i], cfg["act"],
+                        feats[s].data_ptr() + 4 * cols[i], argmaxes[s].data_ptr() + 4 * cols[i], fgs[s].data_ptr() + 4 * cols[i],
+                        h_total, _p(g_b[i]) if with_bias else None, lo, hi, _p(ws), ws.numel(), ctx.flags_l[s], sh),
+                        "rbr_conv_bwd_cmat_scatter")
+            return run
 
         # the arena left the table slot un-zeroed because this backward writes every element of it (NgramFeat.encode decided)
         overwrite = bool(cfg.get("table_overwrite")) and need_table and arena is not None and id(cfg["table_param"]) in arena.no_zero
@@ -410,7 +415,16 @@ class EncodeDocsFn(torch.autograd.Function):
             if any_sparse:
                 per_side(sparse_part(True, not two_pass) if need_table else sparse_part(False, True))
             if cm_ws:
-                per_side(dense_scatter)
+                n_chunks = int(os.environ.get("RBR_CMAT_CHUNKS", "1"))
+                prezero = os.environ.get("RBR_CMAT_PREZERO") == "1"
+                for c in range(n_chunks):
+                    lo, hi = vocab * c // n_chunks, vocab * (c + 1) // n_chunks
+                    if prezero:                                        # timing experiment: C32 rows made L2-resident right before the atomics
+                        for i, ws in cm_ws.items():
+                            h, _, k = shapes[i]
+                            hjp = (h * k + 63) // 64 * 64
+                            ws[lo * hjp * 4:hi * hjp * 4].zero_()
+                    per_side(dense_scatter_rows(lo, hi, c == 0))
                 dense_finish((1 | 2) if need_table else 1)
             if hook is not None:
                 hook(g_table)

@@ -1,0 +1,47 @@
+"""Where do the conv_tc2 roles wait?  Runs the CTA-pair conv on one bench-sized side with RBR_TC2_DEBUG=4 and prints, per role,
+the share of its cycles spent waiting on the pipeline barriers (median over CTAs).
+    RBR_TC2_DEBUG=4 python tools/prof_conv_roles.py [deepconn|narre]"""
+import ctypes
+import os
+import sys
+
+os.environ.setdefault("RBR_TC2_DEBUG", "4")
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+
+import bench
+from rbr_b200 import ops
+from rbr_b200._lib import lib
+
+name = sys.argv[1] if len(sys.argv) > 1 else "deepconn"
+c = bench.CFG[name]
+dev = torch.device("cuda:0")
+model = bench.build(name, dev, "bf16")
+(b, _), = bench.make_batches(name, 1, 0)
+ids, mask = b[0].to(dev), b[2].to(dev)
+if name == "narre":
+    ids, mask = ids.view(-1, c["T"]), mask.view(-1, c["T"])
+we = model.word_embeddings
+conv = model.ngram.conv
+w0, b0 = conv.list_of_conv1d[0].weight.detach(), conv.list_of_conv1d[0].bias.detach()
+args = dict(act=ops.ACT_RELU, precision="bf16", shadow=we.bf16_shadow(), packed=conv.packed(0))
+for _ in range(3):
+    ops.conv_act_maxpool(we.embedding.weight.detach(), ids, mask, w0, b0, 1, **args)
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+ops.conv_act_maxpool(we.embedding.weight.detach(), ids, mask, w0, b0, 1, **args)
+e1.record()
+torch.cuda.synchronize()
+n = 148
+out = np.zeros((n, 8), dtype=np.int64)
+lib.check(lib.rbr_debug_conv_tc2_prof(out.ctypes.data_as(ctypes.c_void_p), n), "prof")
+lead = out[0::2]
+print(f"{name}: launch {e0.elapsed_time(e1) * 1e3:.1f} us (with the pre-pass kernels); tiles per pair median {np.median(lead[:, 7]):.0f}")
+def share(a, b):
+    return f"{np.median(a / np.maximum(b, 1)) * 100:5.1f} %"
+print(f"MMA warp (leaders)   total {np.median(lead[:, 0]):9.0f} clk | waits operands {share(lead[:, 1], lead[:, 0])} | waits accumulator {share(lead[:, 2], lead[:, 0])}")
+print(f"producer warp 0      total {np.median(out[:, 3]):9.0f} clk | waits ring slot {share(out[:, 4], out[:, 3])}")
+print(f"epilogue warp 0      total {np.median(out[:, 5]):9.0f} clk | waits accumulator {share(out[:, 6], out[:, 5])}")
+print(f"clk per tile (MMA warp): {np.median(lead[:, 0] / np.maximum(lead[:, 7], 1)):.0f}")
