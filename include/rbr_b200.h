@@ -154,22 +154,31 @@ int rbr_conv_act_maxpool_bwd(int precision, int activation, const void* table, c
  *   table_grad[v,:]   += sum_hj C[v][hj] * W[hj,:]      (the bf16-rounded conv weights of `packed`; row padding_idx skipped)
  *   weight_grad[h,:,j] += sum_v C[v][h*k+j] * x[v,:]    (x = shadow_bf16)
  * run as tcgen05 GEMMs (rbr_conv_bwd_cmat_finish; C is split into bf16 hi + lo halves, fp32 accumulation).
- * `ws`: rbr_conv_bwd_cmat_workspace_bytes() bytes that the CALLER ZERO-FILLS ONCE; finish() with bit 1 leaves the coefficient
- * matrix zeroed again and bit 4 the weight scratch, so the same workspace serves every following step without a memset.
- * `what`: 1 = close the accumulation (split C; required once after the scatters, before 2 / 4), 2 = table gradient,
- * 4 = weight gradient — data-parallel training runs 1|2, starts the table all-reduce, then 4; 8 (with 2) = the table
- * gradient is OVERWRITTEN (every row and column is written, the padding row with zeros) instead of accumulated into: the
- * caller then need not zero-fill table_grad, and the epilogue stores without reading (halves its HBM traffic).
+ * C is kept as rbr_conv_bwd_cmat_chunks() FILTER BLOCKS of at most ~80 MB, each small enough to stay mostly L2-resident while the atomics of
+ * its (doc, filter) items land in it (an atomic that misses L2 costs a random DRAM read + write-back).  Per step and block c:
+ *   rbr_conv_bwd_cmat_begin(c)            zero-fills the block (the write allocates it in L2 without a DRAM read)
+ *   rbr_conv_bwd_cmat_scatter(side, c)    once per document side — the sides may run on different streams
+ *   rbr_conv_bwd_cmat_finish(1, c)        splits the block into the bf16 hi|lo operand while it is still in L2
+ * then rbr_conv_bwd_cmat_finish(2 / 4, -1) for the two gradients.  chunk = -1 means "every block" in all three calls.
+ * `ws`: rbr_conv_bwd_cmat_workspace_bytes() bytes that the CALLER ZERO-FILLS ONCE (the weight scratch is left zeroed again
+ * by bit 4).
+ * `what`: 1 = close the accumulation of block `chunk` (split C; required once per block after its scatters, before 2 / 4),
+ * 2 = table gradient, 4 = weight gradient — data-parallel training runs 1|2, starts the table all-reduce, then 4; 8 (with 2) =
+ * the table gradient is OVERWRITTEN (every row and column is written, the padding row with zeros) instead of accumulated
+ * into: the caller then need not zero-fill table_grad, and the epilogue stores without reading (halves its HBM traffic).
  * Shapes: emb % 4 == 0, emb <= 512, vocab * round_up(filters*ksize, 64) * 4 bytes <= 3 GiB, no gate
  * (rbr_conv_bwd_cmat_supported; otherwise use K2b).                                                                     */
 int rbr_conv_bwd_cmat_supported(int64_t vocab, int64_t emb, int64_t filters, int64_t ksize);
 int64_t rbr_conv_bwd_cmat_workspace_bytes(int64_t vocab, int64_t emb, int64_t filters, int64_t ksize);
+int rbr_conv_bwd_cmat_chunks(int64_t vocab, int64_t emb, int64_t filters, int64_t ksize);
+int rbr_conv_bwd_cmat_begin(int chunk, int64_t vocab, int64_t emb, int64_t filters, int64_t ksize, void* ws, int64_t ws_bytes,
+                            void* stream);
 int rbr_conv_bwd_cmat_scatter(const void* ids, const uint8_t* mask, int64_t n_docs, int64_t doc_len, int64_t vocab, int64_t emb,
                               int64_t filters, int64_t ksize, int64_t pad, int activation, const float* feat,
-                              const int32_t* argmax, const float* feat_grad, int64_t feat_ld, float* bias_grad,
-                              int64_t row_lo, int64_t row_hi, void* ws, int64_t ws_bytes, int flags, void* stream);
-int rbr_conv_bwd_cmat_finish(int what, const void* shadow_bf16, const void* packed, int64_t vocab, int64_t emb, int64_t filters,
-                             int64_t ksize, int64_t padding_idx, float* table_grad, float* weight_grad, void* ws,
+                              const int32_t* argmax, const float* feat_grad, int64_t feat_ld, float* bias_grad, int chunk,
+                              void* ws, int64_t ws_bytes, int flags, void* stream);
+int rbr_conv_bwd_cmat_finish(int what, int chunk, const void* shadow_bf16, const void* packed, int64_t vocab, int64_t emb,
+                             int64_t filters, int64_t ksize, int64_t padding_idx, float* table_grad, float* weight_grad, void* ws,
                              int64_t ws_bytes, void* stream);
 
 /* ---- K8: the alternate encoder arch="HierPooling" ---------------------------------------------------------------------

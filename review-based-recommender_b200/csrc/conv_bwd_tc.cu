@@ -39,7 +39,17 @@ constexpr int CM_STAGES_W = 3;             // weight GEMM ring (up to 56 KB per 
 struct CmatLayout {
     int64_t V, H, K, E, HJ, HJp, emb_pad, epad4;
     int64_t off_c32, off_chl, off_dw, total;
+    // C32 is stored as n_chunks FILTER BLOCKS, block c = filters [c*hc, min(H, (c+1)*hc)) = columns [c*hc*K, ...) of the logical
+    // [V][HJp] matrix, each block a contiguous [V][width] array (the last one also holds the zero padding columns up to HJp).
+    // A block is sized to stay mostly L2-resident while the scatter's atomics land in it: a RED that misses L2 costs a DRAM
+    // sector read + write-back at random addresses (44 G/s measured), one that hits is several times cheaper.  Blocking by
+    // filter, not by token, means every (doc, filter) item belongs to exactly one block: the passes partition the items,
+    // nothing is re-read.  Measured inside the graphed step (tools/timeline_step.py): DeepCoNN (64 MB) is fastest as ONE block
+    // (939 us/step; 968 with two), NARRE (102 MB) with two (1567 us/step; 1584 with one, 1607 with three) — more passes cost
+    // more in launches and stream joins than the extra L2 hits return, hence the 80 MB target.
+    int64_t n_chunks, hc;
 };
+struct CmatChunk { int64_t h_lo, h_n, col_lo, width, base; };      // base = float offset of the block inside C32
 static CmatLayout cmat_layout(int64_t vocab, int64_t emb, int64_t filters, int64_t ksize) {
     CmatLayout l;
     l.V = vocab; l.H = filters; l.K = ksize; l.E = emb;
@@ -52,44 +62,58 @@ static CmatLayout cmat_layout(int64_t vocab, int64_t emb, int64_t filters, int64
     l.off_chl = off; off += round_up(vocab * 2 * l.HJp * 2, 1024);
     l.off_dw = off; off += round_up(l.HJ * l.epad4 * 4, 1024);
     l.total = off;
+    static const char* ch_env = getenv("RBR_CMAT_CHUNKS");                      // timing experiments: force the block count
+    int64_t want = ch_env ? atoi(ch_env) : (vocab * l.HJp * 4 + (80ll << 20) - 1) / (80ll << 20);
+    want = std::max<int64_t>(1, std::min<int64_t>(want, 16));
+    l.hc = round_up((filters + want - 1) / want, 4);                            // block widths stay float4-aligned
+    l.n_chunks = (filters + l.hc - 1) / l.hc;
     return l;
+}
+static CmatChunk cmat_chunk(const CmatLayout& l, int64_t c) {
+    CmatChunk k;
+    k.h_lo = c * l.hc;
+    k.h_n = std::min(l.H, k.h_lo + l.hc) - k.h_lo;
+    k.col_lo = k.h_lo * l.K;
+    k.width = (c == l.n_chunks - 1) ? l.HJp - k.col_lo : l.hc * l.K;
+    k.base = l.V * k.col_lo;
+    return k;
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// scatter: one thread per (doc, filter)
-// ------------------------------------------------------------------------------------------------------------------
-// The chain per (doc, filter) is two dependent memory round trips — {feat, feat_grad, arg-max} → {the k token ids (and mask
-// bytes) under the window} → k fire-and-forget REDs — and nearly every load misses L2 (the operands of a whole step stream
-// through it), so the kernel is bound by how many of those loads are in flight: the inputs of an item are fetched together, the
-// tap loop is unrolled (KT = k, or 0 = runtime loop) so its k id / mask loads issue back to back, and each thread works on two
-// items at once.  (With the arg-max read after the g == 0 test and a rolled tap loop it was 6 round trips: 2.5x slower.)
-template <int KT>
-__global__ void __launch_bounds__(256) cmat_scatter_kernel(const IdView ids, const uint8_t* __restrict__ mask, int64_t n_docs, int L, int H,
-                                                           int K, int pad, int64_t v_lo, int64_t v_hi, const float* __restrict__ feat,
-                                                           const int32_t* __restrict__ argmax, const float* __restrict__ feat_grad,
-                                                           int feat_ld, int act, float* __restrict__ c32, int HJp,
-                                                           float* __restrict__ bias_grad) {
+// scatter: one thread per (doc, filter) item, IT items in flight per thread.
+// The chain per item is two dependent memory round trips — {feat, feat_grad, arg-max} → {the k token ids (and mask bytes)
+// under the window} → k fire-and-forget REDs — and nearly every load misses L2 (the operands of a whole step stream through
+// it), so the kernel is bound by how many of those loads are in flight: the inputs of an item are fetched together, the tap
+// loop is unrolled (KT = k, or 0 = runtime loop) so its k id / mask loads issue back to back, and the SM is kept full
+// (2048 threads x IT items).
+template <int KT, int IT>
+__global__ void __launch_bounds__(256, IT > 2 ? 6 : 8) cmat_scatter_kernel(const IdView ids, const uint8_t* __restrict__ mask, int64_t n_docs, int L, int H,
+                                                              int K, int pad, int64_t v_lo, int64_t v_hi, const float* __restrict__ feat,
+                                                              const int32_t* __restrict__ argmax, const float* __restrict__ feat_grad,
+                                                              int feat_ld, int act, float* __restrict__ c32, int HJp,
+                                                              float* __restrict__ bias_grad, int dbg) {
+    // H = filters of this block (feat / argmax / feat_grad / bias_grad already point at its first filter), c32 = the block,
+    // HJp = its row pitch
     extern __shared__ float bsum[];            // [H] CTA-partial bias gradient
     for (int i = threadIdx.x; i < H; i += blockDim.x) bsum[i] = 0.f;
     __syncthreads();
     constexpr int KU = KT > 0 ? KT : 1;        // unrolled taps per pass of the tap loop
-    constexpr int IT = 2;                      // items in flight per thread
     const int taps = KT > 0 ? KT : K;
-    const int64_t total = n_docs * H;
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t q0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q0 < total; q0 += IT * stride) {
-        int64_t n[IT];
+    const uint32_t total = (uint32_t)(n_docs * H);                 // < 2^31 (checked by the caller): 32-bit index arithmetic
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t q0 = blockIdx.x * blockDim.x + threadIdx.x; q0 < total; q0 += IT * stride) {
+        uint32_t n[IT];
         int h[IT], ts[IT];
         float g[IT];
 #pragma unroll
         for (int u = 0; u < IT; ++u) {
-            const int64_t q = q0 + u * stride;
+            const uint32_t q = q0 + u * stride;
             g[u] = 0.f;
             n[u] = 0; h[u] = 0; ts[u] = 0;
-            if (q < total) {
-                n[u] = q / H;
-                h[u] = (int)(q - n[u] * H);
-                const int64_t o = n[u] * feat_ld + h[u];
+            if (q < total && q >= q0) {
+                n[u] = q / (uint32_t)H;
+                h[u] = (int)(q - n[u] * (uint32_t)H);
+                const int64_t o = (int64_t)n[u] * feat_ld + h[u];
                 const float y = __ldg(feat + o), gr = __ldg(feat_grad + o);
                 ts[u] = __ldg(argmax + o) - pad;
                 g[u] = gr * act_grad_from_out(act, y);
@@ -97,29 +121,28 @@ __global__ void __launch_bounds__(256) cmat_scatter_kernel(const IdView ids, con
         }
 #pragma unroll
         for (int u = 0; u < IT; ++u)
-            if (g[u] != 0.f && bias_grad) atomicAdd(bsum + h[u], g[u]);
+            if (g[u] != 0.f && bias_grad && !(dbg & 2)) atomicAdd(bsum + h[u], g[u]);
         for (int j0 = 0; j0 < taps; j0 += KU) {
-            int64_t id[IT][KU];
-            bool ok[IT][KU];
+            int row[IT][KU];                   // C row of tap j0 + jj of item u, or -1 (rows are < 2^31: cmat_shape_ok)
 #pragma unroll
             for (int u = 0; u < IT; ++u)
 #pragma unroll
                 for (int jj = 0; jj < KU; ++jj) {
                     const int t = ts[u] + j0 + jj;
-                    ok[u][jj] = g[u] != 0.f && t >= 0 && t < L;
-                    id[u][jj] = 0;
-                    if (ok[u][jj]) {
-                        const int64_t i = n[u] * L + t;
-                        id[u][jj] = ld_id(ids, i);
-                        ok[u][jj] = ld_mask(ids, mask, i, id[u][jj]);
+                    row[u][jj] = -1;
+                    if (g[u] != 0.f && t >= 0 && t < L) {
+                        const int64_t i = (int64_t)n[u] * L + t;
+                        if (dbg & 4) { row[u][jj] = (int)((unsigned)(i * 2654435761u) % (unsigned)v_hi); continue; }
+                        const int64_t id = ld_id(ids, i);
+                        if (ld_mask(ids, mask, i, id) && id >= v_lo && id < v_hi) row[u][jj] = (int)id;
                     }
                 }
 #pragma unroll
             for (int u = 0; u < IT; ++u)
 #pragma unroll
                 for (int jj = 0; jj < KU; ++jj)
-                    if (ok[u][jj] && id[u][jj] >= v_lo && id[u][jj] < v_hi)
-                        atomicAdd(c32 + id[u][jj] * HJp + h[u] * K + j0 + jj, g[u]);      // no return value: compiles to RED.E.ADD.F32
+                    if (row[u][jj] >= 0 && (!(dbg & 1) || g[u] == 12345.f))
+                        atomicAdd(c32 + (int64_t)row[u][jj] * HJp + h[u] * K + j0 + jj, g[u]);      // no return value: RED.E.ADD.F32
         }
     }
     __syncthreads();
@@ -130,16 +153,88 @@ __global__ void __launch_bounds__(256) cmat_scatter_kernel(const IdView ids, con
         }
 }
 
-// C32 → [hi | lo] bf16 and re-zero C32.  One thread per 4 columns.
-__global__ void __launch_bounds__(256) cmat_split_kernel(float4* __restrict__ c32, int64_t rows, int HJp, __nv_bfloat16* __restrict__ chl) {
-    const int q4 = HJp >> 2;
+// The same scatter, specialised until the item loop is ~60 straight-line instructions (the generic kernel above executes ~220
+// per item: index divisions, IdView / mask / range branches, a CAS loop per bias partial — it was issue-bound at 60 us for
+// NARRE's 6.1 M items with every load hitting L2).  Here the grid size makes the thread count a multiple of H, so a thread keeps
+// ONE filter h for its whole life (bias partial in a register, documents advance by a constant, no division in the loop); all
+// indices are 32-bit; window positions are clamped instead of branched around; id width and mask source are template arguments.
+template <int KT, int IT, bool I32, int MM>       // MM: 0 = no mask, 1 = mask bytes, 2 = mask is (id != 0)
+__global__ void __launch_bounds__(256, 8) cmat_scatter_fast_kernel(const void* __restrict__ ids_raw, const uint8_t* __restrict__ mask, int n_docs,
+                                                                   int L, int H, int pad, int v_lo, int v_hi, const float* __restrict__ feat,
+                                                                   const int32_t* __restrict__ argmax, const float* __restrict__ feat_grad,
+                                                                   int feat_ld, int act, float* __restrict__ c32, int HJp,
+                                                                   float* __restrict__ bias_grad, int dbg) {
+    extern __shared__ float bsum[];            // [H] CTA-partial bias gradient
+    for (int i = threadIdx.x; i < H; i += blockDim.x) bsum[i] = 0.f;
+    __syncthreads();
+    const uint32_t gthreads = gridDim.x * blockDim.x;               // a multiple of H (host)
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    const int h = (int)(q % (uint32_t)H);
+    const int dn = (int)(gthreads / (uint32_t)H);                   // documents per grid-wide step
+    const int hk = h * KT;
+    const uint32_t v_span = (uint32_t)(v_hi - v_lo);
+    const bool relu = act == RBR_ACT_RELU;
+    float bacc = 0.f;
+    for (int n0 = (int)(q / (uint32_t)H); n0 < n_docs; n0 += IT * dn) {
+        int nn[IT], ts[IT];
+        float g[IT];
+#pragma unroll
+        for (int u = 0; u < IT; ++u) {
+            const int n = n0 + u * dn;
+            nn[u] = n < n_docs ? n : n_docs - 1;
+            const int o = nn[u] * feat_ld + h;
+            const float y = __ldg(feat + o), gr = __ldg(feat_grad + o);
+            ts[u] = __ldg(argmax + o) - pad;
+            const float d = relu ? (y > 0.f ? 1.f : 0.f) : (1.f - y * y);
+            g[u] = n < n_docs ? gr * d : 0.f;
+        }
+        int row[IT][KT];
+#pragma unroll
+        for (int u = 0; u < IT; ++u)
+#pragma unroll
+            for (int j = 0; j < KT; ++j) {
+                const int t = ts[u] + j;
+                const int tc = min(max(t, 0), L - 1);
+                const int i = nn[u] * L + tc;
+                int id;
+                if (I32) id = __ldg(reinterpret_cast<const int32_t*>(ids_raw) + i);
+                else {
+                    const int64_t w = __ldg(reinterpret_cast<const int64_t*>(ids_raw) + i);
+                    id = (w >= 0 && w < 0x7fffffffll) ? (int)w : -1;
+                }
+                bool ok = (t == tc) && g[u] != 0.f && (uint32_t)(id - v_lo) < v_span;
+                if (MM == 1) ok = ok && __ldg(mask + i) != 0;
+                if (MM == 2) ok = ok && id != 0;
+                row[u][j] = ok ? id : -1;
+            }
+#pragma unroll
+        for (int u = 0; u < IT; ++u) {
+            bacc += g[u];
+#pragma unroll
+            for (int j = 0; j < KT; ++j)
+                if (row[u][j] >= 0 && !(dbg & 1)) atomicAdd(c32 + ((uint32_t)row[u][j] * (uint32_t)HJp + (uint32_t)(hk + j)), g[u]);
+        }
+    }
+    if (bias_grad) {
+        if (bacc != 0.f) atomicAdd(bsum + h, bacc);
+        __syncthreads();
+        for (int i = threadIdx.x; i < H; i += blockDim.x) {
+            const float v = bsum[i];
+            if (v != 0.f) atomicAdd(bias_grad + i, v);
+        }
+    }
+}
+
+// One filter block of C32 ([rows][width] fp32) → its columns of Chl = [hi | lo] bf16 ([rows][2 HJp]).  One thread per 4 columns.
+__global__ void __launch_bounds__(256) cmat_split_kernel(const float4* __restrict__ blk, int64_t rows, int width, int col_lo, int HJp,
+                                                         __nv_bfloat16* __restrict__ chl) {
+    const int q4 = width >> 2;
     const int64_t total = rows * q4;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += stride) {
         const int64_t r = q / q4;
-        const int c = (int)(q - r * q4) * 4;
-        const float4 v = c32[q];
-        if (v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f) c32[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int c = col_lo + (int)(q - r * q4) * 4;
+        const float4 v = __ldg(blk + q);
         const __nv_bfloat162 h01 = __floats2bfloat162_rn(v.x, v.y), h23 = __floats2bfloat162_rn(v.z, v.w);
         const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
         const __nv_bfloat162 l01 = __floats2bfloat162_rn(v.x - f01.x, v.y - f01.y), l23 = __floats2bfloat162_rn(v.z - f23.x, v.w - f23.y);
@@ -417,25 +512,79 @@ extern "C" int64_t rbr_conv_bwd_cmat_workspace_bytes(int64_t vocab, int64_t emb,
     return cmat_layout(vocab, emb, filters, ksize).total;
 }
 
-extern "C" int rbr_conv_bwd_cmat_scatter(const void* ids_raw, const uint8_t* mask, int64_t n_docs, int64_t doc_len, int64_t vocab,
-                                         int64_t emb, int64_t filters, int64_t ksize, int64_t pad, int activation, const float* feat,
-                                         const int32_t* argmax, const float* feat_grad, int64_t feat_ld, float* bias_grad,
-                                         int64_t row_lo, int64_t row_hi, void* ws, int64_t ws_bytes, int flags, void* stream) {
-    RBR_REQUIRE(ids_raw && feat && argmax && feat_grad && ws, RBR_EINVAL, "conv_bwd_cmat_scatter: null pointer");
-    if (row_lo == 0 && row_hi == 0) row_hi = vocab;
-    RBR_REQUIRE(row_lo >= 0 && row_lo <= row_hi && row_hi <= vocab, RBR_EINVAL, "conv_bwd_cmat_scatter: bad row range");
+extern "C" int rbr_conv_bwd_cmat_chunks(int64_t vocab, int64_t emb, int64_t filters, int64_t ksize) {
+    if (!cmat_shape_ok(vocab, emb, filters, ksize)) return 0;
+    return (int)cmat_layout(vocab, emb, filters, ksize).n_chunks;
+}
+
+extern "C" int rbr_conv_bwd_cmat_begin(int chunk, int64_t vocab, int64_t emb, int64_t filters, int64_t ksize, void* ws, int64_t ws_bytes,
+                                       void* stream) {
+    RBR_REQUIRE(ws, RBR_EINVAL, "conv_bwd_cmat_begin: null pointer");
     RBR_REQUIRE(cmat_shape_ok(vocab, emb, filters, ksize), RBR_EUNSUPPORTED, "conv_bwd_cmat: shape outside the dense tensor-core backward");
-    RBR_REQUIRE(n_docs >= 0 && doc_len > 0 && pad >= 0 && feat_ld >= filters, RBR_EINVAL, "conv_bwd_cmat_scatter: bad sizes");
     const CmatLayout l = cmat_layout(vocab, emb, filters, ksize);
-    RBR_REQUIRE(ws_bytes >= l.total, RBR_EWORKSPACE, "conv_bwd_cmat_scatter: workspace too small");
-    if (n_docs == 0) return RBR_OK;
+    RBR_REQUIRE(ws_bytes >= l.total, RBR_EWORKSPACE, "conv_bwd_cmat_begin: workspace too small");
+    RBR_REQUIRE(chunk >= -1 && chunk < l.n_chunks, RBR_EINVAL, "conv_bwd_cmat_begin: bad chunk");
+    float* c32 = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + l.off_c32);
+    if (chunk < 0) {
+        RBR_CUDA(cudaMemsetAsync(c32, 0, (size_t)(vocab * l.HJp * 4), as_stream(stream)));
+    } else {
+        const CmatChunk k = cmat_chunk(l, chunk);
+        RBR_CUDA(cudaMemsetAsync(c32 + k.base, 0, (size_t)(vocab * k.width * 4), as_stream(stream)));
+    }
+    return RBR_OK;
+}
+
+// one filter block of one document side
+static int cmat_scatter_block(const CmatLayout& l, const CmatChunk& k, const void* ids_raw, const uint8_t* mask, int64_t n_docs, int64_t doc_len,
+                              int64_t pad, int activation, const float* feat, const int32_t* argmax, const float* feat_grad, int64_t feat_ld,
+                              float* bias_grad, float* c32, int flags, void* stream) {
+    const int64_t vocab = l.V, ksize = l.K, filters = k.h_n;
+    feat += k.h_lo; argmax += k.h_lo; feat_grad += k.h_lo;
+    if (bias_grad) bias_grad += k.h_lo;
+    float* c32p = c32 + k.base;
+    const int pitch = (int)k.width;
     const int64_t total = n_docs * filters;
-    int64_t blocks = (total + 511) / 512;            // two items per thread
-    if (blocks > 148 * 16) blocks = 148 * 16;
-#define RBR_SCATTER(KT)                                                                                                                   \
-    cmat_scatter_kernel<KT><<<(unsigned)blocks, 256, (size_t)filters * 4, as_stream(stream)>>>(                                           \
-        id_view(ids_raw, flags), mask, n_docs, (int)doc_len, (int)filters, (int)ksize, (int)pad, row_lo, row_hi, feat, argmax, feat_grad, (int)feat_ld, \
-        activation, reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + l.off_c32), (int)l.HJp, bias_grad)
+    RBR_REQUIRE(total < (1ll << 31) - (1ll << 24), RBR_EUNSUPPORTED, "conv_bwd_cmat_scatter: n_docs * filters must stay below 2^31");
+    static const char* dbg_env = getenv("RBR_SCATTER_DEBUG");       // timing experiments only (results wrong): 1 no REDs, 2 no bias, 4 no id loads
+    const int dbg = dbg_env ? atoi(dbg_env) : 0;
+    // fast path: 32-bit indices everywhere, k in {1, 3, 5}, and a grid whose thread count is a multiple of the block's filters
+    {
+        int64_t g = filters, r = 256;
+        while (r) { const int64_t t = g % r; g = r; r = t; }            // g = gcd(filters, 256)
+        const int64_t m = filters / g;                                  // grid must be a multiple of m
+        static const char* fast_env = getenv("RBR_SCATTER_FAST");
+        const bool fast_on = !(fast_env && atoi(fast_env) == 0);
+        const bool small = n_docs * std::max(feat_ld, doc_len) < (1ll << 31) - 1 && vocab < (1ll << 31) - 1 && vocab * k.width < (1ll << 32) &&
+                           filters * ksize < (1 << 20);
+        if (fast_on && small && m <= 148 * 8 && (ksize == 1 || ksize == 3 || ksize == 5)) {
+            constexpr int IT = 2;
+            int64_t blocks = (total + 256 * IT - 1) / (256 * IT);
+            if (blocks > 148 * 8) blocks = 148 * 8;
+            blocks = std::max<int64_t>(m, blocks / m * m);
+            const int mm = mask ? 1 : ((flags & RBR_MASK_FROM_IDS) ? 2 : 0);
+            const bool i32 = (flags & RBR_IDS_I32) != 0;
+#define RBR_SF(KT, I32, MM)                                                                                                              \
+    cmat_scatter_fast_kernel<KT, IT, I32, MM><<<(unsigned)blocks, 256, (size_t)filters * 4, as_stream(stream)>>>(                        \
+        ids_raw, mask, (int)n_docs, (int)doc_len, (int)filters, (int)pad, 0, (int)vocab, feat, argmax, feat_grad, (int)feat_ld,          \
+        activation, c32p, pitch, bias_grad, dbg)
+#define RBR_SF_K(I32, MM)                                                                     \
+    do {                                                                                      \
+        if (ksize == 1) RBR_SF(1, I32, MM); else if (ksize == 3) RBR_SF(3, I32, MM); else RBR_SF(5, I32, MM); \
+    } while (0)
+            if (i32) { if (mm == 0) RBR_SF_K(true, 0); else if (mm == 1) RBR_SF_K(true, 1); else RBR_SF_K(true, 2); }
+            else     { if (mm == 0) RBR_SF_K(false, 0); else if (mm == 1) RBR_SF_K(false, 1); else RBR_SF_K(false, 2); }
+#undef RBR_SF_K
+#undef RBR_SF
+            RBR_LAUNCH_CHECK("cmat_scatter_fast_kernel");
+            return RBR_OK;
+        }
+    }
+    int64_t blocks = (total + 256 * 2 - 1) / (256 * 2);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+#define RBR_SCATTER(KT)                                                                                                                      \
+    cmat_scatter_kernel<KT, 2><<<(unsigned)blocks, 256, (size_t)filters * 4, as_stream(stream)>>>(                                           \
+        id_view(ids_raw, flags), mask, n_docs, (int)doc_len, (int)filters, (int)ksize, (int)pad, 0, vocab, feat, argmax, feat_grad, (int)feat_ld, \
+        activation, c32p, pitch, bias_grad, dbg)
     switch (ksize) {
         case 1: RBR_SCATTER(1); break;
         case 3: RBR_SCATTER(3); break;
@@ -447,8 +596,28 @@ extern "C" int rbr_conv_bwd_cmat_scatter(const void* ids_raw, const uint8_t* mas
     return RBR_OK;
 }
 
-extern "C" int rbr_conv_bwd_cmat_finish(int what, const void* shadow_bf16, const void* packed, int64_t vocab, int64_t emb, int64_t filters,
-                                        int64_t ksize, int64_t padding_idx, float* table_grad, float* weight_grad, void* ws,
+extern "C" int rbr_conv_bwd_cmat_scatter(const void* ids_raw, const uint8_t* mask, int64_t n_docs, int64_t doc_len, int64_t vocab,
+                                         int64_t emb, int64_t filters, int64_t ksize, int64_t pad, int activation, const float* feat,
+                                         const int32_t* argmax, const float* feat_grad, int64_t feat_ld, float* bias_grad, int chunk,
+                                         void* ws, int64_t ws_bytes, int flags, void* stream) {
+    RBR_REQUIRE(ids_raw && feat && argmax && feat_grad && ws, RBR_EINVAL, "conv_bwd_cmat_scatter: null pointer");
+    RBR_REQUIRE(cmat_shape_ok(vocab, emb, filters, ksize), RBR_EUNSUPPORTED, "conv_bwd_cmat: shape outside the dense tensor-core backward");
+    RBR_REQUIRE(n_docs >= 0 && doc_len > 0 && pad >= 0 && feat_ld >= filters, RBR_EINVAL, "conv_bwd_cmat_scatter: bad sizes");
+    const CmatLayout l = cmat_layout(vocab, emb, filters, ksize);
+    RBR_REQUIRE(ws_bytes >= l.total, RBR_EWORKSPACE, "conv_bwd_cmat_scatter: workspace too small");
+    RBR_REQUIRE(chunk >= -1 && chunk < l.n_chunks, RBR_EINVAL, "conv_bwd_cmat_scatter: bad chunk");
+    if (n_docs == 0) return RBR_OK;
+    float* c32 = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + l.off_c32);
+    for (int64_t c = (chunk < 0 ? 0 : chunk); c < (chunk < 0 ? l.n_chunks : chunk + 1); ++c) {
+        const int rc = cmat_scatter_block(l, cmat_chunk(l, c), ids_raw, mask, n_docs, doc_len, pad, activation, feat, argmax, feat_grad, feat_ld,
+                                          bias_grad, c32, flags, stream);
+        if (rc != RBR_OK) return rc;
+    }
+    return RBR_OK;
+}
+
+extern "C" int rbr_conv_bwd_cmat_finish(int what, int chunk, const void* shadow_bf16, const void* packed, int64_t vocab, int64_t emb,
+                                        int64_t filters, int64_t ksize, int64_t padding_idx, float* table_grad, float* weight_grad, void* ws,
                                         int64_t ws_bytes, void* stream) {
     RBR_REQUIRE(ws && packed, RBR_EINVAL, "conv_bwd_cmat_finish: null pointer");
     RBR_REQUIRE(cmat_shape_ok(vocab, emb, filters, ksize), RBR_EUNSUPPORTED, "conv_bwd_cmat: shape outside the dense tensor-core backward");
@@ -463,11 +632,16 @@ extern "C" int rbr_conv_bwd_cmat_finish(int what, const void* shadow_bf16, const
     __nv_bfloat16* chl = reinterpret_cast<__nv_bfloat16*>(base + l.off_chl);
     float* dw = reinterpret_cast<float*>(base + l.off_dw);
     if (what & 1) {
-        const int64_t total = vocab * (l.HJp / 4);
-        int64_t blocks = (total + 255) / 256;
-        if (blocks > 148 * 16) blocks = 148 * 16;
-        cmat_split_kernel<<<(unsigned)blocks, 256, 0, s>>>(reinterpret_cast<float4*>(c32), vocab, (int)l.HJp, chl);
-        RBR_LAUNCH_CHECK("cmat_split_kernel");
+        RBR_REQUIRE(chunk >= -1 && chunk < l.n_chunks, RBR_EINVAL, "conv_bwd_cmat_finish: bad chunk");
+        for (int64_t c = (chunk < 0 ? 0 : chunk); c < (chunk < 0 ? l.n_chunks : chunk + 1); ++c) {
+            const CmatChunk k = cmat_chunk(l, c);
+            const int64_t total = vocab * (k.width / 4);
+            int64_t blocks = (total + 255) / 256;
+            if (blocks > 148 * 16) blocks = 148 * 16;
+            cmat_split_kernel<<<(unsigned)blocks, 256, 0, s>>>(reinterpret_cast<const float4*>(c32 + k.base), vocab, (int)k.width, (int)k.col_lo,
+                                                               (int)l.HJp, chl);
+            RBR_LAUNCH_CHECK("cmat_split_kernel");
+        }
     }
     if (what & 2) {
         RBR_REQUIRE(table_grad, RBR_EINVAL, "conv_bwd_cmat_finish: table part needs table_grad");

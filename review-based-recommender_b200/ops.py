@@ -380,19 +380,31 @@ class EncodeDocsFn(torch.autograd.Function):
                         ws_bytes, ctx.flags_l[s], sh), "rbr_conv_act_maxpool_bwd")
             return run
 
-        def dense_scatter_rows(lo, hi, with_bias):
+        def dense_scatter_chunk(i, c):
+            """Block c of conv i's coefficient matrix, one document side (run per side, possibly on two streams)."""
+            ws = cm_ws[i]
+            h, _, k = shapes[i]
+
             def run(s, sh):
                 ids, mask = ids_l[s], mask_l[s]
                 doc_len = ids.shape[-1]
                 n_docs = ids.numel() // doc_len
-                for i, ws in cm_ws.items():
-                    h, _, k = shapes[i]
-                    lib.check(lib.rbr_conv_bwd_cmat_scatter(
-                        _p(ids), _p(mask), n_docs, doc_len, vocab, emb, h, k, cfg["pads"][i], cfg["act"],
-                        feats[s].data_ptr() + 4 * cols[i], argmaxes[s].data_ptr() + 4 * cols[i], fgs[s].data_ptr() + 4 * cols[i],
-                        h_total, _p(g_b[i]) if with_bias else None, lo, hi, _p(ws), ws.numel(), ctx.flags_l[s], sh),
-                        "rbr_conv_bwd_cmat_scatter")
+                lib.check(lib.rbr_conv_bwd_cmat_scatter(
+                    _p(ids), _p(mask), n_docs, doc_len, vocab, emb, h, k, cfg["pads"][i], cfg["act"],
+                    feats[s].data_ptr() + 4 * cols[i], argmaxes[s].data_ptr() + 4 * cols[i], fgs[s].data_ptr() + 4 * cols[i],
+                    h_total, _p(g_b[i]), c, _p(ws), ws.numel(), ctx.flags_l[s], sh), "rbr_conv_bwd_cmat_scatter")
             return run
+
+        def dense_accumulate():
+            """Per conv and filter block: zero-fill the block (it then sits in L2), scatter every side into it, split it into the
+            bf16 hi|lo operand while it is still there."""
+            for i, ws in cm_ws.items():
+                h, _, k = shapes[i]
+                for c in range(lib.rbr_conv_bwd_cmat_chunks(vocab, emb, h, k)):
+                    lib.check(lib.rbr_conv_bwd_cmat_begin(c, vocab, emb, h, k, _p(ws), ws.numel(), _stream()), "rbr_conv_bwd_cmat_begin")
+                    per_side(dense_scatter_chunk(i, c))
+                    lib.check(lib.rbr_conv_bwd_cmat_finish(1, c, None, _p(ctx.packed[i]), vocab, emb, h, k, cfg["padding_idx"], None, None,
+                                                           _p(ws), ws.numel(), _stream()), "rbr_conv_bwd_cmat_finish")
 
         # the arena left the table slot un-zeroed because this backward writes every element of it (NgramFeat.encode decided)
         overwrite = bool(cfg.get("table_overwrite")) and need_table and arena is not None and id(cfg["table_param"]) in arena.no_zero
@@ -405,7 +417,7 @@ class EncodeDocsFn(torch.autograd.Function):
                 what |= 8
             for i, ws in cm_ws.items():
                 h, _, k = shapes[i]
-                lib.check(lib.rbr_conv_bwd_cmat_finish(what, _p(ctx.shadow), _p(ctx.packed[i]), vocab, emb, h, k, cfg["padding_idx"],
+                lib.check(lib.rbr_conv_bwd_cmat_finish(what, -1, _p(ctx.shadow), _p(ctx.packed[i]), vocab, emb, h, k, cfg["padding_idx"],
                                                        _p(g_table), _p(g_w[i]), _p(ws), ws.numel(), _stream()),
                           "rbr_conv_bwd_cmat_finish")
 
@@ -415,17 +427,9 @@ class EncodeDocsFn(torch.autograd.Function):
             if any_sparse:
                 per_side(sparse_part(True, not two_pass) if need_table else sparse_part(False, True))
             if cm_ws:
-                n_chunks = int(os.environ.get("RBR_CMAT_CHUNKS", "1"))
-                prezero = os.environ.get("RBR_CMAT_PREZERO") == "1"
-                for c in range(n_chunks):
-                    lo, hi = vocab * c // n_chunks, vocab * (c + 1) // n_chunks
-                    if prezero:                                        # timing experiment: C32 rows made L2-resident right before the atomics
-                        for i, ws in cm_ws.items():
-                            h, _, k = shapes[i]
-                            hjp = (h * k + 63) // 64 * 64
-                            ws[lo * hjp * 4:hi * hjp * 4].zero_()
-                    per_side(dense_scatter_rows(lo, hi, c == 0))
-                dense_finish((1 | 2) if need_table else 1)
+                dense_accumulate()
+                if need_table:
+                    dense_finish(2)
             if hook is not None:
                 hook(g_table)
             if any_sparse and two_pass:

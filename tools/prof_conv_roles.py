@@ -34,6 +34,12 @@ e0.record()
 ops.conv_act_maxpool(we.embedding.weight.detach(), ids, mask, w0, b0, 1, **args)
 e1.record()
 torch.cuda.synchronize()
+from torch.profiler import ProfilerActivity, profile
+with profile(activities=[ProfilerActivity.CUDA]) as prof:
+    for _ in range(20):
+        ops.conv_act_maxpool(we.embedding.weight.detach(), ids, mask, w0, b0, 1, **args)
+    torch.cuda.synchronize()
+durs = [ev.device_time for ev in prof.events() if ev.device_type.name == "CUDA" and "conv_tc2_kernel" in ev.name]
 n = 148
 out = np.zeros((n, 8), dtype=np.int64)
 lib.check(lib.rbr_debug_conv_tc2_prof(out.ctypes.data_as(ctypes.c_void_p), n), "prof")
@@ -44,4 +50,8 @@ def share(a, b):
 print(f"MMA warp (leaders)   total {np.median(lead[:, 0]):9.0f} clk | waits operands {share(lead[:, 1], lead[:, 0])} | waits accumulator {share(lead[:, 2], lead[:, 0])}")
 print(f"producer warp 0      total {np.median(out[:, 3]):9.0f} clk | waits ring slot {share(out[:, 4], out[:, 3])}")
 print(f"epilogue warp 0      total {np.median(out[:, 5]):9.0f} clk | waits accumulator {share(out[:, 6], out[:, 5])}")
+if durs:
+    med = float(np.median(durs))
+    print(f"conv_tc2_kernel alone, 20 back-to-back launches (CUPTI): median {med:.1f} us, min {min(durs):.1f} us "
+          f"-> {np.median(lead[:, 0]) / med / 1e3:.3f} GHz effective SM clock")
 print(f"clk per tile (MMA warp): {np.median(lead[:, 0] / np.maximum(lead[:, 7], 1)):.0f}")
