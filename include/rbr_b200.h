@@ -104,8 +104,8 @@ int rbr_conv_pack(const float* weight, int64_t emb, int64_t filters, int64_t ksi
  *   batches (NARRE pads every user / item to 10 reviews: all-padding "documents") are first scanned for documents without
  *   any unmasked token; those get act(bias) / arg-max 0 directly — exactly what the conv over their all-zero rows yields —
  *   and only the others are tiled onto the tensor cores.  Long-document batches (DeepCoNN) are scanned for each document's
- *   last unmasked token, and the 128-position tiles lying entirely in the padding tail are skipped (a position past the
- *   last token + 1 yields the bias again: neither the max nor its first position changes).                                */
+ *   last unmasked token, and the 128-position tiles lying entirely in the padding tail are skipped (every position from
+ *   len + pad on reads zero rows only and yields the bias again: neither the max nor its first position changes).                                */
 int64_t rbr_conv_fwd_workspace_bytes(int64_t n_docs);
 /* Tiling plan of the CTA-pair kernel for a shape (host-only, launches nothing; used by the CPU tests of the tiling logic):
  * out[0..15] = {available, passes, filters/pass, filters/CTA, 64-wide K blocks, K steps, gather4 groups per stage, stage bytes,

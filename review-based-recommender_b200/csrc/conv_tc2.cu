@@ -495,13 +495,17 @@ __global__ void __launch_bounds__(256) conv_doc_select_kernel(const IdView ids, 
 }
 
 // ---- long documents: tiles per document and a list sorted by tile count (descending) ------------------------------------
-// A position t > len (len = last unmasked token + 1) sees only zero rows: its conv output is the bias, the same value as at
-// position len + 1.  Covering positions 0 .. len + 1 therefore yields the same max and the same FIRST arg-max as covering all of
-// them: tiles beyond ceil(min(Lout, len + 2) / 128) are skipped.  ws layout (int32): [0] count, [16..80) bucket counts,
+// Position t reads tokens t - pad .. t - pad + k - 1, so every position t >= len + pad (len = last unmasked token + 1) sees only
+// zero rows: its conv output is the bias, the same value as at position len + pad.  Covering positions 0 .. len + pad therefore
+// yields the same max and the same FIRST arg-max as covering all of them: tiles beyond ceil(min(Lout, len + pad + 1) / 128) are
+// skipped.  (Tried on top of this and rejected: not staging the 32-row blocks / gather4 groups past a document's end inside its
+// last tile, with the epilogue ignoring those positions.  12-25 % fewer gather4s, but no faster: a producer warp's stage time is
+// its own 8-10 serial gather4 issues of ~100 cycles each, so dropping whole warps' groups shortens nothing, and any per-gather4
+// predicate or branch makes the compiler rebuild the uniform-register operands in front of every one — 25-35 % slower.)  ws layout (int32): [0] count, [16..80) bucket counts,
 // [80..144) bucket cursors, [256 ..) list, then tiles-per-entry, then tiles-per-document.
 constexpr int T2_WS_HDR = 256;
 __global__ void __launch_bounds__(256) conv_doc_tiles_count_kernel(const IdView ids, const uint8_t* __restrict__ mask, int64_t n_docs, int L,
-                                                                   int Lout, int32_t* __restrict__ ws) {
+                                                                   int Lout, int pad, int32_t* __restrict__ ws) {
     const int lane = threadIdx.x & 31;
     const int64_t d = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (d >= n_docs) return;
@@ -516,7 +520,7 @@ __global__ void __launch_bounds__(256) conv_doc_tiles_count_kernel(const IdView 
         const unsigned b = __ballot_sync(0xffffffffu, on);
         if (b) len = t0 + (32 - __clz(b));
     }
-    const int covered = min(Lout, len + 2);
+    const int covered = min(Lout, len + pad + 1);          // positions 0 .. len + pad (the first one over zero rows only)
     const int nt = max(1, (covered + T2_M - 1) / T2_M);
     if (lane == 0) {
         ws[T2_WS_HDR + 2 * n_docs + d] = nt;
@@ -697,7 +701,7 @@ int conv_tc2_dispatch(const __nv_bfloat16* shadow, int64_t vocab, int E, IdView 
         } else if (a.p.tpu > 1) {
             // long documents: skip the tiles that lie entirely in a document's padding tail
             RBR_CUDA(cudaMemsetAsync(w32, 0, T2_WS_HDR * 4, s));
-            conv_doc_tiles_count_kernel<<<(unsigned)((n_docs * 32 + 255) / 256), 256, 0, s>>>(ids, mask, n_docs, L, a.p.Lout, w32);
+            conv_doc_tiles_count_kernel<<<(unsigned)((n_docs * 32 + 255) / 256), 256, 0, s>>>(ids, mask, n_docs, L, a.p.Lout, a.p.pad, w32);
             RBR_LAUNCH_CHECK("conv_doc_tiles_count_kernel");
             conv_doc_tiles_scan_kernel<<<1, 32, 0, s>>>(w32, n_docs);
             RBR_LAUNCH_CHECK("conv_doc_tiles_scan_kernel");

@@ -196,6 +196,9 @@ def test_padding_tail_tiles_skipped_bitwise(L, k):
     w = (torch.rand(H, E, k, generator=gen) * 2 - 1) / (E * k) ** 0.5
     b = (torch.rand(H, generator=gen) * 2 - 1) * 0.1
     b[:H // 2] -= 1.0                                              # many units whose max is the padding value relu(bias) = 0
+    table[:, :] = table.abs()
+    w[:10] = -w[:10].abs()                                         # filters 0..9 answer < 0 on every window that holds a token: their
+    #                                                                max is the 0 of the FIRST all-padding position, len + pad
     lens = torch.randint(0, L + 1, (n,), generator=gen)
     edge = [0, 1, 2, 125, 126, 127, 128, 129, 130, 254, 255, 256, 257, L - 2, L - 1, L]
     lens[:len(edge)] = torch.tensor([min(e, L) for e in edge])
@@ -210,6 +213,10 @@ def test_padding_tail_tiles_skipped_bitwise(L, k):
                                          flags=fl))
     assert torch.equal(outs[0][0], outs[1][0])
     assert torch.equal(outs[0][1], outs[1][1])
+    pad = (k - 1) // 2
+    short = (lens > 0) & (lens + pad < L + 2 * pad - k + 1)
+    short[20] = False
+    assert torch.equal(outs[1][1][short.cuda()][:, :10].cpu().long(), (lens[short] + pad).unsqueeze(1).expand(-1, 10))
     # and with the mask derived from the ids (id != 0), the int32 staging path
     f3, a3 = ops.conv_act_maxpool(table.cuda(), ids.int().cuda(), None, w.cuda(), b.cuda(), (k - 1) // 2, precision="bf16",
                                   flags=ops.CONV_TC_PAIR_ONLY, mask_from_ids=True)
