@@ -160,6 +160,8 @@ int rbr_conv_act_maxpool_bwd(int precision, int activation, const void* table, c
  *   rbr_conv_bwd_cmat_scatter(side, c)    once per document side — the sides may run on different streams
  *   rbr_conv_bwd_cmat_finish(1, c)        splits the block into the bf16 hi|lo operand while it is still in L2
  * then rbr_conv_bwd_cmat_finish(2 / 4, -1) for the two gradients.  chunk = -1 means "every block" in all three calls.
+ * Bit 2 computes table rows [row_lo, row_hi) (cut on multiples of 128; 0, 0 = all): data-parallel training produces the
+ * gradient in row slices and starts the all-reduce of each slice while the next one is still being computed.
  * `ws`: rbr_conv_bwd_cmat_workspace_bytes() bytes that the CALLER ZERO-FILLS ONCE (the weight scratch is left zeroed again
  * by bit 4).
  * `what`: 1 = close the accumulation of block `chunk` (split C; required once per block after its scatters, before 2 / 4),
@@ -177,9 +179,9 @@ int rbr_conv_bwd_cmat_scatter(const void* ids, const uint8_t* mask, int64_t n_do
                               int64_t filters, int64_t ksize, int64_t pad, int activation, const float* feat,
                               const int32_t* argmax, const float* feat_grad, int64_t feat_ld, float* bias_grad, int chunk,
                               void* ws, int64_t ws_bytes, int flags, void* stream);
-int rbr_conv_bwd_cmat_finish(int what, int chunk, const void* shadow_bf16, const void* packed, int64_t vocab, int64_t emb,
-                             int64_t filters, int64_t ksize, int64_t padding_idx, float* table_grad, float* weight_grad, void* ws,
-                             int64_t ws_bytes, void* stream);
+int rbr_conv_bwd_cmat_finish(int what, int chunk, int64_t row_lo, int64_t row_hi, const void* shadow_bf16, const void* packed,
+                             int64_t vocab, int64_t emb, int64_t filters, int64_t ksize, int64_t padding_idx, float* table_grad,
+                             float* weight_grad, void* ws, int64_t ws_bytes, void* stream);
 
 /* ---- K8: the alternate encoder arch="HierPooling" ---------------------------------------------------------------------
  * Replaces HierPooling.forward (models/deepconn/layers.py:81-98: F.avg_pool1d(kernel k, stride 1) over time, then F.max_pool1d

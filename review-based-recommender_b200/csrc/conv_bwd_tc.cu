@@ -266,6 +266,7 @@ struct TableGemmArgs {
     int64_t padding_idx;
     float* table_grad;         // [vocab][E]
     int overwrite;             // 1: table_grad = tile (every row and column of the gradient is written, padding row = 0); 0: +=
+    int tile0;                 // first 128-token tile of this launch (the gradient can be produced in row slices)
 };
 
 __global__ void __launch_bounds__(CM_THREADS, 2)
@@ -279,7 +280,7 @@ cmat_table_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     const int stage_bytes = 16384 + b_bytes;
     const uint32_t bars = sbase + CM_STAGES_T * stage_bytes;            // full[S], empty[S], acc_full
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + CM_STAGES_T * stage_bytes + 8 * (2 * CM_STAGES_T + 1));
-    const int m0 = blockIdx.x * 128, n0 = blockIdx.y * a.NT;
+    const int m0 = ((int)blockIdx.x + a.tile0) * 128, n0 = blockIdx.y * a.NT;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < CM_STAGES_T; ++i) { mbar_init(bars + 8 * i, 1); mbar_init(bars + 8 * (CM_STAGES_T + i), 1); }
@@ -616,9 +617,9 @@ extern "C" int rbr_conv_bwd_cmat_scatter(const void* ids_raw, const uint8_t* mas
     return RBR_OK;
 }
 
-extern "C" int rbr_conv_bwd_cmat_finish(int what, int chunk, const void* shadow_bf16, const void* packed, int64_t vocab, int64_t emb,
-                                        int64_t filters, int64_t ksize, int64_t padding_idx, float* table_grad, float* weight_grad, void* ws,
-                                        int64_t ws_bytes, void* stream) {
+extern "C" int rbr_conv_bwd_cmat_finish(int what, int chunk, int64_t row_lo, int64_t row_hi, const void* shadow_bf16, const void* packed,
+                                        int64_t vocab, int64_t emb, int64_t filters, int64_t ksize, int64_t padding_idx, float* table_grad,
+                                        float* weight_grad, void* ws, int64_t ws_bytes, void* stream) {
     RBR_REQUIRE(ws && packed, RBR_EINVAL, "conv_bwd_cmat_finish: null pointer");
     RBR_REQUIRE(cmat_shape_ok(vocab, emb, filters, ksize), RBR_EUNSUPPORTED, "conv_bwd_cmat: shape outside the dense tensor-core backward");
     RBR_REQUIRE((what & ~15) == 0 && (what & 7) != 0, RBR_EINVAL,
@@ -655,6 +656,10 @@ extern "C" int rbr_conv_bwd_cmat_finish(int what, int chunk, const void* shadow_
         a.vocab = vocab; a.E = (int)emb; a.NT = (int)pl.NT; a.nkb = (int)(2 * l.HJp / 64); a.padding_idx = padding_idx;
         a.table_grad = table_grad;
         a.overwrite = (what & 8) ? 1 : 0;
+        if (row_lo == 0 && row_hi == 0) row_hi = vocab;
+        RBR_REQUIRE(row_lo >= 0 && row_lo < row_hi && row_hi <= vocab && row_lo % 128 == 0 && (row_hi % 128 == 0 || row_hi == vocab), RBR_EINVAL,
+                    "conv_bwd_cmat_finish: the table row range must be cut on multiples of 128 rows");
+        a.tile0 = (int)(row_lo / 128);
         const int smem = CM_STAGES_T * (16384 + (int)pl.NT * 128) + 8 * (2 * CM_STAGES_T + 1) + 16 + 1024;
         static bool attr = false;
         if (!attr) {
@@ -662,7 +667,7 @@ extern "C" int rbr_conv_bwd_cmat_finish(int what, int chunk, const void* shadow_
             attr = true;
         }
         RBR_REQUIRE(smem <= 116 * 1024, RBR_EUNSUPPORTED, "conv_bwd_cmat_finish: shared memory");
-        dim3 grid((unsigned)((vocab + 127) / 128), (unsigned)pl.n_tiles);
+        dim3 grid((unsigned)((row_hi - row_lo + 127) / 128), (unsigned)pl.n_tiles);
         cmat_table_gemm_kernel<<<grid, CM_THREADS, smem, s>>>(tmA, tmB, a);
         RBR_LAUNCH_CHECK("cmat_table_gemm_kernel");
     }

@@ -159,8 +159,10 @@ def enable_nvls_allreduce(model: torch.nn.Module, group=None, overlap: bool = Tr
                                                          st.side.cuda_stream), "rbr_multimem_allreduce_f32")
                 hdl.barrier(channel=3)
                 st.ev_done.record(st.side)
-            st.early = (lo, lo + cnt)
+            # called once per row slice of the table gradient (consecutive slices): the reduced range grows
+            st.early = (lo, lo + cnt) if st.early is None or st.early[1] != lo else (st.early[0], lo + cnt)
 
+        hook.accepts_slices = True           # may be called once per consecutive row slice of the table gradient
         ngram.table_grad_hook = hook
     return True
 
