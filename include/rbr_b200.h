@@ -119,9 +119,9 @@ int rbr_conv_act_maxpool_fwd(int precision, int activation, const void* table, c
                              int64_t pad, float* feat, int32_t* argmax, float* pool_raw, int64_t feat_ld,
                              void* ws, int64_t ws_bytes, int flags, void* stream);
 /* Timing experiments only.  With RBR_TC2_DEBUG=4 in the environment the CTA-pair conv kernel accumulates per-CTA cycle
- * counters; this copies out[cta][8] = {MMA warp total, its wait for operands, its wait for a free accumulator, producer warp 0
- * total, its wait for a free ring slot, epilogue warp 0 total, its wait for a finished accumulator, tiles} of the last launch
- * (synchronises the device). */
+ * counters; this copies out[cta][12] = {MMA warp total, its wait for operands, its wait for a free accumulator, producer warp 0
+ * total, its wait for a free ring slot, epilogue warp 0 total, its wait for a finished accumulator, tiles, epilogue warp 0's
+ * TMEM loads + column max, its per-document finalisation, 0, 0} of the last launch (synchronises the device). */
 int rbr_debug_conv_tc2_prof(int64_t* out, int n_ctas);
 
 /* ---- K2b: arg-max-sparse backward of K2 ------------------------------------------------------------

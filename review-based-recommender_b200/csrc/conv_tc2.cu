@@ -106,8 +106,9 @@ struct Tc2Args {
 
 // RBR_TC2_DEBUG bit 4: per-CTA cycle counters (timing experiments): [0] MMA warp total, [1] its wait on the ring (full), [2] its wait on
 // the accumulators (acc_empty), [3] producer warp 0 total, [4] its wait on the ring (empty), [5] epilogue warp 0 total, [6] its wait
-// on the accumulators (acc_full), [7] tiles
-__device__ long long g_tc2_prof[1024][8];
+// on the accumulators (acc_full), [7] tiles, [8] epilogue warp 0: TMEM loads + column max, [9] its document finalisation (named barrier
+// + stores)
+__device__ long long g_tc2_prof[1024][12];
 
 // list slot li (unit * D + slot) → document index
 __device__ __forceinline__ int64_t t2_doc_of(const int32_t* live, int64_t li) { return live ? (int64_t)__ldg(live + 1 + li) : li; }
@@ -369,8 +370,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const Tc2Args a) {
         int64_t uj = 0;
         int tt = -1, unt = pair_units > 0 ? step_tiles(0) : 0;
         const bool prof = (p.dbg & 4) != 0 && warp == 0;
-        long long pt0 = prof ? clock64() : 0, pw_accf = 0, pt;
+        long long pt0 = prof ? clock64() : 0, pw_accf = 0, pw_red = 0, pw_fin = 0, pt;
         for (int64_t g = 0; g < pair_tiles; ++g) {
+            if (prof && g > 0) pw_fin += clock64() - pt;
             if (++tt >= unt) { ++uj; tt = 0; unt = step_tiles(uj); }
             const int64_t unit = ci + uj * ctas_per_pass;
             const int buf = (int)(g & 1);
@@ -396,6 +398,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const Tc2Args a) {
             // Chunks are pulled out of TMEM MAXC at a time; the accumulator is handed back to the MMA warp as soon as the warp's
             // LAST chunk is in registers, i.e. before any reduction when all its chunks fit one group (8-warp mode, <= 4 chunks
             // per warp): the max-reduction then overlaps the MMAs of tile g+2 instead of delaying them.
+            if (prof) pt = clock64();
             for (int chg = chunk_lo; chg < chunk_hi; chg += MAXC) {
                 uint32_t v[MAXC][16];
 #pragma unroll
@@ -435,6 +438,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const Tc2Args a) {
                 __syncwarp();
                 if (lane == 0) mbar_arrive_cluster(bar_acce + 8 * buf, 0);
             }
+            if (prof) { pw_red += clock64() - pt; pt = clock64(); }
             if (tt == unt - 1) {
                 asm volatile("bar.sync 1, %0;" ::"n"(T2_EPI_THREADS) : "memory");
                 const int qps = p.mode_b ? p.S / 32 : 4;      // quadrants per document slot
@@ -459,7 +463,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const Tc2Args a) {
                 }
             }
         }
-        if (prof && lane == 0 && blockIdx.x < 1024) { g_tc2_prof[blockIdx.x][5] = clock64() - pt0; g_tc2_prof[blockIdx.x][6] = pw_accf; }
+        if (prof && lane == 0 && blockIdx.x < 1024) {
+            g_tc2_prof[blockIdx.x][5] = clock64() - pt0; g_tc2_prof[blockIdx.x][6] = pw_accf;
+            g_tc2_prof[blockIdx.x][8] = pw_red; g_tc2_prof[blockIdx.x][9] = pw_fin;
+        }
     }
     // teardown: neither CTA may free TMEM / exit while the pair's MMAs can still touch its shared or tensor memory
     tc_fence_before();
@@ -719,6 +726,9 @@ int conv_tc2_dispatch(const __nv_bfloat16* shadow, int64_t vocab, int E, IdView 
     const bool wide = ew_env ? atoi(ew_env) == 16 : (a.p.mode_b || a.p.Nb / 16 >= 9 || a.p.nkb <= 2);
     static const char* pw_env = getenv("RBR_TC2_PROD_WARPS");                   // timing experiments: 4 or 8
     const bool pw8 = pw_env ? atoi(pw_env) == 8 : false;      // measured: 8 producer warps = 4 (the floor is the TMA unit's row rate, not per-warp issue)
+    // (Tried and rejected: 20 epilogue warps = five column shares, so that Nb = 160 = 10 chunks splits 2,2,2,2,2 instead of 3,2,3,2 and
+    // the per-document finalisation waits less for the slowest warp.  NARRE conv 305 -> 340 us: the extra warps take issue slots
+    // from the producer warps, and gather issue is what bounds the kernel.)
 #define RBR_T2(KT_)                                                                                                   \
     return wide ? (pw8 ? tc2_launch<KT_, 16, 8>(tm, a, s) : tc2_launch<KT_, 16, 4>(tm, a, s))                          \
                 : (pw8 ? tc2_launch<KT_, 8, 8>(tm, a, s) : tc2_launch<KT_, 8, 4>(tm, a, s))
@@ -755,6 +765,6 @@ RBR_DEFINE_OOB_ACCESSOR(conv_tc2)
 extern "C" int rbr_debug_conv_tc2_prof(int64_t* out, int n_ctas) {
     if (!out || n_ctas < 1 || n_ctas > 1024) return RBR_EINVAL;
     RBR_CUDA(cudaDeviceSynchronize());
-    RBR_CUDA(cudaMemcpyFromSymbol(out, rbr::g_tc2_prof, sizeof(long long) * 8 * (size_t)n_ctas));
+    RBR_CUDA(cudaMemcpyFromSymbol(out, rbr::g_tc2_prof, sizeof(long long) * 12 * (size_t)n_ctas));
     return RBR_OK;
 }

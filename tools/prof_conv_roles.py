@@ -41,7 +41,7 @@ with profile(activities=[ProfilerActivity.CUDA]) as prof:
     torch.cuda.synchronize()
 durs = [ev.device_time for ev in prof.events() if ev.device_type.name == "CUDA" and "conv_tc2_kernel" in ev.name]
 n = 148
-out = np.zeros((n, 8), dtype=np.int64)
+out = np.zeros((n, 12), dtype=np.int64)
 lib.check(lib.rbr_debug_conv_tc2_prof(out.ctypes.data_as(ctypes.c_void_p), n), "prof")
 lead = out[0::2]
 print(f"{name}: launch {e0.elapsed_time(e1) * 1e3:.1f} us (with the pre-pass kernels); tiles per pair median {np.median(lead[:, 7]):.0f}")
@@ -54,4 +54,5 @@ if durs:
     med = float(np.median(durs))
     print(f"conv_tc2_kernel alone, 20 back-to-back launches (CUPTI): median {med:.1f} us, min {min(durs):.1f} us "
           f"-> {np.median(lead[:, 0]) / med / 1e3:.3f} GHz effective SM clock")
+print(f"epilogue warp 0      TMEM loads + column max {share(out[:, 8], out[:, 5])} | finalisation (barrier + stores) {share(out[:, 9], out[:, 5])}")
 print(f"clk per tile (MMA warp): {np.median(lead[:, 0] / np.maximum(lead[:, 7], 1)):.0f}")
