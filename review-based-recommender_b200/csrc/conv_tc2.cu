@@ -726,6 +726,8 @@ int conv_tc2_dispatch(const __nv_bfloat16* shadow, int64_t vocab, int E, IdView 
     const bool wide = ew_env ? atoi(ew_env) == 16 : (a.p.mode_b || a.p.Nb / 16 >= 9 || a.p.nkb <= 2);
     static const char* pw_env = getenv("RBR_TC2_PROD_WARPS");                   // timing experiments: 4 or 8
     const bool pw8 = pw_env ? atoi(pw_env) == 8 : false;      // measured: 8 producer warps = 4 (the floor is the TMA unit's row rate, not per-warp issue)
+    // (Tried and rejected: the column max as a transposed shuffle butterfly (24 shfl.bfly per 16 columns, value + first row carried
+    // along) instead of redux.sync + ballot: DeepCoNN conv 299 -> 361 us, NARRE 313 -> 380 us — the redux form is the cheap one.)
     // (Tried and rejected: 20 epilogue warps = five column shares, so that Nb = 160 = 10 chunks splits 2,2,2,2,2 instead of 3,2,3,2 and
     // the per-document finalisation waits less for the slowest warp.  NARRE conv 305 -> 340 us: the extra warps take issue slots
     // from the producer warps, and gather issue is what bounds the kernel.)
