@@ -183,8 +183,9 @@ __global__ void __launch_bounds__(256, 8) cmat_scatter_fast_kernel(const void* _
             const int n = n0 + u * dn;
             nn[u] = n < n_docs ? n : n_docs - 1;
             const int o = nn[u] * feat_ld + h;
-            const float y = __ldg(feat + o), gr = __ldg(feat_grad + o);
-            ts[u] = __ldg(argmax + o) - pad;
+            // streamed once: evict-first, so that they do not push the coefficient block the atomics land in out of L2
+            const float y = __ldcs(feat + o), gr = __ldcs(feat_grad + o);
+            ts[u] = __ldcs(argmax + o) - pad;
             const float d = relu ? (y > 0.f ? 1.f : 0.f) : (1.f - y * y);
             g[u] = n < n_docs ? gr * d : 0.f;
         }
