@@ -235,7 +235,7 @@ __global__ void __launch_bounds__(256) cmat_split_kernel(const float4* __restric
     for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += stride) {
         const int64_t r = q / q4;
         const int c = col_lo + (int)(q - r * q4) * 4;
-        const float4 v = __ldg(blk + q);
+        const float4 v = __ldcs(blk + q);                          // dead after this read
         const __nv_bfloat162 h01 = __floats2bfloat162_rn(v.x, v.y), h23 = __floats2bfloat162_rn(v.z, v.w);
         const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
         const __nv_bfloat162 l01 = __floats2bfloat162_rn(v.x - f01.x, v.y - f01.y), l23 = __floats2bfloat162_rn(v.z - f23.x, v.w - f23.y);
@@ -355,7 +355,7 @@ cmat_table_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                         if (!a.overwrite) o = *p;
                         o.x += keep * __uint_as_float(v[4 * q]); o.y += keep * __uint_as_float(v[4 * q + 1]);
                         o.z += keep * __uint_as_float(v[4 * q + 2]); o.w += keep * __uint_as_float(v[4 * q + 3]);
-                        *p = o;
+                        __stcs(p, o);                                   // streamed: keep Chl (read again by the weight GEMM) in L2 instead
                     }
                 }
             }
