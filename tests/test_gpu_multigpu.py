@@ -79,8 +79,12 @@ for overlap in (False, True):
         dist.barrier(); dist.destroy_process_group(); sys.exit(0)
     batch, ratings = synth.deepconn_batch(B, L, V, U, I, seed=100 + rank)
     batch, ratings = [t.cuda() for t in batch], ratings.cuda()
-    # expected: NCCL average of every rank's local gradients
+    # expected: NCCL average of every rank's LOCAL gradients — taken with the early-reduction hook detached: with it, backward
+    # already starts averaging the word-table slice on the side stream, and only allreduce_gradients() waits for that
+    hook = model.ngram.table_grad_hook
+    model.ngram.table_grad_hook = None
     step(model, batch, ratings)
+    model.ngram.table_grad_hook = hook
     flat = model.last_arena.flat
     expect = flat.detach().clone()
     dist.all_reduce(expect, op=dist.ReduceOp.AVG)
