@@ -328,11 +328,13 @@ def measure(ctx, name, args):
         hook_ = getattr(ngram_, "table_grad_hook", None)
         if ngram_ is not None:
             ngram_.table_grad_hook = None
+        torch.manual_seed(4321 + rank)                 # both steps draw the same dropout masks
         eager_step(model, *dev_batches[0], loss_fn, None)
         if ngram_ is not None:
             ngram_.table_grad_hook = hook_
         expect = model.last_arena.flat.detach().clone()
         dist.all_reduce(expect, op=dist.ReduceOp.AVG)
+        torch.manual_seed(4321 + rank)
         eager_step(model, *dev_batches[0], loss_fn, None)
         flat = model.last_arena.flat
         parallel.allreduce_gradients(model, compress=compress)
