@@ -481,17 +481,33 @@ __global__ void __launch_bounds__(256) conv_doc_select_kernel(const IdView ids, 
                                                               int32_t* __restrict__ live, const float* __restrict__ bias, int H, int act,
                                                               float* __restrict__ feat, int32_t* __restrict__ argmax,
                                                               float* __restrict__ pool_raw, int feat_ld) {
-    const int lane = threadIdx.x & 31;
+    __shared__ int s_any[8], s_base;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int64_t d = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (d >= n_docs) return;
     bool any = false;
-    for (int t = lane; t < L && !any; t += 32) {
-        const int64_t i = d * L + t;
-        any = mask ? (__ldg(mask + i) != 0) : (ld_id(ids, i) != 0);
+    if (d < n_docs) {
+        for (int t = lane; t < L && !any; t += 32) {
+            const int64_t i = d * L + t;
+            any = mask ? (__ldg(mask + i) != 0) : (ld_id(ids, i) != 0);
+        }
     }
     any = __any_sync(0xffffffffu, any);
+    // one list reservation per CTA (8 documents), not per document: the counter is a single address
+    if (lane == 0) s_any[w] = any ? 1 : 0;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int n = 0;
+        for (int i = 0; i < 8; ++i) n += s_any[i];
+        s_base = n ? atomicAdd(live, n) : 0;
+    }
+    __syncthreads();
+    if (d >= n_docs) return;
     if (any) {
-        if (lane == 0) live[1 + atomicAdd(live, 1)] = (int32_t)d;
+        if (lane == 0) {
+            int pos = s_base;
+            for (int i = 0; i < w; ++i) pos += s_any[i];
+            live[1 + pos] = (int32_t)d;
+        }
     } else {
         for (int h = lane; h < H; h += 32) {
             feat[d * feat_ld + h] = act_apply(act, __ldg(bias + h));
