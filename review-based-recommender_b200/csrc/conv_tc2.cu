@@ -550,18 +550,23 @@ __global__ void __launch_bounds__(256) conv_doc_tiles_count_kernel(const IdView 
         atomicAdd(ws + 16 + min(nt, 63), 1);
     }
 }
-__global__ void conv_doc_tiles_scan_kernel(int32_t* __restrict__ ws, int64_t n_docs) {
-    if (threadIdx.x == 0) {
-        int off = 0;
-        for (int b = 63; b >= 0; --b) { ws[80 + b] = off; off += ws[16 + b]; }       // longest documents first
-        ws[0] = (int32_t)n_docs;
-    }
-}
+// bucket offsets (longest documents first) are recomputed by every CTA from the 64 counters — cheaper than a scan launch; the
+// cursors [80..144) count within a bucket.  Thread 0 of CTA 0 also publishes the list's entry count where the conv kernel
+// reads it (just below the list).
 __global__ void __launch_bounds__(256) conv_doc_tiles_fill_kernel(int32_t* __restrict__ ws, int64_t n_docs) {
+    __shared__ int s_off[64];
+    if (threadIdx.x < 64) {
+        int off = 0;
+        for (int b = 63; b > (int)threadIdx.x; --b) off += ws[16 + b];
+        s_off[threadIdx.x] = off;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { ws[0] = (int32_t)n_docs; ws[T2_WS_HDR - 1] = (int32_t)n_docs; }
+    __syncthreads();
     const int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (d >= n_docs) return;
     const int nt = ws[T2_WS_HDR + 2 * n_docs + d];
-    const int pos = atomicAdd(ws + 80 + min(nt, 63), 1);
+    const int bkt = min(nt, 63);
+    const int pos = s_off[bkt] + atomicAdd(ws + 80 + bkt, 1);
     ws[T2_WS_HDR + pos] = (int32_t)d;
     ws[T2_WS_HDR + n_docs + pos] = nt;
 }
@@ -726,12 +731,9 @@ int conv_tc2_dispatch(const __nv_bfloat16* shadow, int64_t vocab, int E, IdView 
             RBR_CUDA(cudaMemsetAsync(w32, 0, T2_WS_HDR * 4, s));
             conv_doc_tiles_count_kernel<<<(unsigned)((n_docs * 32 + 255) / 256), 256, 0, s>>>(ids, mask, n_docs, L, a.p.Lout, a.p.pad, w32);
             RBR_LAUNCH_CHECK("conv_doc_tiles_count_kernel");
-            conv_doc_tiles_scan_kernel<<<1, 32, 0, s>>>(w32, n_docs);
-            RBR_LAUNCH_CHECK("conv_doc_tiles_scan_kernel");
             conv_doc_tiles_fill_kernel<<<(unsigned)((n_docs + 255) / 256), 256, 0, s>>>(w32, n_docs);
             RBR_LAUNCH_CHECK("conv_doc_tiles_fill_kernel");
-            // live[0] must be the count and live[1 + i] the list: the count is duplicated just below the list
-            RBR_CUDA(cudaMemcpyAsync(w32 + T2_WS_HDR - 1, w32, 4, cudaMemcpyDeviceToDevice, s));
+            // (live[0] must be the count and live[1 + i] the list: the fill kernel writes the count just below the list)
             a.live = w32 + T2_WS_HDR - 1;
             a.ntl = w32 + T2_WS_HDR + n_docs;
         }
