@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(256, IT > 2 ? 6 : 8) cmat_scatter_kernel(const
                                                               int K, int pad, int64_t v_lo, int64_t v_hi, const float* __restrict__ feat,
                                                               const int32_t* __restrict__ argmax, const float* __restrict__ feat_grad,
                                                               int feat_ld, int act, float* __restrict__ c32, int HJp,
-                                                              float* __restrict__ bias_grad, int dbg) {
+                                                              float* __restrict__ bias_grad) {
     // H = filters of this block (feat / argmax / feat_grad / bias_grad already point at its first filter), c32 = the block,
     // HJp = its row pitch
     extern __shared__ float bsum[];            // [H] CTA-partial bias gradient
@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(256, IT > 2 ? 6 : 8) cmat_scatter_kernel(const
         }
 #pragma unroll
         for (int u = 0; u < IT; ++u)
-            if (g[u] != 0.f && bias_grad && !(dbg & 2)) atomicAdd(bsum + h[u], g[u]);
+            if (g[u] != 0.f && bias_grad) atomicAdd(bsum + h[u], g[u]);
         for (int j0 = 0; j0 < taps; j0 += KU) {
             int row[IT][KU];                   // C row of tap j0 + jj of item u, or -1 (rows are < 2^31: cmat_shape_ok)
 #pragma unroll
@@ -132,7 +132,6 @@ __global__ void __launch_bounds__(256, IT > 2 ? 6 : 8) cmat_scatter_kernel(const
                     row[u][jj] = -1;
                     if (g[u] != 0.f && t >= 0 && t < L) {
                         const int64_t i = (int64_t)n[u] * L + t;
-                        if (dbg & 4) { row[u][jj] = (int)((unsigned)(i * 2654435761u) % (unsigned)v_hi); continue; }
                         const int64_t id = ld_id(ids, i);
                         if (ld_mask(ids, mask, i, id) && id >= v_lo && id < v_hi) row[u][jj] = (int)id;
                     }
@@ -141,7 +140,7 @@ __global__ void __launch_bounds__(256, IT > 2 ? 6 : 8) cmat_scatter_kernel(const
             for (int u = 0; u < IT; ++u)
 #pragma unroll
                 for (int jj = 0; jj < KU; ++jj)
-                    if (row[u][jj] >= 0 && (!(dbg & 1) || g[u] == 12345.f))
+                    if (row[u][jj] >= 0)
                         atomicAdd(c32 + (int64_t)row[u][jj] * HJp + h[u] * K + j0 + jj, g[u]);      // no return value: RED.E.ADD.F32
         }
     }
@@ -163,7 +162,7 @@ __global__ void __launch_bounds__(256, 8) cmat_scatter_fast_kernel(const void* _
                                                                    int L, int H, int pad, int v_lo, int v_hi, const float* __restrict__ feat,
                                                                    const int32_t* __restrict__ argmax, const float* __restrict__ feat_grad,
                                                                    int feat_ld, int act, float* __restrict__ c32, int HJp,
-                                                                   float* __restrict__ bias_grad, int dbg) {
+                                                                   float* __restrict__ bias_grad) {
     extern __shared__ float bsum[];            // [H] CTA-partial bias gradient
     for (int i = threadIdx.x; i < H; i += blockDim.x) bsum[i] = 0.f;
     __syncthreads();
@@ -213,7 +212,7 @@ __global__ void __launch_bounds__(256, 8) cmat_scatter_fast_kernel(const void* _
             bacc += g[u];
 #pragma unroll
             for (int j = 0; j < KT; ++j)
-                if (row[u][j] >= 0 && !(dbg & 1)) atomicAdd(c32 + ((uint32_t)row[u][j] * (uint32_t)HJp + (uint32_t)(hk + j)), g[u]);
+                if (row[u][j] >= 0) atomicAdd(c32 + ((uint32_t)row[u][j] * (uint32_t)HJp + (uint32_t)(hk + j)), g[u]);
         }
     }
     if (bias_grad) {
@@ -547,8 +546,6 @@ static int cmat_scatter_block(const CmatLayout& l, const CmatChunk& k, const voi
     const int pitch = (int)k.width;
     const int64_t total = n_docs * filters;
     RBR_REQUIRE(total < (1ll << 31) - (1ll << 24), RBR_EUNSUPPORTED, "conv_bwd_cmat_scatter: n_docs * filters must stay below 2^31");
-    static const char* dbg_env = getenv("RBR_SCATTER_DEBUG");       // timing experiments only (results wrong): 1 no REDs, 2 no bias, 4 no id loads
-    const int dbg = dbg_env ? atoi(dbg_env) : 0;
     // fast path: 32-bit indices everywhere, k in {1, 3, 5}, and a grid whose thread count is a multiple of the block's filters
     {
         int64_t g = filters, r = 256;
@@ -568,7 +565,7 @@ static int cmat_scatter_block(const CmatLayout& l, const CmatChunk& k, const voi
 #define RBR_SF(KT, I32, MM)                                                                                                              \
     cmat_scatter_fast_kernel<KT, IT, I32, MM><<<(unsigned)blocks, 256, (size_t)filters * 4, as_stream(stream)>>>(                        \
         ids_raw, mask, (int)n_docs, (int)doc_len, (int)filters, (int)pad, 0, (int)vocab, feat, argmax, feat_grad, (int)feat_ld,          \
-        activation, c32p, pitch, bias_grad, dbg)
+        activation, c32p, pitch, bias_grad)
 #define RBR_SF_K(I32, MM)                                                                     \
     do {                                                                                      \
         if (ksize == 1) RBR_SF(1, I32, MM); else if (ksize == 3) RBR_SF(3, I32, MM); else RBR_SF(5, I32, MM); \
@@ -586,7 +583,7 @@ static int cmat_scatter_block(const CmatLayout& l, const CmatChunk& k, const voi
 #define RBR_SCATTER(KT)                                                                                                                      \
     cmat_scatter_kernel<KT, 2><<<(unsigned)blocks, 256, (size_t)filters * 4, as_stream(stream)>>>(                                           \
         id_view(ids_raw, flags), mask, n_docs, (int)doc_len, (int)filters, (int)ksize, (int)pad, 0, vocab, feat, argmax, feat_grad, (int)feat_ld, \
-        activation, c32p, pitch, bias_grad, dbg)
+        activation, c32p, pitch, bias_grad)
     switch (ksize) {
         case 1: RBR_SCATTER(1); break;
         case 3: RBR_SCATTER(3); break;

@@ -1,5 +1,6 @@
-"""Timing harness for cmat_scatter_kernel on synthetic NARRE / DeepCoNN shaped inputs (L2 flushed between launches).
-    [RBR_SCATTER_DEBUG=bits] python tools/ubench_scatter.py narre|deepconn"""
+"""Timing harness for the K2c coefficient scatter on synthetic NARRE / DeepCoNN shaped inputs (L2 flushed between launches).
+    [RBR_CMAT_CHUNKS=n] [UB_I64=1] [UB_FLUSH=write|read|none] python tools/ubench_scatter.py narre|deepconn
+(The numbers in profiles/r02_ub_scatter.txt with "dbg=1" were taken with a since-removed switch that disabled the atomics.)"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -45,5 +46,5 @@ def timeit(fn, reps=5):
         e0.record(); fn(); e1.record(); torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1) * 1e3)
     return min(ts[1:])
-print(f"flush={FLUSH} i64={I64} {name} chunks={nch} dbg={os.environ.get('RBR_SCATTER_DEBUG', '0')}: all blocks (zero-fill + scatter) {timeit(run):.1f} us | "
+print(f"flush={FLUSH} i64={I64} {name} chunks={nch}: all blocks (zero-fill + scatter) {timeit(run):.1f} us | "
       f"without the zero-fill {timeit(lambda: run(begin=False)):.1f} us | block 0 only: with fill {timeit(lambda: run(0)):.1f} us, without {timeit(lambda: run(0, begin=False)):.1f} us")
