@@ -107,6 +107,12 @@ int rbr_conv_pack(const float* weight, int64_t emb, int64_t filters, int64_t ksi
  *   last unmasked token, and the 128-position tiles lying entirely in the padding tail are skipped (every position from
  *   len + pad on reads zero rows only and yields the bias again: neither the max nor its first position changes).                                */
 int64_t rbr_conv_fwd_workspace_bytes(int64_t n_docs);
+/* The same plus room for the row-index table of a (doc_len, ksize, pad) conv: with a scratch of at least this size the call
+ * first resolves every staged position of every document to its word-table row (int32, -1 = reads as zeros: outside the document,
+ * masked out, or an id outside the table) in one coalesced pass, and the tensor-core kernel bulk-copies each tile's 136
+ * indices from that table instead of chasing ids and masks (HBM misses of several microseconds under its own gather traffic)
+ * on its critical path.  Results are identical with either scratch size.                                                        */
+int64_t rbr_conv_fwd_workspace_bytes2(int64_t n_docs, int64_t doc_len, int64_t ksize, int64_t pad);
 /* Tiling plan of the CTA-pair kernel for a shape (host-only, launches nothing; used by the CPU tests of the tiling logic):
  * out[0..15] = {available, passes, filters/pass, filters/CTA, 64-wide K blocks, K steps, gather4 groups per stage, stage bytes,
  * ring stages, resident weight bytes per CTA, short-document mode, documents per tile, document row stride, tiles per document,
@@ -121,7 +127,7 @@ int rbr_conv_act_maxpool_fwd(int precision, int activation, const void* table, c
 /* Timing experiments only.  With RBR_TC2_DEBUG=4 in the environment the CTA-pair conv kernel accumulates per-CTA cycle
  * counters; this copies out[cta][12] = {MMA warp total, its wait for operands, its wait for a free accumulator, producer warp 0
  * total, its wait for a free ring slot, epilogue warp 0 total, its wait for a finished accumulator, tiles, epilogue warp 0's
- * TMEM loads + column max, its per-document finalisation, 0, 0} of the last launch (synchronises the device). */
+ * TMEM loads + column max, its per-document finalisation, producer warp 0's per-tile prologue, 0} of the last launch (synchronises the device). */
 int rbr_debug_conv_tc2_prof(int64_t* out, int n_ctas);
 
 /* ---- K2b: arg-max-sparse backward of K2 ------------------------------------------------------------

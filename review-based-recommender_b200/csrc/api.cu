@@ -38,6 +38,7 @@ int conv_tc2_dispatch(const __nv_bfloat16* shadow, int64_t vocab, int E, IdView 
                       int H, int K, int pad, int act, float* feat, int32_t* argmax, float* preact, int feat_ld, void* ws, int64_t ws_bytes,
                       cudaStream_t s);
 int64_t conv_tc2_select_bytes(int64_t n_docs);
+int64_t conv_tc2_workspace_bytes(int64_t n_docs, int64_t L, int64_t K, int64_t pad);
 
 int oob_consume_embed(cudaStream_t, unsigned int*);
 int oob_consume_conv_fp32(cudaStream_t, unsigned int*);
@@ -55,6 +56,9 @@ int oob_consume_datt(cudaStream_t, unsigned int*);
 using namespace rbr;
 
 extern "C" int64_t rbr_conv_fwd_workspace_bytes(int64_t n_docs) { return conv_tc2_select_bytes(n_docs); }
+extern "C" int64_t rbr_conv_fwd_workspace_bytes2(int64_t n_docs, int64_t doc_len, int64_t ksize, int64_t pad) {
+    return conv_tc2_workspace_bytes(n_docs, doc_len, ksize, pad);
+}
 
 extern "C" int rbr_version(void) { return 100; }   // 0.1.0
 

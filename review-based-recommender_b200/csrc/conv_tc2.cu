@@ -25,17 +25,27 @@
 
 namespace rbr {
 
-constexpr int T2_SMEM_MAX = 232448;        // 227 KB opt-in dynamic shared memory per CTA
 constexpr int T2_M = 128;                  // positions per CTA tile (UMMA M = 256 over the pair)
 // Epilogue warps EW (template parameter of the kernel): 8 or 16 = 2 or 4 per TMEM lane quadrant, each reducing a share of
 // the 16-column chunks.  The max-reduction is a chain of fixed-latency warp ops: 16 warps hide it when there is a lot of it
 // per tile relative to the MMA/gather work (many filter chunks, short documents = per-tile finalisation, or a narrow
 // embedding = few K blocks per tile), 8 leave more issue slots to the MMA warp.
-// Warp roles: [0, EW) epilogue, [EW, EW+4) TMA producers (TMA issue is serialised per warp), EW+4 = TMEM owner + MMA issuer.
+// Warp roles: [0, EW) epilogue, [EW, EW+PW) TMA producers (TMA issue is serialised per warp), EW+PW = TMEM owner + MMA issuer,
+// EW+PW+1 = index warp (resolves the table row of every staged tile row ahead of the producers).
 // Producer warps PW (template parameter): issuing one gather4 costs a warp ~100 cycles (the TMA unit accepts the instruction's
 // uniform-register operands serially per warp), so the 32 + halo gather4s of a K block are spread over PW warps; each
 // stages 128 / PW tile rows.
-constexpr int t2_threads(int ew, int pw) { return (ew + pw + 1) * 32; }
+constexpr int t2_threads(int ew, int pw) { return (ew + pw + 2) * 32; }
+constexpr int T2_IDX_BUFS = 3;               // index buffers at most (plan: nib = as many as fit without costing a ring stage, >= 1; the
+                                             // producers copy a tile's indices to registers at the top of the tile, so one buffer already
+                                             // lets the index warp finish tile g+1 while tile g streams — more only absorb jitter)
+constexpr int T2_IDX_AHEAD = 2;              // unit steps ahead of the index warp's cursor whose id / mask rows are prefetched into L2
+constexpr int T2_IDX_ROWS = 136;             // ints per index buffer (128 tile rows + 8 halo rows)
+constexpr int T2_SMEM_MAX = 232448;          // 227 KB opt-in dynamic shared memory per CTA
+// shared memory after the ring and the weights: bias, arg-max keys, nib index buffers (+ their 2 barriers each), barriers, TMEM slot
+constexpr int t2_tail_bytes(int Nb, int nib) {
+    return Nb * 4 + 8 + 2 * 4 * Nb * 8 + 16 + nib * (T2_IDX_ROWS * 4 + 16) + 8 * (2 * 16 + 5) + 16 + 16;
+}
 constexpr int T2_MIN_STAGES = 3;
 
 struct Tc2Plan {
@@ -54,7 +64,9 @@ struct Tc2Plan {
     int S;            // mode B: tile rows between consecutive documents = Lext rounded up to 32 (one document per epilogue warp row block)
     int64_t n_units;
     int tmem_cols, acc_stride;
-    int off_ring, off_w, off_bias, off_keys, off_bars, off_slot, smem_bytes;   // offsets from the 1024-aligned base
+    int nib;          // index buffers (1..T2_IDX_BUFS)
+    int RS;           // row-index table: int32 entries per document row (tpu * 128 + 8, or S with several documents per tile)
+    int off_ring, off_w, off_bias, off_keys, off_idx, off_bars, off_slot, smem_bytes;   // offsets from the 1024-aligned base
     int act;
     uint32_t boff[4 * 8];   // B-descriptor offset (16-byte units) of (K-step ks, tap j) inside a K block: [ks * 8 + j]
     int dbg;          // RBR_TC2_DEBUG bits (timing experiments only; results are wrong): 1 = skip the MMAs, 2 = skip the max-reduction
@@ -71,9 +83,13 @@ void tc2_pass_split(int64_t E, int64_t H, int64_t K, int64_t* P, int64_t* Nb) {
     if (K < 1 || K > 8) return;
     const int64_t epad16 = round_up(E, 16);
     const int64_t bytes_per_row = K * epad16 * 2;                    // one local filter row of B
-    const int64_t budget = T2_SMEM_MAX - 1024 - T2_MIN_STAGES * t2_stage_bytes((int)K) - 8192;
-    int64_t nl_max = budget / bytes_per_row / 8 * 8;
-    if (nl_max > 128) nl_max = 128;                                  // UMMA N <= 256
+    // the most local filters (multiple of 8, UMMA N = 2 * nl <= 256) that leave room for T2_MIN_STAGES ring stages and the tail
+    int64_t nl_max = 0;
+    for (int64_t nl = 128; nl >= 8; nl -= 8)
+        if (1024 + bytes_per_row * nl + T2_MIN_STAGES * t2_stage_bytes((int)K) + t2_tail_bytes((int)(2 * nl), 1) + 256 <= T2_SMEM_MAX) {
+            nl_max = nl;
+            break;
+        }
     if (nl_max < 8) return;
     const int64_t npad = round_up(H, 16);
     *P = (npad + 2 * nl_max - 1) / (2 * nl_max);
@@ -101,42 +117,22 @@ struct Tc2Args {
     // in its padding tail are skipped (conv_doc_tiles_* kernels; the list is sorted by tile count so that the two CTAs of a
     // pair, which advance in lockstep, get documents of equal length)
     const int32_t* ntl;
+    // optional row-index table (conv_rowidx_kernel): rowidx[doc][e] = table row staged for extended position e of the document
+    // (input position e - pad), or -1 = reads as zeros (outside the document, masked out, or an id outside the table); row n_docs
+    // is all -1.  With it a tile's 136 row indices are ONE contiguous run (or one run per document slot), and the index warp
+    // only issues bulk copies of them into the index buffers — no id / mask loads on the conv kernel's critical path.
+    const int32_t* rowidx;
     Tc2Plan p;
 };
 
 // RBR_TC2_DEBUG bit 4: per-CTA cycle counters (timing experiments): [0] MMA warp total, [1] its wait on the ring (full), [2] its wait on
 // the accumulators (acc_empty), [3] producer warp 0 total, [4] its wait on the ring (empty), [5] epilogue warp 0 total, [6] its wait
 // on the accumulators (acc_full), [7] tiles, [8] epilogue warp 0: TMEM loads + column max, [9] its document finalisation (named barrier
-// + stores)
+// + stores), [10] producer warp 0: per-tile prologue (row indices of the tile: ids, range checks, shuffles) before its first gather4
 __device__ long long g_tc2_prof[1024][12];
 
 // list slot li (unit * D + slot) → document index
 __device__ __forceinline__ int64_t t2_doc_of(const int32_t* live, int64_t li) { return live ? (int64_t)__ldg(live + 1 + li) : li; }
-
-// row r of the staged tile → (document, input position), or false = "reads as zeros"
-__device__ __forceinline__ bool t2_row_source(const Tc2Plan& p, int64_t n_units, int64_t n_live, const int32_t* live, int64_t unit, int tt,
-                                              int r, int64_t* doc, int* t_in) {
-    if (r >= p.rows || unit >= n_units) return false;
-    int64_t li;
-    int ext;
-    if (p.mode_b) {
-        const int q = r / p.S;
-        if (q >= p.D) return false;
-        li = unit * p.D + q;
-        ext = r - q * p.S;
-        if (ext >= p.Lext) return false;
-    } else {
-        li = unit;
-        ext = tt * T2_M + r;
-        if (ext >= p.Lext) return false;
-    }
-    if (li >= n_live) return false;
-    const int t = ext - p.pad;
-    if (t < 0 || t >= p.L) return false;
-    *doc = t2_doc_of(live, li);
-    *t_in = t;
-    return true;
-}
 
 template <int KT, int EW, int PW>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(t2_threads(EW, PW), 1)
@@ -144,7 +140,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const Tc2Args a) {
     constexpr int T2_PROD_WARPS = PW, ROWS_PW = T2_M / PW, G4_PW = ROWS_PW / 4;
     constexpr int T2_EPI_WARPS = EW, T2_EPI_SHARES = EW / 4, T2_EPI_THREADS = EW * 32;
     constexpr int MAXC = 1;   // TMEM chunks held in registers at once (2 or 4 with an earlier accumulator release measured slower: 0.34 / 0.38 vs 0.31 ms)
-    constexpr int T2_PROD_WARP0 = EW, T2_MMA_WARP = EW + T2_PROD_WARPS;
+    constexpr int T2_PROD_WARP0 = EW, T2_MMA_WARP = EW + T2_PROD_WARPS, T2_IDX_WARP = T2_MMA_WARP + 1;
     extern __shared__ uint8_t smem_raw[];
     const Tc2Plan& p = a.p;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -154,10 +150,12 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const Tc2Args a) {
     const uint32_t ring_s = sbase + p.off_ring, w_s = sbase + p.off_w;
     float* bias_s = reinterpret_cast<float*>(smem + p.off_bias);
     unsigned long long* keys_s = reinterpret_cast<unsigned long long*>(smem + p.off_keys);
+    int* idx_s = reinterpret_cast<int*>(smem + p.off_idx);
     const uint32_t bars = sbase + p.off_bars;
-    // barrier slots: full[nst] (used in the leader), empty[nst], acc_full[2], acc_empty[2] (used in the leader), w_ready
+    // barrier slots: full[nst] (used in the leader), empty[nst], acc_full[2], acc_empty[2] (used in the leader), w_ready,
+    // idx_full[nib] (32 index-warp lanes arrive), idx_empty[nib] (one arrival per producer warp)
     const uint32_t bar_full = bars, bar_empty = bars + 8 * p.nst, bar_accf = bars + 16 * p.nst, bar_acce = bar_accf + 16,
-                   bar_w = bar_acce + 16;
+                   bar_w = bar_acce + 16, bar_idxf = bar_w + 8, bar_idxe = bar_idxf + 8 * p.nib;
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + p.off_slot);
 
     const uint32_t rank = cluster_ctarank();
@@ -191,6 +189,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const Tc2Args a) {
         mbar_init(bar_accf, 1); mbar_init(bar_accf + 8, 1);
         mbar_init(bar_acce, 2 * T2_EPI_WARPS); mbar_init(bar_acce + 8, 2 * T2_EPI_WARPS);
         mbar_init(bar_w, 1);
+        for (int i = 0; i < p.nib; ++i) { mbar_init(bar_idxf + 8 * i, a.rowidx ? 1 : 32); mbar_init(bar_idxe + 8 * i, T2_PROD_WARPS); }
         fence_barrier_init();
     }
     for (int i = threadIdx.x; i < p.Nb; i += blockDim.x) bias_s[i] = (h0 + i < p.H) ? a.bias[h0 + i] : 0.f;
@@ -271,64 +270,44 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const Tc2Args a) {
             }
         }
         __syncwarp();
-    } else if (warp >= T2_PROD_WARP0) {
+    } else if (warp >= T2_PROD_WARP0 && warp < T2_MMA_WARP) {
         // =========================== TMA gather producers (4 warps per CTA) ===========================
-        // Producer warp pw stages tile rows 32pw..32pw+31: lane l resolves row 32pw+l once per tile (token id, or -1 = zero
-        // row), quads of lanes assemble the 4 row indices of a gather4 group with shuffles, and lanes 0,4,..,28 issue one
-        // gather4 each per K block (TMA issue is serialised per warp, hence four warps).  The k-1 halo rows (128..) belong
-        // to warp 0.  ids/mask of tile g+1 are fetched while tile g streams.
+        // Producer warp pw stages tile rows ROWS_PW·pw .. +ROWS_PW-1 (warp 0 also the k-1 halo rows 128..): it takes the tile's row
+        // indices (table row, or -1 = reads as zeros) from the index warp's shared-memory buffer and ONE elected lane issues the
+        // warp's gather4s of each K block as straight-line code with its operands in registers (TMA issue is serialised per warp,
+        // hence four warps; a per-lane issue loop serialises on the TMA unit accepting each instruction's uniform registers).
+        // Resolving the indices here (list -> document -> ids -> range checks, then 40 shuffles) was 30-36 % of a producer
+        // warp's time, all four warps at once at the top of every tile with the TMA unit running dry: hence the index warp.
         const int pw = warp - T2_PROD_WARP0;
         const int halo_groups = p.groups - 32;                      // 0 (k == 1), 1 or 2
-        const bool halo_lane = (pw == 0) && (lane < 4 * halo_groups);
-        int64_t id_next[2];
-        uint8_t ok_next[2];
-        auto prefetch_ids = [&](int64_t j, int tt) {
-            const int64_t unit = ci + j * ctas_per_pass;
-#pragma unroll
-            for (int i = 0; i < 2; ++i) {
-                id_next[i] = -1;
-                ok_next[i] = 0;
-                if (j >= pair_units || (i == 1 && !halo_lane) || (i == 0 && lane >= ROWS_PW)) continue;
-                const int r = (i == 0) ? pw * ROWS_PW + lane : T2_M + lane;
-                int64_t doc;
-                int t;
-                if (t2_row_source(p, n_units, n_live, a.live, unit, tt, r, &doc, &t)) {
-                    id_next[i] = ld_id(a.ids, doc * p.L + t);
-                    ok_next[i] = ld_mask(a.ids, a.mask, doc * p.L + t, id_next[i]) ? (uint8_t)1 : (uint8_t)0;
-                }
-            }
-        };
-        int stage = 0;
-        uint32_t ph = 0;
+        int stage = 0, ib = 0;
+        uint32_t ph = 0, iph = 0;
         bool w_checked = false;
         const uint32_t dst0 = ring_s + (uint32_t)(pw * G4_PW) * 512u;
         const uint32_t dst_halo = ring_s + 32u * 512u;
-        int64_t uj = 0;                     // unit step, tile within it, tiles of the step
-        int utt = 0, unt = pair_units > 0 ? step_tiles(0) : 0;
-        prefetch_ids(0, 0);
         const bool prof = (p.dbg & 4) != 0 && pw == 0;
         long long pt0 = prof ? clock64() : 0, pw_empty = 0, pt;
+        long long pw_pro = 0, pt_pro = 0;
         for (int64_t g = 0; g < pair_tiles; ++g) {
-            int mine[2];
-#pragma unroll
-            for (int i = 0; i < 2; ++i) {
-                mine[i] = -1;
-                if (ok_next[i]) {
-                    const int64_t id = id_next[i];
-                    if (id >= 0 && id < a.vocab) mine[i] = (int)id;
-                    else note_oob();
-                }
-            }
-            if (++utt >= unt) { ++uj; utt = 0; unt = uj < pair_units ? step_tiles(uj) : 0; }
-            prefetch_ids(uj, utt);
-            // every lane gets all 32 row indices of the warp (and the halo's 8): the issuing lane then has its operands in
-            // registers and the gather4s of a stage are straight-line code (a per-lane issue loop serialises on the TMA
-            // unit accepting each instruction's uniform registers: ~100 cycles per gather4)
+            if (prof) pt_pro = clock64();
+            mbar_wait(bar_idxf + 8 * ib, iph);
             int idx[ROWS_PW], hidx[8];
+            {
+                const int4* src = reinterpret_cast<const int4*>(idx_s + ib * T2_IDX_ROWS + pw * ROWS_PW);
 #pragma unroll
-            for (int i = 0; i < ROWS_PW; ++i) idx[i] = __shfl_sync(0xffffffffu, mine[0], i);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) hidx[i] = __shfl_sync(0xffffffffu, mine[1], i);
+                for (int gi = 0; gi < G4_PW; ++gi) {
+                    const int4 v = src[gi];
+                    idx[4 * gi] = v.x; idx[4 * gi + 1] = v.y; idx[4 * gi + 2] = v.z; idx[4 * gi + 3] = v.w;
+                }
+                const int4* hsrc = reinterpret_cast<const int4*>(idx_s + ib * T2_IDX_ROWS + T2_M);
+                const int4 h0v = hsrc[0], h1v = hsrc[1];
+                hidx[0] = h0v.x; hidx[1] = h0v.y; hidx[2] = h0v.z; hidx[3] = h0v.w;
+                hidx[4] = h1v.x; hidx[5] = h1v.y; hidx[6] = h1v.z; hidx[7] = h1v.w;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_idxe + 8 * ib);          // the buffer may be rewritten (tile g + nib)
+            if (++ib == p.nib) { ib = 0; iph ^= 1; }
+            if (prof) pw_pro += clock64() - pt_pro;
             for (int kb = 0; kb < p.nkb; ++kb) {
                 if (prof) pt = clock64();
                 mbar_wait(bar_empty + 8 * stage, ph ^ 1);
@@ -357,7 +336,196 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const Tc2Args a) {
                 if (++stage == p.nst) { stage = 0; ph ^= 1; }
             }
         }
-        if (prof && lane == 0 && blockIdx.x < 1024) { g_tc2_prof[blockIdx.x][3] = clock64() - pt0; g_tc2_prof[blockIdx.x][4] = pw_empty; }
+        if (prof && lane == 0 && blockIdx.x < 1024) {
+            g_tc2_prof[blockIdx.x][3] = clock64() - pt0; g_tc2_prof[blockIdx.x][4] = pw_empty; g_tc2_prof[blockIdx.x][10] = pw_pro;
+        }
+    } else if (warp == T2_IDX_WARP) {
+        // =========================== index warp: table row (or -1) of every staged row, a few tiles ahead of the producers ===========
+        // Lane l resolves tile rows l, 32 + l, 64 + l, 96 + l and halo row 128 + l (slots 0..4).  The resolution is pipelined over
+        // THREE tiles, each step one iteration after the loads it depends on were issued, so no load is waited for where it is issued:
+        //   stage A (tile g+2): schedule position -> list slot -> document index        (loads: live[], tile counts ntl[])
+        //   stage B (tile g+1): document index -> token id and mask byte                (loads: ids, mask)
+        //   stage C (tile g)  : id / mask byte -> table row or -1, written to the tile's index buffer
+        // Everything loaded stays RAW in registers (either id width, the mask byte, the list entry, a unit step's two tile counts)
+        // and is converted an iteration later.
+        if (a.rowidx) {
+            // ---- row-index table present: one elected lane copies each tile's indices (544 bytes) into the next index buffer ----
+            // Lane l of the warp holds the documents and the tile count of unit step jb + l (one coalesced read of the lists per 32
+            // unit steps); they reach the issuing code by shuffle, so no list load is waited for per tile.
+            const uint32_t idx_sa = sbase + p.off_idx;
+            const int nseg = p.mode_b ? (T2_IDX_ROWS + p.S - 1) / p.S : 1;
+            int32_t docq[4] = {0, 0, 0, 0};
+            int cnt = 1;
+            int ib = 0;
+            uint32_t iph = 0;
+            for (int64_t uj = 0; uj < pair_units; ++uj) {
+                if ((uj & 31) == 0) {
+                    const int64_t j = uj + lane;
+                    const int64_t unit = ci + j * ctas_per_pass;
+                    const bool uok = j < pair_units && unit < n_units;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int64_t li = p.mode_b ? unit * p.D + q : unit;
+                        docq[q] = (uok && q < p.D && li < n_live) ? (int32_t)t2_doc_of(a.live, li) : (int32_t)a.n_docs;
+                    }
+                    cnt = j < pair_units ? step_tiles(j) : 1;
+                }
+                const int src = (int)(uj & 31);
+                int32_t dq[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) dq[q] = __shfl_sync(0xffffffffu, docq[q], src);
+                const int unt = __shfl_sync(0xffffffffu, cnt, src);
+                for (int utt = 0; utt < unt; ++utt) {
+                    if (lane == 0) {
+                        mbar_wait(bar_idxe + 8 * ib, iph ^ 1);          // every producer warp has read this buffer's previous tile
+                        const uint32_t fb = bar_idxf + 8 * ib, dst = idx_sa + (uint32_t)(ib * T2_IDX_ROWS * 4);
+                        mbar_expect_tx(fb, (uint32_t)(T2_IDX_ROWS * 4));
+                        if (!p.mode_b) {
+                            bulk_g2s(dst, a.rowidx + (int64_t)dq[0] * p.RS + utt * T2_M, (uint32_t)(T2_IDX_ROWS * 4), fb);
+                        } else {
+                            for (int q = 0; q < nseg; ++q) {
+                                const int n = min(p.S, T2_IDX_ROWS - q * p.S);
+                                const int64_t d = q < 4 ? (q == 0 ? dq[0] : q == 1 ? dq[1] : q == 2 ? dq[2] : dq[3]) : a.n_docs;
+                                bulk_g2s(dst + (uint32_t)(q * p.S * 4), a.rowidx + d * p.RS, (uint32_t)(n * 4), fb);
+                            }
+                        }
+                    }
+                    if (++ib == p.nib) { ib = 0; iph ^= 1; }
+                }
+            }
+        } else {
+        constexpr int NS = 5;
+        const int halo_groups = p.groups - 32;
+        int row[NS], qb[NS], extb[NS];
+        bool rowok[NS];
+#pragma unroll
+        for (int i = 0; i < NS; ++i) {
+            row[i] = i * 32 + lane;
+            rowok[i] = i < 4 ? true : (lane < 4 * halo_groups && row[i] < p.rows);
+            qb[i] = 0; extb[i] = 0;
+            if (p.mode_b) {                                         // several documents per tile: slot and offset are tile-invariant
+                qb[i] = row[i] / p.S;
+                extb[i] = row[i] - qb[i] * p.S;
+                rowok[i] = rowok[i] && qb[i] < p.D && extb[i] < p.Lext;
+            }
+        }
+        // stage A state: schedule position (unit step, tile within it) and the step's raw tile counts
+        int uj = 0, utt = 0;
+        int32_t n0r = 0, n1r = 0;
+        auto load_counts = [&](int j) {
+            n0r = 0; n1r = 0;
+            if (a.ntl && j < pair_units) {
+                const int64_t li0 = ci_even + (int64_t)j * ctas_per_pass;
+                if (li0 < n_live) n0r = __ldg(a.ntl + li0);
+                if (li0 + 1 < n_live) n1r = __ldg(a.ntl + li0 + 1);
+            }
+        };
+        // The ids / mask of a batch come from HBM (a batch is read once per step), and under this kernel's gather traffic a miss
+        // takes several microseconds — longer than a tile.  So the id / mask rows of the unit T2_IDX_AHEAD unit steps ahead of
+        // the stage-A cursor are pulled into L2 when the cursor enters a new unit (a whole document row: 128-byte lines spread
+        // over the lanes), and stage B's loads are L2 hits.
+        const int idsz = a.ids.i32 ? 4 : 8;
+        auto prefetch_unit = [&](int j) {
+            const int64_t unit = ci + (int64_t)j * ctas_per_pass;
+            if (j >= pair_units || unit >= n_units) return;
+            for (int q = 0; q < p.D; ++q) {
+                const int64_t li = p.mode_b ? unit * p.D + q : unit;
+                if (li >= n_live) break;
+                const int64_t doc = t2_doc_of(a.live, li);
+                const char* ib0 = reinterpret_cast<const char*>(a.ids.p) + doc * p.L * idsz;
+                const char* ie = ib0 + (int64_t)p.L * idsz;
+                for (const char* c = reinterpret_cast<const char*>(reinterpret_cast<uintptr_t>(ib0) & ~(uintptr_t)127) + lane * 128; c < ie;
+                     c += 32 * 128)
+                    prefetch_l2(c);
+                if (a.mask) {
+                    const char* mb0 = reinterpret_cast<const char*>(a.mask) + doc * p.L;
+                    const char* me = mb0 + p.L;
+                    for (const char* c = reinterpret_cast<const char*>(reinterpret_cast<uintptr_t>(mb0) & ~(uintptr_t)127) + lane * 128; c < me;
+                         c += 32 * 128)
+                        prefetch_l2(c);
+                }
+            }
+        };
+        auto advance = [&]() {
+            int unt = p.tpu;
+            if (a.ntl) { unt = n0r > n1r ? n0r : n1r; unt = unt < 1 ? 1 : unt; }
+            if (++utt >= unt) { ++uj; utt = 0; load_counts(uj); prefetch_unit(uj + T2_IDX_AHEAD); }
+        };
+        // A -> B
+        int32_t docr[NS];                // document index: the raw list entry, or the slot itself without a list (n_docs < 2^31)
+        int tB[NS];
+        bool vB[NS];
+        auto stage_a = [&]() {
+            const int64_t unit = ci + (int64_t)uj * ctas_per_pass;
+            const bool unit_ok = uj < pair_units && unit < n_units;
+#pragma unroll
+            for (int i = 0; i < NS; ++i) {
+                const int64_t li = p.mode_b ? unit * p.D + qb[i] : unit;
+                const int ext = p.mode_b ? extb[i] : utt * T2_M + row[i];
+                const int t = ext - p.pad;
+                vB[i] = unit_ok && rowok[i] && ext < p.Lext && li < n_live && t >= 0 && t < p.L;
+                tB[i] = t;
+                docr[i] = (int32_t)li;
+                if (vB[i] && a.live) docr[i] = __ldg(a.live + 1 + li);
+            }
+        };
+        // B -> C
+        int2 rawid[NS];                  // int32 id in .x, or the two halves of an int64 id
+        uint8_t rawm[NS];
+        bool vC[NS];
+#pragma unroll
+        for (int i = 0; i < NS; ++i) { rawid[i] = make_int2(0, 0); rawm[i] = 0; vC[i] = false; }
+        auto stage_b = [&]() {
+#pragma unroll
+            for (int i = 0; i < NS; ++i) {
+                vC[i] = vB[i];
+                if (!vB[i]) continue;
+                const int64_t at = (int64_t)docr[i] * p.L + tB[i];
+                if (a.ids.i32) rawid[i].x = __ldg(reinterpret_cast<const int32_t*>(a.ids.p) + at);
+                else rawid[i] = __ldg(reinterpret_cast<const int2*>(a.ids.p) + at);
+                if (a.mask) rawm[i] = __ldg(a.mask + at);
+            }
+        };
+        for (int j = 1; j <= T2_IDX_AHEAD; ++j) prefetch_unit(j);
+        load_counts(0);
+        stage_a();                          // tile 0
+        stage_b();
+        advance();
+        stage_a();                          // tile 1
+        int ib = 0;
+        uint32_t iph = 0;
+        const bool prof = (p.dbg & 4) != 0;
+        long long pt0 = prof ? clock64() : 0, pw_wait = 0, pt;
+        for (int64_t g = 0; g < pair_tiles; ++g) {
+            int mine[NS];
+#pragma unroll
+            for (int i = 0; i < NS; ++i) {
+                mine[i] = -1;
+                if (vC[i]) {
+                    const int64_t id = a.ids.i32 ? (int64_t)rawid[i].x
+                                                 : (int64_t)(((unsigned long long)(uint32_t)rawid[i].y << 32) | (uint32_t)rawid[i].x);
+                    const bool ok = a.mask ? rawm[i] != 0 : (a.ids.mask_ids ? id != 0 : true);
+                    if (ok) {
+                        if (id >= 0 && id < a.vocab) mine[i] = (int)id;
+                        else note_oob();
+                    }
+                }
+            }
+            stage_b();                      // tile g + 1
+            advance();
+            stage_a();                      // tile g + 2
+            if (prof) pt = clock64();
+            mbar_wait(bar_idxe + 8 * ib, iph ^ 1);                  // every producer warp has read this buffer's previous tile
+            if (prof) pw_wait += clock64() - pt;
+            int* dst = idx_s + ib * T2_IDX_ROWS;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) dst[row[i]] = mine[i];
+            if (lane < 8) dst[T2_M + lane] = mine[4];
+            mbar_arrive(bar_idxf + 8 * ib);                         // 32 arrivals (release): the tile's indices are visible
+            if (++ib == p.nib) { ib = 0; iph ^= 1; }
+        }
+        if (prof && lane == 0 && blockIdx.x < 1024) g_tc2_prof[blockIdx.x][11] = clock64() - pt0 - pw_wait;
+        }
     } else {
         // =========================== epilogue (16 warps; warp w reads TMEM lanes 32(w&3)..+31 and reduces 1/4 of the column chunks:
         // the reduction is a chain of fixed-latency warp ops, so it is latency- not issue-bound and more warps hide it) ===========================
@@ -573,6 +741,37 @@ __global__ void __launch_bounds__(256) conv_doc_tiles_fill_kernel(int32_t* __res
 
 int64_t conv_tc2_select_bytes(int64_t n_docs) { return round_up((T2_WS_HDR + 3 * n_docs) * 4, 256); }
 
+// ---- row-index table: the table row (or -1) of every extended position of every document ------------------------------------
+// One thread per entry, coalesced over a document row.  Row n_docs (all -1) stands in for absent documents.
+__global__ void __launch_bounds__(256) conv_rowidx_kernel(const IdView ids, const uint8_t* __restrict__ mask, int64_t n_docs, int L, int pad,
+                                                          int Lext, int RS, int64_t vocab, int32_t* __restrict__ rowidx) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (n_docs + 1) * RS) return;
+    const int64_t d = i / RS;
+    const int e = (int)(i - d * RS), t = e - pad;
+    int32_t v = -1;
+    if (d < n_docs && e < Lext && t >= 0 && t < L) {
+        const int64_t at = d * L + t;
+        const int64_t id = ld_id(ids, at);
+        if (ld_mask(ids, mask, at, id)) {
+            if (id >= 0 && id < vocab) v = (int32_t)id;
+            else note_oob();
+        }
+    }
+    rowidx[i] = v;
+}
+static int tc2_rowidx_stride(int K, int L, int pad) {
+    const int Lext = L + 2 * pad, Lout = Lext - K + 1, S = (int)round_up(Lext, 32);
+    if (Lout < 1) return 0;
+    if (S + Lext <= T2_M + K - 1) return S;                          // several documents per tile (as tc2_make_plan decides)
+    return (Lout + T2_M - 1) / T2_M * T2_M + 8;
+}
+int64_t conv_tc2_workspace_bytes(int64_t n_docs, int64_t L, int64_t K, int64_t pad) {
+    int64_t b = conv_tc2_select_bytes(n_docs);
+    if (K >= 1 && K <= 8 && L >= 1 && L < (1 << 24) && pad >= 0 && pad < 64) b += (n_docs + 1) * tc2_rowidx_stride((int)K, (int)L, (int)pad) * 4;
+    return b;
+}
+
 static bool tc2_make_plan(int E, int H, int K, int L, int pad, int act, int64_t n_docs, Tc2Plan* out) {
     Tc2Plan p{};
     p.E = E; p.H = H; p.K = K; p.L = L; p.pad = pad; p.act = act;
@@ -610,11 +809,17 @@ static bool tc2_make_plan(int E, int H, int K, int L, int pad, int act, int64_t 
         for (int j = 0; j < 8; ++j) p.boff[ks * 8 + j] = (uint32_t)(ks * 2 * p.NL + j * p.C * p.NL);   // K-step = 2 chunk columns, tap = C
     p.acc_stride = p.Nb <= 128 ? 128 : 256;
     p.tmem_cols = 2 * p.acc_stride;
-    const int tail = p.Nb * 4 + 8 + 2 * 4 * p.Nb * 8 + 8 * (2 * 16 + 5) + 16;
-    int nst = (T2_SMEM_MAX - 1024 - p.w_bytes - tail - 256) / p.stage_bytes;
-    if (nst > 16) nst = 16;
+    p.RS = tc2_rowidx_stride(K, L, pad);
+    auto stages_with = [&](int nib) {
+        const int n = (T2_SMEM_MAX - 1024 - p.w_bytes - t2_tail_bytes(p.Nb, nib) - 256) / p.stage_bytes;
+        return n > 16 ? 16 : n;
+    };
+    const int nst = stages_with(1);
     if (nst < T2_MIN_STAGES) return false;
     p.nst = nst;
+    p.nib = 1;
+    while (p.nib < T2_IDX_BUFS && stages_with(p.nib + 1) == nst) ++p.nib;
+    const int idx_bytes = p.nib * T2_IDX_ROWS * 4;
     int off = 0;
     p.off_ring = off; off += nst * p.stage_bytes;
     p.off_w = off; off += p.w_bytes;
@@ -622,7 +827,9 @@ static bool tc2_make_plan(int E, int H, int K, int L, int pad, int act, int64_t 
     p.off_bias = off; off += p.Nb * 4;
     off = (off + 7) / 8 * 8;
     p.off_keys = off; off += 2 * 4 * p.Nb * 8;
-    p.off_bars = off; off += 8 * (2 * nst + 5);
+    off = (off + 15) / 16 * 16;
+    p.off_idx = off; off += idx_bytes;
+    p.off_bars = off; off += 8 * (2 * nst + 5 + 2 * p.nib);
     p.off_slot = off; off += 16;
     p.smem_bytes = off + 1024;                   // slack for the manual 1024-byte alignment of the base
     if (p.smem_bytes > T2_SMEM_MAX) return false;
@@ -689,7 +896,7 @@ int conv_tc2_dispatch(const __nv_bfloat16* shadow, int64_t vocab, int E, IdView 
                       int H, int K, int pad, int act, float* feat, int32_t* argmax, float* preact, int feat_ld, void* ws,
                       int64_t ws_bytes, cudaStream_t s) {
     Tc2Args a{};
-    if (vocab >= (1ll << 31) || !tc2_make_plan(E, H, K, L, pad, act, n_docs, &a.p)) return RBR_EUNSUPPORTED;
+    if (vocab >= (1ll << 31) || n_docs >= (1ll << 31) || !tc2_make_plan(E, H, K, L, pad, act, n_docs, &a.p)) return RBR_EUNSUPPORTED;
     {
         static const char* dbg = getenv("RBR_TC2_DEBUG");
         a.p.dbg = dbg ? atoi(dbg) : 0;
@@ -737,6 +944,16 @@ int conv_tc2_dispatch(const __nv_bfloat16* shadow, int64_t vocab, int E, IdView 
             a.live = w32 + T2_WS_HDR - 1;
             a.ntl = w32 + T2_WS_HDR + n_docs;
         }
+    }
+    a.rowidx = nullptr;
+    static const char* ri_env = getenv("RBR_TC2_ROWIDX");                       // timing experiments: 0 = index warp resolves ids itself
+    if (!(ri_env && atoi(ri_env) == 0) && ws && ws_bytes >= conv_tc2_workspace_bytes(n_docs, L, K, pad) &&
+        ws_bytes > conv_tc2_select_bytes(n_docs) && (reinterpret_cast<uintptr_t>(ws) & 15) == 0) {
+        int32_t* ri = reinterpret_cast<int32_t*>(reinterpret_cast<char*>(ws) + conv_tc2_select_bytes(n_docs));
+        const int64_t n = (n_docs + 1) * a.p.RS;
+        conv_rowidx_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(ids, mask, n_docs, L, pad, a.p.Lext, a.p.RS, vocab, ri);
+        RBR_LAUNCH_CHECK("conv_rowidx_kernel");
+        a.rowidx = ri;
     }
     a.vocab = vocab; a.ids = ids; a.mask = mask; a.n_docs = n_docs; a.wpack = umma_w2; a.bias = bias;
     a.feat = feat; a.argmax = argmax; a.preact = preact; a.gate = gate; a.gate_mode = gate_mode; a.feat_ld = feat_ld;

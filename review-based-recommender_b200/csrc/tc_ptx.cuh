@@ -215,6 +215,7 @@ __device__ __forceinline__ void tma_gather4_pair(uint32_t dst, const void* tmap,
         "r"(bar & 0xFEFFFFFFu)
         : "memory");
 }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
 }

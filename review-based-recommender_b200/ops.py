@@ -282,7 +282,8 @@ class EncodeDocsFn(torch.autograd.Function):
             feat = torch.empty(n_docs, h_total, dtype=torch.float32, device=table.device)
             amax = torch.empty(n_docs, h_total, dtype=torch.int32, device=table.device)
             col = 0
-            ws_bytes = lib.rbr_conv_fwd_workspace_bytes(n_docs) if prec == PREC_BF16 else 0
+            ws_bytes = (max(lib.rbr_conv_fwd_workspace_bytes2(n_docs, doc_len, w.shape[2], pad) for w, pad in zip(weights, pads))
+                        if prec == PREC_BF16 else 0)
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=table.device) if ws_bytes else None
             for w, b, pk, pad in zip(weights, biases, packed, pads):
                 h, _, k = w.shape
@@ -810,8 +811,10 @@ def head_dropout_mask(batch: int, latent: int, drop_p: float, drop_seed: int, se
 def conv_act_maxpool(table: torch.Tensor, ids: torch.Tensor, mask: Optional[torch.Tensor], weight: torch.Tensor,
                      bias: torch.Tensor, pad: int, act: int = ACT_RELU, precision: str = "bf16",
                      shadow: Optional[torch.Tensor] = None, packed: Optional[torch.Tensor] = None, flags: int = 0,
-                     mask_from_ids: bool = False, select_docs: bool = True):
-    """One K2 launch: returns (feat [n_docs, H] fp32, argmax [n_docs, H] int32).  `flags`: CONV_TC_* kernel selection."""
+                     mask_from_ids: bool = False, select_docs: bool = True, row_index_table: bool = True):
+    """One K2 launch: returns (feat [n_docs, H] fp32, argmax [n_docs, H] int32).  `flags`: CONV_TC_* kernel selection.
+    `select_docs=False`: no scratch at all; `row_index_table=False`: scratch for the document selection only, so the kernel's
+    index warp resolves ids and masks itself (rbr_conv_fwd_workspace_bytes vs ..._bytes2)."""
     table = _req(table, torch.float32, "table")
     ids = _ids(ids, "ids")
     flags |= _id_flags(ids, mask, mask_from_ids)
@@ -826,7 +829,10 @@ def conv_act_maxpool(table: torch.Tensor, ids: torch.Tensor, mask: Optional[torc
     n_docs = ids.numel() // doc_len
     feat = torch.empty(n_docs, h, dtype=torch.float32, device=table.device)
     amax = torch.empty(n_docs, h, dtype=torch.int32, device=table.device)
-    ws_bytes = lib.rbr_conv_fwd_workspace_bytes(n_docs) if (prec == PREC_BF16 and select_docs) else 0
+    ws_bytes = 0
+    if prec == PREC_BF16 and select_docs:
+        ws_bytes = (lib.rbr_conv_fwd_workspace_bytes2(n_docs, doc_len, k, pad) if row_index_table
+                    else lib.rbr_conv_fwd_workspace_bytes(n_docs))
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=table.device) if ws_bytes else None
     lib.check(lib.rbr_conv_act_maxpool_fwd(prec, act, _p(table), _p(shadow), table.shape[0], emb, _p(ids), _p(mask), None, 0,
                                            n_docs, doc_len, _p(packed), _p(_req(bias, torch.float32, "bias")), h, k, pad,
@@ -881,12 +887,15 @@ class DattEncodeFn(torch.autograd.Function):
             amax = torch.empty(n_docs, h_total, dtype=torch.int32, device=dev)
             pre = torch.empty(n_docs, h_total, dtype=torch.float32, device=dev)
             col = 0
+            ws_bytes = (max(lib.rbr_conv_fwd_workspace_bytes2(n_docs, doc_len, w.shape[2], 0) for w, _, _, _ in convs)
+                        if prec == PREC_BF16 else 0)
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev) if ws_bytes else None
             for (w, b, gate, mode), pk in zip(convs, packed):
                 h, _, k = w.shape
                 lib.check(lib.rbr_conv_act_maxpool_fwd(prec, ACT_TANH, _p(table), _p(shadow), vocab, emb, _p(ids), None, _p(gate),
                                                        mode, n_docs, doc_len, _p(pk), _p(b), h, k, 0, feat.data_ptr() + 4 * col,
-                                                       amax.data_ptr() + 4 * col, pre.data_ptr() + 4 * col, h_total, None, 0, idf,
-                                                       _stream()), "rbr_conv_act_maxpool_fwd")
+                                                       amax.data_ptr() + 4 * col, pre.data_ptr() + 4 * col, h_total, _p(ws), ws_bytes,
+                                                       idf, _stream()), "rbr_conv_act_maxpool_fwd")
                 col += h
             saved += [ids, gate_l, gate_g, feat, amax, pre]
             feats.append(feat)
