@@ -537,6 +537,15 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const Tc2Args a) {
         const int chunk_hi = n_chunks * (share + 1) / T2_EPI_SHARES;
         int64_t uj = 0;
         int tt = -1, unt = pair_units > 0 ? step_tiles(0) : 0;
+        // Finalisation (a unit's last tile) is local to a warp GROUP: the warps of one column share that hold the rows of one
+        // document slot (all four quadrants with one document per tile, S / 32 of them with several).  Only they touch that
+        // slot's keys in those columns, so they synchronise among themselves on a named barrier of their own (one warp: no
+        // barrier) and write their share of the slot's outputs — the CTA-wide barrier made every warp wait for the slowest of
+        // 8 or 16 on every tile of a short-document batch.  The slot's document index is fetched from the list at the TOP of
+        // the unit's last tile: no dependent global load between the barrier and the stores.
+        const int qps = p.mode_b ? p.S / 32 : 4;              // quadrants (warps of a share) per document slot
+        const int grp_bar = 1 + share * (4 / qps) + quad / qps, grp_threads = qps * 32, grp_tid = (quad % qps) * 32 + lane;
+        int32_t fin_doc = -1;
         const bool prof = (p.dbg & 4) != 0 && warp == 0;
         long long pt0 = prof ? clock64() : 0, pw_accf = 0, pw_red = 0, pw_fin = 0, pt;
         for (int64_t g = 0; g < pair_tiles; ++g) {
@@ -547,14 +556,16 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const Tc2Args a) {
             // Pooled keys (value, ~position) live in shared memory per TMEM lane quadrant: entry [quad][column] is owned by exactly
             // one warp (quad = warp & 3, column chunk by share), so the running max over the tiles of a document is a plain
             // read-modify-write — no atomics (a 64-bit shared atomicMax is a CAS loop, and four quadrants contended for every
-            // column).  Double buffered by unit parity: ONE named barrier per unit (the buffer is next written two units
-            // later, i.e. after the following unit's barrier, which every thread passes only once it has finalised this unit).
+            // column).  Double buffered by unit parity: ONE (group) barrier per unit (the buffer is next written two units
+            // later, i.e. after the following unit's barrier, which a thread of the group passes only once all of them have
+            // finalised this unit).
             unsigned long long* keys_u = keys_s + (uj & 1) * (4 * p.Nb);
             // mode B packs documents on 32-row (warp) boundaries: a warp's rows all belong to one document slot
             const int slot = p.mode_b ? (quad * 32) / p.S : 0;
             const int t = p.mode_b ? m - slot * p.S : tt * T2_M + m;
             const int64_t my_li = p.mode_b ? unit * p.D + slot : unit;
             const bool valid = (t < p.Lout) && (slot < p.D) && (unit < n_units) && (my_li < n_live);
+            if (tt == unt - 1) fin_doc = (slot < p.D && unit < n_units && my_li < n_live) ? (int32_t)t2_doc_of(a.live, my_li) : -1;
             float row_gate = 1.f;
             if (a.gate_mode == 1 && valid) row_gate = a.gate[t2_doc_of(a.live, my_li) * p.L + t];
 
@@ -608,19 +619,18 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const Tc2Args a) {
             }
             if (prof) { pw_red += clock64() - pt; pt = clock64(); }
             if (tt == unt - 1) {
-                asm volatile("bar.sync 1, %0;" ::"n"(T2_EPI_THREADS) : "memory");
-                const int qps = p.mode_b ? p.S / 32 : 4;      // quadrants per document slot
-                for (int o = threadIdx.x; o < p.D * p.Nb; o += T2_EPI_THREADS) {
-                    const int sl = o / p.Nb, c = o - sl * p.Nb;
-                    const int64_t li = p.mode_b ? unit * p.D + sl : unit;
+                if (qps > 1) asm volatile("bar.sync %0, %1;" ::"r"(grp_bar), "r"(grp_threads) : "memory");
+                else __syncwarp();
+                const int q0 = (quad / qps) * qps;
+                for (int c = chunk_lo * 16 + grp_tid; c < chunk_hi * 16; c += grp_threads) {
                     unsigned long long key = 0ull;
-                    for (int q = sl * qps; q < sl * qps + qps && q < 4; ++q) {
+                    for (int q = q0; q < q0 + qps; ++q) {
                         const unsigned long long k2 = keys_u[q * p.Nb + c];
                         keys_u[q * p.Nb + c] = 0ull;
                         key = k2 > key ? k2 : key;
                     }
-                    if (unit < n_units && li < n_live && h0 + c < p.H) {
-                        const int64_t doc = t2_doc_of(a.live, li);
+                    if (fin_doc >= 0 && h0 + c < p.H) {
+                        const int64_t doc = fin_doc;
                         const float raw_v = __uint_as_float(ord2f((uint32_t)(key >> 32)));
                         const int tbest = (int)(0xFFFFFFFFu - (uint32_t)key);
                         const float gated = a.gate_mode == 2 ? raw_v * a.gate[doc] : raw_v;                 // per-doc gate > 0: monotone
@@ -742,9 +752,29 @@ __global__ void __launch_bounds__(256) conv_doc_tiles_fill_kernel(int32_t* __res
 int64_t conv_tc2_select_bytes(int64_t n_docs) { return round_up((T2_WS_HDR + 3 * n_docs) * 4, 256); }
 
 // ---- row-index table: the table row (or -1) of every extended position of every document ------------------------------------
-// One thread per entry, coalesced over a document row.  Row n_docs (all -1) stands in for absent documents.
+// One thread per entry, coalesced over a document row; a CTA walks documents blockIdx.x, blockIdx.x + gridDim.x, ...
+// Row n_docs (all -1) stands in for absent documents.
 __global__ void __launch_bounds__(256) conv_rowidx_kernel(const IdView ids, const uint8_t* __restrict__ mask, int64_t n_docs, int L, int pad,
                                                           int Lext, int RS, int64_t vocab, int32_t* __restrict__ rowidx) {
+    for (int64_t d = blockIdx.x; d <= n_docs; d += gridDim.x) {
+        for (int e = threadIdx.x; e < RS; e += 256) {
+            const int t = e - pad;
+            int32_t v = -1;
+            if (d < n_docs && e < Lext && t >= 0 && t < L) {
+                const int64_t at = d * L + t;
+                const int64_t id = ld_id(ids, at);
+                if (ld_mask(ids, mask, at, id)) {
+                    if (id >= 0 && id < vocab) v = (int32_t)id;
+                    else note_oob();
+                }
+            }
+            rowidx[d * RS + e] = v;
+        }
+    }
+}
+// the same for short rows (RS = 32 or 64, a multiple of 32): one thread per entry over the flat table
+__global__ void __launch_bounds__(256) conv_rowidx_short_kernel(const IdView ids, const uint8_t* __restrict__ mask, int64_t n_docs, int L,
+                                                                int pad, int Lext, int RS, int64_t vocab, int32_t* __restrict__ rowidx) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (n_docs + 1) * RS) return;
     const int64_t d = i / RS;
@@ -946,12 +976,21 @@ int conv_tc2_dispatch(const __nv_bfloat16* shadow, int64_t vocab, int E, IdView 
         }
     }
     a.rowidx = nullptr;
-    static const char* ri_env = getenv("RBR_TC2_ROWIDX");                       // timing experiments: 0 = index warp resolves ids itself
-    if (!(ri_env && atoi(ri_env) == 0) && ws && ws_bytes >= conv_tc2_workspace_bytes(n_docs, L, K, pad) &&
+    // Built for long documents only: with several short documents per tile the index warp keeps up on its own (its wait is 5-6 %
+    // of a producer warp's time either way, NARRE bench shape) and the pre-pass would cost more than it saves.
+    static const char* ri_env = getenv("RBR_TC2_ROWIDX");      // timing experiments: 0 = never, 2 = also for short documents
+    const int ri_mode = ri_env ? atoi(ri_env) : 1;
+    if (ri_mode != 0 && (ri_mode == 2 || !a.p.mode_b) && ws && ws_bytes >= conv_tc2_workspace_bytes(n_docs, L, K, pad) &&
         ws_bytes > conv_tc2_select_bytes(n_docs) && (reinterpret_cast<uintptr_t>(ws) & 15) == 0) {
         int32_t* ri = reinterpret_cast<int32_t*>(reinterpret_cast<char*>(ws) + conv_tc2_select_bytes(n_docs));
-        const int64_t n = (n_docs + 1) * a.p.RS;
-        conv_rowidx_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(ids, mask, n_docs, L, pad, a.p.Lext, a.p.RS, vocab, ri);
+        // short rows (several documents per tile): a thread block of 256 would idle on a 32- or 64-entry row — pack rows instead
+        const int64_t n_blocks = a.p.RS >= 128 ? n_docs + 1 : 0;
+        if (n_blocks == 0) {
+            conv_rowidx_short_kernel<<<(unsigned)(((n_docs + 1) * a.p.RS + 255) / 256), 256, 0, s>>>(ids, mask, n_docs, L, pad, a.p.Lext,
+                                                                                                   a.p.RS, vocab, ri);
+            RBR_LAUNCH_CHECK("conv_rowidx_short_kernel");
+        } else
+        conv_rowidx_kernel<<<(unsigned)(n_blocks < 148 * 64 ? n_blocks : 148 * 64), 256, 0, s>>>(ids, mask, n_docs, L, pad, a.p.Lext, a.p.RS, vocab, ri);
         RBR_LAUNCH_CHECK("conv_rowidx_kernel");
         a.rowidx = ri;
     }
