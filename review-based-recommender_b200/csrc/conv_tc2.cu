@@ -753,10 +753,19 @@ int64_t conv_tc2_select_bytes(int64_t n_docs) { return round_up((T2_WS_HDR + 3 *
 
 // ---- row-index table: the table row (or -1) of every extended position of every document ------------------------------------
 // One thread per entry, coalesced over a document row; a CTA walks documents blockIdx.x, blockIdx.x + gridDim.x, ...
-// Row n_docs (all -1) stands in for absent documents.
+// Row n_docs (all -1) stands in for absent documents.  With `tiles_ws` the pass also does conv_doc_tiles_count_kernel's job
+// (it sees every mask byte anyway): the document's tile count and its bucket counter.
 __global__ void __launch_bounds__(256) conv_rowidx_kernel(const IdView ids, const uint8_t* __restrict__ mask, int64_t n_docs, int L, int pad,
-                                                          int Lext, int RS, int64_t vocab, int32_t* __restrict__ rowidx) {
+                                                          int Lext, int RS, int64_t vocab, int32_t* __restrict__ rowidx, int Lout,
+                                                          int32_t* __restrict__ tiles_ws) {
+    __shared__ int s_len;
     for (int64_t d = blockIdx.x; d <= n_docs; d += gridDim.x) {
+        if (tiles_ws) {
+            __syncthreads();
+            if (threadIdx.x == 0) s_len = 0;
+            __syncthreads();
+        }
+        int len = 0;
         for (int e = threadIdx.x; e < RS; e += 256) {
             const int t = e - pad;
             int32_t v = -1;
@@ -764,11 +773,23 @@ __global__ void __launch_bounds__(256) conv_rowidx_kernel(const IdView ids, cons
                 const int64_t at = d * L + t;
                 const int64_t id = ld_id(ids, at);
                 if (ld_mask(ids, mask, at, id)) {
+                    len = t + 1;
                     if (id >= 0 && id < vocab) v = (int32_t)id;
                     else note_oob();
                 }
             }
             rowidx[d * RS + e] = v;
+        }
+        if (tiles_ws && d < n_docs) {
+            len = __reduce_max_sync(0xffffffffu, len);
+            if ((threadIdx.x & 31) == 0 && len > 0) atomicMax(&s_len, len);
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                const int covered = min(Lout, s_len + pad + 1);
+                const int nt = max(1, (covered + T2_M - 1) / T2_M);
+                tiles_ws[T2_WS_HDR + 2 * n_docs + d] = nt;
+                atomicAdd(tiles_ws + 16 + min(nt, 63), 1);
+            }
         }
     }
 }
@@ -950,6 +971,14 @@ int conv_tc2_dispatch(const __nv_bfloat16* shadow, int64_t vocab, int E, IdView 
     // all-padding documents are cheap to find and need no tensor-core work (short documents only: NARRE's padded review slots)
     a.live = nullptr;
     a.ntl = nullptr;
+    a.rowidx = nullptr;
+    // Row-index table: built for long documents only — with several short documents per tile the index warp keeps up on its own
+    // (its wait is 5-6 % of a producer warp's time either way, NARRE bench shape) and the pre-pass would cost more than it saves.
+    static const char* ri_env = getenv("RBR_TC2_ROWIDX");      // timing experiments: 0 = never, 2 = also for short documents
+    const int ri_mode = ri_env ? atoi(ri_env) : 1;
+    const bool want_ri = ri_mode != 0 && (ri_mode == 2 || !a.p.mode_b) && ws && ws_bytes >= conv_tc2_workspace_bytes(n_docs, L, K, pad) &&
+                         ws_bytes > conv_tc2_select_bytes(n_docs) && (reinterpret_cast<uintptr_t>(ws) & 15) == 0;
+    int32_t* ri = want_ri ? reinterpret_cast<int32_t*>(reinterpret_cast<char*>(ws) + conv_tc2_select_bytes(n_docs)) : nullptr;
     static const char* sel_env = getenv("RBR_TC2_SELECT");                      // timing experiments: 0 disables both selections
     const bool sel_on = !(sel_env && atoi(sel_env) == 0);
     if (sel_on && ws && ws_bytes >= conv_tc2_select_bytes(n_docs) && (mask || ids.mask_ids) && gate_mode == 0 && n_docs >= 64 &&
@@ -966,8 +995,15 @@ int conv_tc2_dispatch(const __nv_bfloat16* shadow, int64_t vocab, int E, IdView 
         } else if (a.p.tpu > 1) {
             // long documents: skip the tiles that lie entirely in a document's padding tail
             RBR_CUDA(cudaMemsetAsync(w32, 0, T2_WS_HDR * 4, s));
-            conv_doc_tiles_count_kernel<<<(unsigned)((n_docs * 32 + 255) / 256), 256, 0, s>>>(ids, mask, n_docs, L, a.p.Lout, a.p.pad, w32);
-            RBR_LAUNCH_CHECK("conv_doc_tiles_count_kernel");
+            if (want_ri) {                                   // the row-index pass counts the tiles as it goes
+                conv_rowidx_kernel<<<(unsigned)(n_docs + 1 < 148 * 64 ? n_docs + 1 : 148 * 64), 256, 0, s>>>(
+                    ids, mask, n_docs, L, pad, a.p.Lext, a.p.RS, vocab, ri, a.p.Lout, w32);
+                RBR_LAUNCH_CHECK("conv_rowidx_kernel");
+                a.rowidx = ri;
+            } else {
+                conv_doc_tiles_count_kernel<<<(unsigned)((n_docs * 32 + 255) / 256), 256, 0, s>>>(ids, mask, n_docs, L, a.p.Lout, a.p.pad, w32);
+                RBR_LAUNCH_CHECK("conv_doc_tiles_count_kernel");
+            }
             conv_doc_tiles_fill_kernel<<<(unsigned)((n_docs + 255) / 256), 256, 0, s>>>(w32, n_docs);
             RBR_LAUNCH_CHECK("conv_doc_tiles_fill_kernel");
             // (live[0] must be the count and live[1 + i] the list: the fill kernel writes the count just below the list)
@@ -975,23 +1011,17 @@ int conv_tc2_dispatch(const __nv_bfloat16* shadow, int64_t vocab, int E, IdView 
             a.ntl = w32 + T2_WS_HDR + n_docs;
         }
     }
-    a.rowidx = nullptr;
-    // Built for long documents only: with several short documents per tile the index warp keeps up on its own (its wait is 5-6 %
-    // of a producer warp's time either way, NARRE bench shape) and the pre-pass would cost more than it saves.
-    static const char* ri_env = getenv("RBR_TC2_ROWIDX");      // timing experiments: 0 = never, 2 = also for short documents
-    const int ri_mode = ri_env ? atoi(ri_env) : 1;
-    if (ri_mode != 0 && (ri_mode == 2 || !a.p.mode_b) && ws && ws_bytes >= conv_tc2_workspace_bytes(n_docs, L, K, pad) &&
-        ws_bytes > conv_tc2_select_bytes(n_docs) && (reinterpret_cast<uintptr_t>(ws) & 15) == 0) {
-        int32_t* ri = reinterpret_cast<int32_t*>(reinterpret_cast<char*>(ws) + conv_tc2_select_bytes(n_docs));
-        // short rows (several documents per tile): a thread block of 256 would idle on a 32- or 64-entry row — pack rows instead
-        const int64_t n_blocks = a.p.RS >= 128 ? n_docs + 1 : 0;
-        if (n_blocks == 0) {
+    if (want_ri && !a.rowidx) {
+        // short rows (several documents per tile): a thread block of 256 would idle on a 32- or 64-entry row — flat indexing instead
+        if (a.p.RS < 128) {
             conv_rowidx_short_kernel<<<(unsigned)(((n_docs + 1) * a.p.RS + 255) / 256), 256, 0, s>>>(ids, mask, n_docs, L, pad, a.p.Lext,
                                                                                                    a.p.RS, vocab, ri);
             RBR_LAUNCH_CHECK("conv_rowidx_short_kernel");
-        } else
-        conv_rowidx_kernel<<<(unsigned)(n_blocks < 148 * 64 ? n_blocks : 148 * 64), 256, 0, s>>>(ids, mask, n_docs, L, pad, a.p.Lext, a.p.RS, vocab, ri);
-        RBR_LAUNCH_CHECK("conv_rowidx_kernel");
+        } else {
+            conv_rowidx_kernel<<<(unsigned)(n_docs + 1 < 148 * 64 ? n_docs + 1 : 148 * 64), 256, 0, s>>>(
+                ids, mask, n_docs, L, pad, a.p.Lext, a.p.RS, vocab, ri, a.p.Lout, nullptr);
+            RBR_LAUNCH_CHECK("conv_rowidx_kernel");
+        }
         a.rowidx = ri;
     }
     a.vocab = vocab; a.ids = ids; a.mask = mask; a.n_docs = n_docs; a.wpack = umma_w2; a.bias = bias;
