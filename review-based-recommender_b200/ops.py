@@ -273,27 +273,43 @@ class EncodeDocsFn(torch.autograd.Function):
         shadow = cfg["shadow_fn"]() if prec == PREC_BF16 else None
         packed = [cfg["pack_fn"](i) for i in range(n_conv)]
         h_total = sum(w.shape[0] for w in weights)
-        feats, argmaxes = [], []
-        for ids, mask, fl in zip(ids_l, mask_l, flags_l):
+        feats, argmaxes, scratch = [], [], []
+        for ids, mask in zip(ids_l, mask_l):             # every buffer is allocated on the calling stream, before the fork
             doc_len = ids.shape[-1]
             n_docs = ids.numel() // doc_len
             if mask is not None and mask.numel() != ids.numel():
                 raise ValueError("rbr_b200: mask shape does not match token ids")
-            feat = torch.empty(n_docs, h_total, dtype=torch.float32, device=table.device)
-            amax = torch.empty(n_docs, h_total, dtype=torch.int32, device=table.device)
-            col = 0
+            feats.append(torch.empty(n_docs, h_total, dtype=torch.float32, device=table.device))
+            argmaxes.append(torch.empty(n_docs, h_total, dtype=torch.int32, device=table.device))
             ws_bytes = (max(lib.rbr_conv_fwd_workspace_bytes2(n_docs, doc_len, w.shape[2], pad) for w, pad in zip(weights, pads))
                         if prec == PREC_BF16 else 0)
-            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=table.device) if ws_bytes else None
-            for w, b, pk, pad in zip(weights, biases, packed, pads):
-                h, _, k = w.shape
-                lib.check(lib.rbr_conv_act_maxpool_fwd(
-                    prec, act, _p(table), _p(shadow), vocab, emb, _p(ids), _p(mask), None, 0, n_docs, doc_len, _p(pk),
-                    _p(_req(b, torch.float32, "conv bias")), h, k, pad, feat.data_ptr() + 4 * col, amax.data_ptr() + 4 * col,
-                    None, h_total, _p(ws), ws_bytes, fl, _stream()), "rbr_conv_act_maxpool_fwd")
-                col += h
-            feats.append(feat)
-            argmaxes.append(amax)
+            scratch.append((torch.empty(ws_bytes, dtype=torch.uint8, device=table.device) if ws_bytes else None, ws_bytes))
+        # The sides are independent: side s > 0 runs on its own stream, so its pre-pass kernels (document selection, row-index
+        # table: a few small launches) overlap the previous side's tensor-core kernel, which leaves room for them on every SM.
+        main = torch.cuda.current_stream()
+        side_streams = _side_streams(table.device, max(0, len(ids_l) - 1))
+        ev_fork = main.record_event() if len(ids_l) > 1 else None
+        for s, (ids, mask, fl) in enumerate(zip(ids_l, mask_l, flags_l)):
+            doc_len = ids.shape[-1]
+            n_docs = ids.numel() // doc_len
+            feat, amax, (ws, ws_bytes) = feats[s], argmaxes[s], scratch[s]
+            stream_s = main if s == 0 else side_streams[s - 1]
+            if s > 0:
+                stream_s.wait_event(ev_fork)
+            with torch.cuda.stream(stream_s):
+                sh = _stream(refresh=True)
+                col = 0
+                for w, b, pk, pad in zip(weights, biases, packed, pads):
+                    h, _, k = w.shape
+                    lib.check(lib.rbr_conv_act_maxpool_fwd(
+                        prec, act, _p(table), _p(shadow), vocab, emb, _p(ids), _p(mask), None, 0, n_docs, doc_len, _p(pk),
+                        _p(_req(b, torch.float32, "conv bias")), h, k, pad, feat.data_ptr() + 4 * col, amax.data_ptr() + 4 * col,
+                        None, h_total, _p(ws), ws_bytes, fl, sh), "rbr_conv_act_maxpool_fwd")
+                    col += h
+        for s in range(1, len(ids_l)):
+            main.wait_event(side_streams[s - 1].record_event())
+        _stream(refresh=True)
+        del scratch
         ctx.cfg, ctx.n_conv, ctx.n_sides = cfg, n_conv, len(ids_l)
         ctx.table, ctx.weights, ctx.biases = table, weights, biases
         ctx.shadow, ctx.packed = shadow, packed
