@@ -44,7 +44,7 @@ constexpr int T2_IDX_ROWS = 136;             // ints per index buffer (128 tile 
 constexpr int T2_SMEM_MAX = 232448;          // 227 KB opt-in dynamic shared memory per CTA
 // shared memory after the ring and the weights: bias, arg-max keys, nib index buffers (+ their 2 barriers each), barriers, TMEM slot
 constexpr int t2_tail_bytes(int Nb, int nib) {
-    return Nb * 4 + 8 + 2 * 4 * Nb * 8 + 16 + nib * (T2_IDX_ROWS * 4 + 16) + 8 * (2 * 16 + 5) + 16 + 16;
+    return Nb * 4 + 8 + 2 * 4 * Nb * 8 + 16 + nib * (T2_IDX_ROWS * 4 + 16) + 8 * (2 * 16 + 9) + 16 + 16;
 }
 constexpr int T2_MIN_STAGES = 3;
 
@@ -64,6 +64,7 @@ struct Tc2Plan {
     int S;            // mode B: tile rows between consecutive documents = Lext rounded up to 32 (one document per epilogue warp row block)
     int64_t n_units;
     int tmem_cols, acc_stride;
+    int nacc_log2;    // accumulator buffers in TMEM: 4 (filters per pass <= 128) or 2 — the MMA warp runs that many tiles ahead of the epilogue
     int nib;          // index buffers (1..T2_IDX_BUFS)
     int RS;           // row-index table: int32 entries per document row (tpu * 128 + 8, or S with several documents per tile)
     int off_ring, off_w, off_bias, off_keys, off_idx, off_bars, off_slot, smem_bytes;   // offsets from the 1024-aligned base
@@ -152,10 +153,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const Tc2Args a) {
     unsigned long long* keys_s = reinterpret_cast<unsigned long long*>(smem + p.off_keys);
     int* idx_s = reinterpret_cast<int*>(smem + p.off_idx);
     const uint32_t bars = sbase + p.off_bars;
-    // barrier slots: full[nst] (used in the leader), empty[nst], acc_full[2], acc_empty[2] (used in the leader), w_ready,
+    // barrier slots: full[nst] (used in the leader), empty[nst], acc_full[4], acc_empty[4] (used in the leader), w_ready,
     // idx_full[nib] (32 index-warp lanes arrive), idx_empty[nib] (one arrival per producer warp)
-    const uint32_t bar_full = bars, bar_empty = bars + 8 * p.nst, bar_accf = bars + 16 * p.nst, bar_acce = bar_accf + 16,
-                   bar_w = bar_acce + 16, bar_idxf = bar_w + 8, bar_idxe = bar_idxf + 8 * p.nib;
+    const uint32_t bar_full = bars, bar_empty = bars + 8 * p.nst, bar_accf = bars + 16 * p.nst, bar_acce = bar_accf + 32,
+                   bar_w = bar_acce + 32, bar_idxf = bar_w + 8, bar_idxe = bar_idxf + 8 * p.nib;
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + p.off_slot);
 
     const uint32_t rank = cluster_ctarank();
@@ -186,8 +187,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const Tc2Args a) {
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < p.nst; ++i) { mbar_init(bar_full + 8 * i, 2); mbar_init(bar_empty + 8 * i, 1); }
-        mbar_init(bar_accf, 1); mbar_init(bar_accf + 8, 1);
-        mbar_init(bar_acce, 2 * T2_EPI_WARPS); mbar_init(bar_acce + 8, 2 * T2_EPI_WARPS);
+        for (int i = 0; i < 4; ++i) { mbar_init(bar_accf + 8 * i, 1); mbar_init(bar_acce + 8 * i, 2 * T2_EPI_WARPS); }
         mbar_init(bar_w, 1);
         for (int i = 0; i < p.nib; ++i) { mbar_init(bar_idxf + 8 * i, a.rowidx ? 1 : 32); mbar_init(bar_idxe + 8 * i, T2_PROD_WARPS); }
         fence_barrier_init();
@@ -228,9 +228,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const Tc2Args a) {
                 const bool prof = (p.dbg & 4) != 0;
                 long long pt0 = prof ? clock64() : 0, pw_full = 0, pw_acce = 0, pt;
                 for (int64_t g = 0; g < pair_tiles; ++g) {
-                    const int buf = (int)(g & 1);
+                    const int buf = (int)(g & ((1 << p.nacc_log2) - 1));
                     if (prof) pt = clock64();
-                    mbar_wait(bar_acce + 8 * buf, (uint32_t)(((g >> 1) & 1) ^ 1));        // both CTAs' epilogues drained this buffer
+                    mbar_wait(bar_acce + 8 * buf, (uint32_t)(((g >> p.nacc_log2) & 1) ^ 1));        // both CTAs' epilogues drained this buffer
                     if (prof) pw_acce += clock64() - pt;
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + (uint32_t)(buf * p.acc_stride);
@@ -426,6 +426,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const Tc2Args a) {
         // over the lanes), and stage B's loads are L2 hits.
         const int idsz = a.ids.i32 ? 4 : 8;
         auto prefetch_unit = [&](int j) {
+            // (long documents only: with several documents per tile every tile is a new unit, and the list loads in here —
+            // waited for on the spot — cost the index warp more than the misses they avoid: NARRE shape, 6 % -> 36 % producer wait)
+            if (p.mode_b) return;
             const int64_t unit = ci + (int64_t)j * ctas_per_pass;
             if (j >= pair_units || unit >= n_units) return;
             for (int q = 0; q < p.D; ++q) {
@@ -552,7 +555,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const Tc2Args a) {
             if (prof && g > 0) pw_fin += clock64() - pt;
             if (++tt >= unt) { ++uj; tt = 0; unt = step_tiles(uj); }
             const int64_t unit = ci + uj * ctas_per_pass;
-            const int buf = (int)(g & 1);
+            const int buf = (int)(g & ((1 << p.nacc_log2) - 1));
             // Pooled keys (value, ~position) live in shared memory per TMEM lane quadrant: entry [quad][column] is owned by exactly
             // one warp (quad = warp & 3, column chunk by share), so the running max over the tiles of a document is a plain
             // read-modify-write — no atomics (a 64-bit shared atomicMax is a CAS loop, and four quadrants contended for every
@@ -570,7 +573,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const Tc2Args a) {
             if (a.gate_mode == 1 && valid) row_gate = a.gate[t2_doc_of(a.live, my_li) * p.L + t];
 
             if (prof) pt = clock64();
-            mbar_wait(bar_accf + 8 * buf, (uint32_t)((g >> 1) & 1));
+            mbar_wait(bar_accf + 8 * buf, (uint32_t)((g >> p.nacc_log2) & 1));
             if (prof) pw_accf += clock64() - pt;
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * p.acc_stride);
@@ -659,12 +662,32 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const Tc2Args a) {
 __global__ void __launch_bounds__(256) conv_doc_select_kernel(const IdView ids, const uint8_t* __restrict__ mask, int64_t n_docs, int L,
                                                               int32_t* __restrict__ live, const float* __restrict__ bias, int H, int act,
                                                               float* __restrict__ feat, int32_t* __restrict__ argmax,
-                                                              float* __restrict__ pool_raw, int feat_ld) {
+                                                              float* __restrict__ pool_raw, int feat_ld,
+                                                              int32_t* __restrict__ rowidx, int RS, int pad, int Lext, int64_t vocab) {
     __shared__ int s_any[8], s_base;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int64_t d = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     bool any = false;
-    if (d < n_docs) {
+    if (rowidx) {
+        // the pass sees every id / mask byte anyway: it also writes the document's row of the row-index table (see
+        // conv_rowidx_kernel; the warp of "document" n_docs writes the all -1 row that stands in for absent documents)
+        if (d <= n_docs) {
+            for (int e = lane; e < RS; e += 32) {
+                const int t = e - pad;
+                int32_t v = -1;
+                if (d < n_docs && e < Lext && t >= 0 && t < L) {
+                    const int64_t at = d * L + t;
+                    const int64_t id = ld_id(ids, at);
+                    if (ld_mask(ids, mask, at, id)) {
+                        any = true;
+                        if (id >= 0 && id < vocab) v = (int32_t)id;
+                        else note_oob();
+                    }
+                }
+                rowidx[d * RS + e] = v;
+            }
+        }
+    } else if (d < n_docs) {
         for (int t = lane; t < L && !any; t += 32) {
             const int64_t i = d * L + t;
             any = mask ? (__ldg(mask + i) != 0) : (ld_id(ids, i) != 0);
@@ -860,7 +883,8 @@ static bool tc2_make_plan(int E, int H, int K, int L, int pad, int act, int64_t 
     for (int ks = 0; ks < 4; ++ks)
         for (int j = 0; j < 8; ++j) p.boff[ks * 8 + j] = (uint32_t)(ks * 2 * p.NL + j * p.C * p.NL);   // K-step = 2 chunk columns, tap = C
     p.acc_stride = p.Nb <= 128 ? 128 : 256;
-    p.tmem_cols = 2 * p.acc_stride;
+    p.nacc_log2 = p.acc_stride == 128 ? 2 : 1;
+    p.tmem_cols = 512;
     p.RS = tc2_rowidx_stride(K, L, pad);
     auto stages_with = [&](int nib) {
         const int n = (T2_SMEM_MAX - 1024 - p.w_bytes - t2_tail_bytes(p.Nb, nib) - 256) / p.stage_bytes;
@@ -881,7 +905,7 @@ static bool tc2_make_plan(int E, int H, int K, int L, int pad, int act, int64_t 
     p.off_keys = off; off += 2 * 4 * p.Nb * 8;
     off = (off + 15) / 16 * 16;
     p.off_idx = off; off += idx_bytes;
-    p.off_bars = off; off += 8 * (2 * nst + 5 + 2 * p.nib);
+    p.off_bars = off; off += 8 * (2 * nst + 9 + 2 * p.nib);
     p.off_slot = off; off += 16;
     p.smem_bytes = off + 1024;                   // slack for the manual 1024-byte alignment of the base
     if (p.smem_bytes > T2_SMEM_MAX) return false;
@@ -952,6 +976,8 @@ int conv_tc2_dispatch(const __nv_bfloat16* shadow, int64_t vocab, int E, IdView 
     {
         static const char* dbg = getenv("RBR_TC2_DEBUG");
         a.p.dbg = dbg ? atoi(dbg) : 0;
+        static const char* nacc = getenv("RBR_TC2_ACC_BUFS");                    // timing experiments: 2 = two accumulator buffers always
+        if (nacc && atoi(nacc) == 2) a.p.nacc_log2 = 1;
     }
     if (K != 1 && K != 2 && K != 3 && K != 4 && K != 5 && K != 7) return RBR_EUNSUPPORTED;
     EncodeTiledFn enc = tc2_encoder();
@@ -973,11 +999,11 @@ int conv_tc2_dispatch(const __nv_bfloat16* shadow, int64_t vocab, int E, IdView 
     a.live = nullptr;
     a.ntl = nullptr;
     a.rowidx = nullptr;
-    // Row-index table: built for long documents only — with several short documents per tile the index warp keeps up on its own
-    // (its wait is 5-6 % of a producer warp's time either way, NARRE bench shape) and the pre-pass would cost more than it saves.
-    static const char* ri_env = getenv("RBR_TC2_ROWIDX");      // timing experiments: 0 = never, 2 = also for short documents
+    // Row-index table (written by the pre-pass that reads the ids / masks anyway: the tile-count pass for long documents, the
+    // document selection for short ones; a pass of its own otherwise).
+    static const char* ri_env = getenv("RBR_TC2_ROWIDX");      // timing experiments: 0 = never (the index warp resolves ids itself)
     const int ri_mode = ri_env ? atoi(ri_env) : 1;
-    const bool want_ri = ri_mode != 0 && (ri_mode == 2 || !a.p.mode_b) && ws && ws_bytes >= conv_tc2_workspace_bytes(n_docs, L, K, pad) &&
+    const bool want_ri = ri_mode != 0 && ws && ws_bytes >= conv_tc2_workspace_bytes(n_docs, L, K, pad) &&
                          ws_bytes > conv_tc2_select_bytes(n_docs) && (reinterpret_cast<uintptr_t>(ws) & 15) == 0;
     int32_t* ri = want_ri ? reinterpret_cast<int32_t*>(reinterpret_cast<char*>(ws) + conv_tc2_select_bytes(n_docs)) : nullptr;
     static const char* sel_env = getenv("RBR_TC2_SELECT");                      // timing experiments: 0 disables both selections
@@ -989,10 +1015,12 @@ int conv_tc2_dispatch(const __nv_bfloat16* shadow, int64_t vocab, int E, IdView 
             // short documents: drop the all-padding ones.  The list (count at [T2_WS_HDR - 1]) is read as live[0], live[1 + i]
             int32_t* live = w32 + T2_WS_HDR - 1;
             RBR_CUDA(cudaMemsetAsync(live, 0, 4, s));
-            conv_doc_select_kernel<<<(unsigned)((n_docs * 32 + 255) / 256), 256, 0, s>>>(ids, mask, n_docs, L, live, bias, H, act, feat,
-                                                                                     argmax, preact, feat_ld);
+            // (with the row-index table: one more warp, for the table's all -1 row)
+            conv_doc_select_kernel<<<(unsigned)(((n_docs + (want_ri ? 1 : 0)) * 32 + 255) / 256), 256, 0, s>>>(
+                ids, mask, n_docs, L, live, bias, H, act, feat, argmax, preact, feat_ld, want_ri ? ri : nullptr, a.p.RS, pad, a.p.Lext, vocab);
             RBR_LAUNCH_CHECK("conv_doc_select_kernel");
             a.live = live;
+            if (want_ri) a.rowidx = ri;
         } else if (a.p.tpu > 1) {
             // long documents: skip the tiles that lie entirely in a document's padding tail
             RBR_CUDA(cudaMemsetAsync(w32, 0, T2_WS_HDR * 4, s));
