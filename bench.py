@@ -453,42 +453,42 @@ def measure(ctx, name, args):
     # arena is collate work (the DataLoader's pin thread) and is done before the timed region, like pin_memory().
     e2e_steps, e2e_note, packed = None, "nn.Module forward/backward (eager), one H2D copy per input tensor (int64 ids + bool masks)", None
     if graphs is not None:
-        e2e_steps = [GraphedTrainStep(model, loss_fn, *dev_batches[j], warmup=1, pool=pool, post_backward=post, staged=True)
-                     for j in range(2)]
+        e2e_steps = [GraphedTrainStep(model, loss_fn, *dev_batches[j], warmup=1, pool=pool, post_backward=post, staged=True,
+                                      host_loss=True) for j in range(2)]
         packed = [e2e_steps[0].staged.pack(b, r) for b, r in host_batches]
         h2d_bytes = e2e_steps[0].staged.h2d_bytes
         e2e_note = ("rbr_b200.graphs.GraphedTrainStep(staged=True): CUDA-graph replay; one cudaMemcpyAsync per step from a pinned arena "
-                    "(int32 token ids, masks derived on the device) straight into the graph's static inputs")
-    free_ev = [None, None]          # replay of the object finished → its input buffers may be overwritten
-
+                    f"({str(e2e_steps[0].staged.token_dtype).replace('torch.', '')} token ids — the narrowest type the vocabulary of "
+                    f"{c['V']} allows —, masks derived on the device) straight into the graph's static inputs")
     def e2e_loop_graphed(n):
-        main = torch.cuda.current_stream()
-
+        # Two step objects ping-pong.  The main stream carries NOTHING but graph launches: the loss read-back is the last node
+        # of each graph (host_loss=True), and instead of a device-side event wait in front of a launch the HOST waits for the
+        # upload of step i+1 (0.15 ms, while step i runs 0.8 ms) before it launches graph i+1 — an event wait or a copy between
+        # two launches keeps the next graph from being staged during the current one (tools/e2e_probe.py: +30..70 us per step).
         def load(i):
-            o = e2e_steps[i & 1]
-            if free_ev[i & 1] is not None:
-                copy_stream.wait_event(free_ev[i & 1])
-            o.load_packed(packed[i % NB], stream=copy_stream)
+            e2e_steps[i & 1].load_packed(packed[i % NB], stream=copy_stream)
             ev = torch.cuda.Event()
             ev.record(copy_stream)
             return ev
-        nxt = load(0)
-        last = None
+        done = [None, None]
+        seen = 0.0
+        load(0).synchronize()
         for i in range(n):
-            ev = nxt
+            o = e2e_steps[i & 1]
+            o.replay()                                   # inputs of step i are in place (host-verified)
+            d = torch.cuda.Event()
+            d.record()
+            done[i & 1] = d
             if i + 1 < n:
-                nxt = load(i + 1)
-            main.wait_event(ev)
-            loss = e2e_steps[i & 1].replay()
-            loss_host[i & 1].copy_(loss.detach(), non_blocking=True)
-            done = torch.cuda.Event()
-            done.record()
-            free_ev[i & 1] = done
-            if last is not None:
-                last.synchronize()
-            last = done
-        if last is not None:
-            last.synchronize()
+                if done[(i + 1) & 1] is not None:
+                    done[(i + 1) & 1].synchronize()      # step i-1 finished: its loss is on the host, its input arena is free
+                    seen += float(e2e_steps[(i + 1) & 1].loss_host[0])
+                load(i + 1).synchronize()                # upload of step i+1 overlaps the replay of step i
+        for j in range(2):
+            if done[j] is not None:
+                done[j].synchronize()
+        loss_host[0] = float(e2e_steps[(n - 1) & 1].loss_host[0])
+        return seen
 
     e2e_loop = e2e_loop_graphed if e2e_steps is not None else e2e_loop_eager
     e2e_loop(W)
@@ -736,8 +736,9 @@ def measure(ctx, name, args):
                     "parity_note": PARITY_NOTE},
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                     "how": "pinned host buffers → H2D on a copy stream (prefetch depth 1) → " + e2e_note + " → "
-                           "loss read back to pinned host memory every step (asynchronously: the host consumes step i-1's loss while "
-                           "step i runs); wall clock, max over ranks",
+                           "loss copied to pinned host memory every step by the graph's last node (the host consumes step i-1's loss "
+                           "while step i runs, and waits for the upload of step i+1 before launching its graph, so the compute stream "
+                           "carries graph launches only); wall clock, max over ranks",
                     "h2d_bytes_per_step_reference_loop": h2d_ref},
             "gpu_launches": int(launches), "gpu_launches_per_step": launches / K,
             "clocks": sampler.summarise(samples, reasons), "roofline": roofline, "cpu_baseline": cpu_baseline,

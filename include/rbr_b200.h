@@ -48,6 +48,7 @@ extern "C" {
                                     default = chosen by shape                                                                  */
 #define RBR_CONV_BWD_SPARSE 8    /* backward: force the arg-max-sparse CUDA-core formulation                                   */
 #define RBR_IDS_I32 16           /* `ids` points to int32 token ids (staged input pipeline) instead of int64     */
+#define RBR_IDS_U16 64           /* `ids` points to uint16 token ids (staged input pipeline when the vocabulary has <= 65536 rows) */
 #define RBR_MASK_FROM_IDS 32     /* mask == NULL means mask = (ids != 0) — utils.py:30-42's get_mask — instead of "all true"   */
 
 int rbr_version(void);
@@ -98,7 +99,7 @@ int rbr_conv_pack(const float* weight, int64_t emb, int64_t filters, int64_t ksi
  *         the FIRST position attaining the max (nn.MaxPool1d tie rule);  pool_raw (optional, same shape):
  *         the pooled value before bias and activation, gate included (gate * conv_nobias(x) at the arg-max;
  *         needed by the backward of a gated conv).
- *   ids   int64 (torch.LongTensor) or, with RBR_IDS_I32 in `flags`, int32; RBR_MASK_FROM_IDS: see above.
+ *   ids   int64 (torch.LongTensor) or, with RBR_IDS_I32 / RBR_IDS_U16 in `flags`, int32 / uint16; RBR_MASK_FROM_IDS: see above.
  *   RBR_PREC_BF16 shapes outside both tensor-core kernels fall back to the fp32 kernel when `table` is given.
  *   ws / ws_bytes: optional scratch of rbr_conv_fwd_workspace_bytes(n_docs) bytes (NULL: none).  With it, short-document
  *   batches (NARRE pads every user / item to 10 reviews: all-padding "documents") are first scanned for documents without

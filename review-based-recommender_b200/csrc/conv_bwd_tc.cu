@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(256, IT > 2 ? 6 : 8) cmat_scatter_kernel(const
 // NARRE's 6.1 M items with every load hitting L2).  Here the grid size makes the thread count a multiple of H, so a thread keeps
 // ONE filter h for its whole life (bias partial in a register, documents advance by a constant, no division in the loop); all
 // indices are 32-bit; window positions are clamped instead of branched around; id width and mask source are template arguments.
-template <int KT, int IT, bool I32, int MM>       // MM: 0 = no mask, 1 = mask bytes, 2 = mask is (id != 0)
+template <int KT, int IT, int I32, int MM>       // I32: id width 0 = int64, 1 = int32, 2 = uint16;       // MM: 0 = no mask, 1 = mask bytes, 2 = mask is (id != 0)
 __global__ void __launch_bounds__(256, 8) cmat_scatter_fast_kernel(const void* __restrict__ ids_raw, const uint8_t* __restrict__ mask, int n_docs,
                                                                    int L, int H, int pad, int v_lo, int v_hi, const float* __restrict__ feat,
                                                                    const int32_t* __restrict__ argmax, const float* __restrict__ feat_grad,
@@ -197,7 +197,8 @@ __global__ void __launch_bounds__(256, 8) cmat_scatter_fast_kernel(const void* _
                 const int tc = min(max(t, 0), L - 1);
                 const int i = nn[u] * L + tc;
                 int id;
-                if (I32) id = __ldg(reinterpret_cast<const int32_t*>(ids_raw) + i);
+                if (I32 == 2) id = (int)__ldg(reinterpret_cast<const uint16_t*>(ids_raw) + i);
+                else if (I32 == 1) id = __ldg(reinterpret_cast<const int32_t*>(ids_raw) + i);
                 else {
                     const int64_t w = __ldg(reinterpret_cast<const int64_t*>(ids_raw) + i);
                     id = (w >= 0 && w < 0x7fffffffll) ? (int)w : -1;
@@ -561,7 +562,7 @@ static int cmat_scatter_block(const CmatLayout& l, const CmatChunk& k, const voi
             if (blocks > 148 * 8) blocks = 148 * 8;
             blocks = std::max<int64_t>(m, blocks / m * m);
             const int mm = mask ? 1 : ((flags & RBR_MASK_FROM_IDS) ? 2 : 0);
-            const bool i32 = (flags & RBR_IDS_I32) != 0;
+            const int i32 = (flags & RBR_IDS_U16) ? 2 : ((flags & RBR_IDS_I32) ? 1 : 0);
 #define RBR_SF(KT, I32, MM)                                                                                                              \
     cmat_scatter_fast_kernel<KT, IT, I32, MM><<<(unsigned)blocks, 256, (size_t)filters * 4, as_stream(stream)>>>(                        \
         ids_raw, mask, (int)n_docs, (int)doc_len, (int)filters, (int)pad, 0, (int)vocab, feat, argmax, feat_grad, (int)feat_ld,          \
@@ -570,8 +571,9 @@ static int cmat_scatter_block(const CmatLayout& l, const CmatChunk& k, const voi
     do {                                                                                      \
         if (ksize == 1) RBR_SF(1, I32, MM); else if (ksize == 3) RBR_SF(3, I32, MM); else RBR_SF(5, I32, MM); \
     } while (0)
-            if (i32) { if (mm == 0) RBR_SF_K(true, 0); else if (mm == 1) RBR_SF_K(true, 1); else RBR_SF_K(true, 2); }
-            else     { if (mm == 0) RBR_SF_K(false, 0); else if (mm == 1) RBR_SF_K(false, 1); else RBR_SF_K(false, 2); }
+            if (i32 == 2)      { if (mm == 0) RBR_SF_K(2, 0); else if (mm == 1) RBR_SF_K(2, 1); else RBR_SF_K(2, 2); }
+            else if (i32 == 1) { if (mm == 0) RBR_SF_K(1, 0); else if (mm == 1) RBR_SF_K(1, 1); else RBR_SF_K(1, 2); }
+            else               { if (mm == 0) RBR_SF_K(0, 0); else if (mm == 1) RBR_SF_K(0, 1); else RBR_SF_K(0, 2); }
 #undef RBR_SF_K
 #undef RBR_SF
             RBR_LAUNCH_CHECK("cmat_scatter_fast_kernel");

@@ -424,7 +424,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const Tc2Args a) {
         // takes several microseconds — longer than a tile.  So the id / mask rows of the unit T2_IDX_AHEAD unit steps ahead of
         // the stage-A cursor are pulled into L2 when the cursor enters a new unit (a whole document row: 128-byte lines spread
         // over the lanes), and stage B's loads are L2 hits.
-        const int idsz = a.ids.i32 ? 4 : 8;
+        const int idsz = a.ids.u16 ? 2 : a.ids.i32 ? 4 : 8;
         auto prefetch_unit = [&](int j) {
             // (long documents only: with several documents per tile every tile is a new unit, and the list loads in here —
             // waited for on the spot — cost the index warp more than the misses they avoid: NARRE shape, 6 % -> 36 % producer wait)
@@ -484,7 +484,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const Tc2Args a) {
                 vC[i] = vB[i];
                 if (!vB[i]) continue;
                 const int64_t at = (int64_t)docr[i] * p.L + tB[i];
-                if (a.ids.i32) rawid[i].x = __ldg(reinterpret_cast<const int32_t*>(a.ids.p) + at);
+                if (a.ids.u16) rawid[i].x = (int)__ldg(reinterpret_cast<const uint16_t*>(a.ids.p) + at);
+                else if (a.ids.i32) rawid[i].x = __ldg(reinterpret_cast<const int32_t*>(a.ids.p) + at);
                 else rawid[i] = __ldg(reinterpret_cast<const int2*>(a.ids.p) + at);
                 if (a.mask) rawm[i] = __ldg(a.mask + at);
             }
@@ -505,7 +506,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const Tc2Args a) {
             for (int i = 0; i < NS; ++i) {
                 mine[i] = -1;
                 if (vC[i]) {
-                    const int64_t id = a.ids.i32 ? (int64_t)rawid[i].x
+                    const int64_t id = (a.ids.i32 || a.ids.u16) ? (int64_t)rawid[i].x
                                                  : (int64_t)(((unsigned long long)(uint32_t)rawid[i].y << 32) | (uint32_t)rawid[i].x);
                     const bool ok = a.mask ? rawm[i] != 0 : (a.ids.mask_ids ? id != 0 : true);
                     if (ok) {

@@ -151,14 +151,16 @@ __device__ __forceinline__ float act_grad_from_out(int act, float y) {
 struct IdView {
     const void* p;
     int i32;         // ids are int32
+    int u16;         // ids are uint16
     int mask_ids;    // NULL mask → id != 0
 };
 __host__ __device__ inline IdView id_view(const void* ids, int flags) {
     IdView v;
-    v.p = ids; v.i32 = (flags & RBR_IDS_I32) ? 1 : 0; v.mask_ids = (flags & RBR_MASK_FROM_IDS) ? 1 : 0;
+    v.p = ids; v.i32 = (flags & RBR_IDS_I32) ? 1 : 0; v.u16 = (flags & RBR_IDS_U16) ? 1 : 0; v.mask_ids = (flags & RBR_MASK_FROM_IDS) ? 1 : 0;
     return v;
 }
 __device__ __forceinline__ int64_t ld_id(const IdView& v, int64_t i) {
+    if (v.u16) return (int64_t)__ldg(reinterpret_cast<const uint16_t*>(v.p) + i);
     return v.i32 ? (int64_t)__ldg(reinterpret_cast<const int32_t*>(v.p) + i) : __ldg(reinterpret_cast<const int64_t*>(v.p) + i);
 }
 __device__ __forceinline__ bool ld_mask(const IdView& v, const uint8_t* mask, int64_t i, int64_t id) {

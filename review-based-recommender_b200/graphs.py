@@ -29,7 +29,8 @@ class GraphedTrainStep:
     def __init__(self, model: torch.nn.Module, loss_fn: Callable, example_batch: Sequence[torch.Tensor],
                  example_ratings: torch.Tensor, restage_operands: bool = True, warmup: int = 3,
                  pool=None, device: Optional[torch.device] = None, post_backward: Optional[Callable[[], None]] = None,
-                 fuse_mse: bool = True, staged: bool = False, optimizer=None, max_grad_norm: Optional[float] = None):
+                 fuse_mse: bool = True, staged: bool = False, optimizer=None, max_grad_norm: Optional[float] = None,
+                 host_loss: bool = False):
         dev = device or next(model.parameters()).device
         if dev.type != "cuda":
             raise RuntimeError("GraphedTrainStep needs the model on a CUDA device")
@@ -65,8 +66,15 @@ class GraphedTrainStep:
         torch.cuda.synchronize(dev)
         self.graph = torch.cuda.CUDAGraph()
         model.zero_grad(set_to_none=True)
+        # host_loss=True: the step's loss is copied to pinned host memory by the graph's LAST node (`loss_host`, valid once the
+        # replay has finished), so a training loop that reads every step's loss puts nothing between two graph launches —
+        # a separate D2H copy (or an event wait) between them keeps the next graph from being staged while this one runs
+        # (measured: 0.77 -> 0.80 ms per DeepCoNN step for the 4-byte copy alone)
+        self.loss_host = torch.zeros(1, dtype=torch.float32).pin_memory() if host_loss else None
         with torch.cuda.graph(self.graph, pool=pool):
             self.loss = self._body()
+            if self.loss_host is not None:
+                self.loss_host.copy_(self.loss.detach().reshape(1), non_blocking=True)
         self.pool = self.graph.pool()
 
     def _body(self) -> torch.Tensor:

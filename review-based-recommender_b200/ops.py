@@ -18,7 +18,7 @@ PREC_FP32, PREC_BF16 = 0, 1
 ACT_RELU, ACT_TANH = 0, 1
 _PREC = {"fp32": PREC_FP32, "bf16": PREC_BF16}
 # per-call `flags` of the conv entry points (include/rbr_b200.h)
-CONV_TC_SINGLE_CTA, CONV_TC_PAIR_ONLY, CONV_BWD_DENSE_TC, CONV_BWD_SPARSE, IDS_I32, MASK_FROM_IDS = 1, 2, 4, 8, 16, 32
+CONV_TC_SINGLE_CTA, CONV_TC_PAIR_ONLY, CONV_BWD_DENSE_TC, CONV_BWD_SPARSE, IDS_I32, MASK_FROM_IDS, IDS_U16 = 1, 2, 4, 8, 16, 32, 64
 
 
 _STREAM_CACHE = [0, None]
@@ -60,16 +60,20 @@ def _req(t: torch.Tensor, dtype, name: str) -> torch.Tensor:
 
 
 def _ids(t: torch.Tensor, name: str) -> torch.Tensor:
-    """Token ids: int64 (torch.LongTensor, what the reference's collate_fn yields) or int32 (staged input pipeline)."""
+    """Token ids: int64 (torch.LongTensor, what the reference's collate_fn yields), or int32 / uint16 (staged input pipeline)."""
     if not isinstance(t, torch.Tensor) or not t.is_cuda:
         raise RuntimeError(f"rbr_b200: `{name}` must be a CUDA tensor (the hot path has no CPU implementation)")
-    if t.dtype not in (torch.int64, torch.int32):
-        raise TypeError(f"rbr_b200: `{name}` must be int64 or int32, got {t.dtype}")
+    if t.dtype not in (torch.int64, torch.int32, torch.uint16):
+        raise TypeError(f"rbr_b200: `{name}` must be int64, int32 or uint16, got {t.dtype}")
     return t if t.is_contiguous() else t.contiguous()
 
 
+def _id_width_flag(ids: torch.Tensor) -> int:
+    return IDS_I32 if ids.dtype == torch.int32 else (IDS_U16 if ids.dtype == torch.uint16 else 0)
+
+
 def _id_flags(ids: torch.Tensor, mask: Optional[torch.Tensor], mask_from_ids: bool) -> int:
-    return (IDS_I32 if ids.dtype == torch.int32 else 0) | (MASK_FROM_IDS if (mask is None and mask_from_ids) else 0)
+    return _id_width_flag(ids) | (MASK_FROM_IDS if (mask is None and mask_from_ids) else 0)
 
 
 def _mask_u8(mask: Optional[torch.Tensor], name: str) -> Optional[torch.Tensor]:
@@ -884,7 +888,7 @@ class DattEncodeFn(torch.autograd.Function):
         saved, feats, side_ctx = [], [], []
         for s in range(n_sides):
             ids = _ids(rest[s * stride], "token ids")
-            idf = IDS_I32 if ids.dtype == torch.int32 else 0
+            idf = _id_width_flag(ids)
             prm = [_req(t, torch.float32, "D-ATT parameter") for t in rest[s * stride + 1:(s + 1) * stride]]
             la_w, la_b, lc_w, lc_b, ga_w, ga_b = prm[:6]
             g_convs = [(prm[6 + 2 * i], prm[7 + 2 * i]) for i in range(3)]
@@ -966,7 +970,7 @@ class DattEncodeFn(torch.autograd.Function):
                        emb, dev):
         if True:
             n_docs, doc_len = ids.shape
-            idf = IDS_I32 if ids.dtype == torch.int32 else 0
+            idf = _id_width_flag(ids)
             la_w, la_b, lc_w, lc_b, ga_w, ga_b = prm[:6]
             convs = [(lc_w, lc_b, gate_l, 1, 2, 3)] + [(prm[6 + 2 * i], prm[7 + 2 * i], gate_g, 2, 6 + 2 * i, 7 + 2 * i)
                                                        for i in range(3)]

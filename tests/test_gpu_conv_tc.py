@@ -306,12 +306,12 @@ def test_dense_tc_backward_with_frozen_table_and_table_hook():
 
 @pytest.mark.parametrize("L,k,pad,n,H", [(500, 3, 1, 300, 100), (30, 3, 1, 4001, 150), (60, 5, 2, 777, 100), (200, 1, 0, 130, 64),
                                          (129, 4, 0, 67, 100), (1000, 7, 3, 70, 50), (14, 2, 0, 999, 100)])
-@pytest.mark.parametrize("i32", [False, True])
-def test_row_index_table_equals_index_warp(L, k, pad, n, H, i32):
+@pytest.mark.parametrize("width", [64, 32, 16])
+def test_row_index_table_equals_index_warp(L, k, pad, n, H, width):
     """The CTA-pair kernel gets its tile row indices either from the row-index table (conv_rowidx_kernel + bulk copies into
     the index buffers) or from its index warp resolving ids / masks itself, and with no scratch at all (no document selection):
     all three must agree bit for bit, and with the single-CTA kernel.  Short documents (several per tile, all-padding documents
-    dropped), long ones (tile skipping), k = 1 (no halo rows), explicit masks and masks derived from int32 ids."""
+    dropped), long ones (tile skipping), k = 1 (no halo rows), explicit masks and masks derived from int32 / uint16 ids."""
     gen = torch.Generator().manual_seed(L * 31 + k)
     V, E = 2000, 300 if L < 600 else 64
     table = torch.randn(V, E, generator=gen)
@@ -322,14 +322,15 @@ def test_row_index_table_equals_index_warp(L, k, pad, n, H, i32):
     lens[1::11] = L
     ids = torch.randint(1, V, (n, L), generator=gen)
     mask = torch.arange(L).unsqueeze(0) < lens.unsqueeze(1)
+    i32 = width != 64
     if not i32:
         mask = mask & (torch.rand(n, L, generator=gen) > 0.05)    # holes: an explicit mask that disagrees with ids != 0
     else:
         ids = ids * mask
     args = dict(precision="bf16")
     if i32:
-        call = lambda **kw: ops.conv_act_maxpool(table.cuda(), ids.int().cuda(), None, w.cuda(), b.cuda(), pad, mask_from_ids=True,
-                                                 **args, **kw)
+        narrow = ids.int().cuda() if width == 32 else ids.to(torch.uint16).cuda()
+        call = lambda **kw: ops.conv_act_maxpool(table.cuda(), narrow, None, w.cuda(), b.cuda(), pad, mask_from_ids=True, **args, **kw)
     else:
         call = lambda **kw: ops.conv_act_maxpool(table.cuda(), ids.cuda(), mask.cuda(), w.cuda(), b.cuda(), pad, **args, **kw)
     ref = call(flags=ops.CONV_TC_SINGLE_CTA)

@@ -118,10 +118,12 @@ def test_graphed_step_dual_att_matches_eager(precision):
                 assert rel_err(p.grad.cpu(), ref_grads[k].cpu(), 1e-9) < 2e-6, k
 
 
+@pytest.mark.parametrize("wire", ["uint16", "int32"])
 @pytest.mark.parametrize("model_name", ["deepconn", "narre", "dual_att"])
-def test_staged_inputs_int32_ids_and_derived_masks_match_the_reference_wire_format(model_name):
-    """one pinned arena per step (token ids int32, masks derived on the device as ids != 0) uploaded with one
-    copy into the graph's static inputs gives the same loss and gradients as int64 ids + bool masks, eager and graphed."""
+def test_staged_inputs_int32_ids_and_derived_masks_match_the_reference_wire_format(model_name, wire):
+    """one pinned arena per step (token ids uint16 — the vocabulary fits — or int32, masks derived on the device
+    as ids != 0) uploaded with one copy into the graph's static inputs gives the same loss and gradients as int64 ids + bool
+    masks, eager and graphed."""
     if model_name == "deepconn":
         model, (U, I, V, L) = _model(0.0, "bf16")
         mk = lambda seed: synth.deepconn_batch(32, L, V, U, I, seed=seed)
@@ -137,12 +139,15 @@ def test_staged_inputs_int32_ids_and_derived_masks_match_the_reference_wire_form
         model.load_state_dict(synth.dual_att_params(V, L, 5, 24, 16, E, 40, 10, seed=5))
         model.cuda().train()
         mk = lambda seed: synth.dual_att_batch(16, L, V, seed=seed)
+    if wire == "int32":                                                    # as for a vocabulary of more than 65536 rows
+        model.staging_spec = dict(model.staging_spec, vocab=1 << 20)
     host = [mk(s) for s in (5, 6, 7)]
     ref = [_eager_step(model, [t.cuda() for t in b], r.cuda()) for b, r in host]
     step = GraphedTrainStep(model, torch.nn.MSELoss(), [t.cuda() for t in host[0][0]], host[0][1].cuda(), staged=True)
     st = step.staged
     ref_bytes = sum(t.numel() * t.element_size() for t in host[0][0]) + host[0][1].numel() * 4
-    assert st.h2d_bytes < 0.52 * ref_bytes + 4096                          # int32 ids, no masks
+    assert st.token_dtype == (torch.uint16 if wire == "uint16" else torch.int32)
+    assert st.h2d_bytes < (0.52 if wire == "int32" else 0.30) * ref_bytes + 4096     # narrow ids, no masks
     assert all(v is None or v.dtype != torch.bool for v in st.batch)
     for (b, r), (ref_loss, ref_grads) in zip(host, ref):
         arena = st.pack(b, r)                                              # pinned host arena in wire format
