@@ -270,3 +270,22 @@ def test_conv_tc2_plan_invariants():
     assert out[0] == 1 and out[1] == 1 and out[2] == 112 and out[8] >= 6
     lib.rbr_conv_tc2_plan(300, 150, 3, 60, 1, 40960, ctypes.cast(out, ctypes.c_void_p))
     assert out[0] == 1 and out[1] == 1 and out[2] == 160 and out[10] == 1 and out[11] == 2 and out[12] == 64
+
+
+def test_conv_fwd_workspace_holds_the_row_index_table():
+    """rbr_conv_fwd_workspace_bytes2 = the document lists + one int32 per staged position of every document (and one all -1 row):
+    a row is `tiles * 128 + 8` entries with one document per tile (a tile's 136 indices are then one contiguous, 16-byte aligned
+    run for the index warp's bulk copy) or the slot stride S with several documents per tile (host code, no GPU)."""
+    import ctypes
+    from rbr_b200._lib import lib
+    out = (ctypes.c_int64 * 16)()
+    for E, H, K, L, pad, n in [(300, 100, 3, 500, 1, 4096), (300, 150, 3, 60, 1, 40960), (300, 100, 5, 1000, 2, 333), (300, 100, 1, 200, 0, 130),
+                               (300, 100, 4, 129, 0, 67), (300, 100, 2, 14, 0, 999)]:
+        lib.rbr_conv_tc2_plan(E, H, K, L, pad, n, ctypes.cast(out, ctypes.c_void_p))
+        assert out[0] == 1
+        mode_b, S, tpu = out[10], out[12], out[13]
+        rs = S if mode_b else tpu * 128 + 8
+        assert rs % 4 == 0 and rs >= L + 2 * pad
+        base = lib.rbr_conv_fwd_workspace_bytes(n)
+        assert base % 256 == 0                                                       # the table starts 16-byte aligned behind the lists
+        assert lib.rbr_conv_fwd_workspace_bytes2(n, L, K, pad) == base + (n + 1) * rs * 4
