@@ -310,9 +310,14 @@ def measure(ctx, name, args):
     ar_kind = None
     if world > 1 and train:
         ar_kind = "nccl"
-        if args.allreduce == "nvls" and args.grad_allreduce == "fp32":
-            ar_kind = ("nvls-multimem (own kernel), word-table slice overlapped with the weight-gradient kernels"
-                       if parallel.enable_nvls_allreduce(model, overlap=True) else "nccl (no NVLS multicast)")
+        if args.allreduce != "nccl" and args.grad_allreduce == "fp32":
+            kind = {"nvls": "auto", "multimem": "multimem", "p2p": "p2p"}[args.allreduce]
+            if parallel.enable_nvls_allreduce(model, overlap=True, kind=kind):
+                k = model.__dict__["_rbr_nvls"].kind
+                ar_kind = (("own kernel over the symmetric-memory arena: peer loads / stores (rbr_p2p_allreduce_f32)" if k == "p2p" else
+                            "nvls-multimem (own kernel)") + ", word-table slice overlapped with the weight-gradient kernels")
+            else:
+                ar_kind = "nccl (no NVLS multicast)"
     compress = "bf16" if args.grad_allreduce == "bf16" else None
     post = (lambda: parallel.allreduce_gradients(model, compress=compress)) if (world > 1 and train) else None
     NB = 4   # distinct input batches rotated through: 4 x 37 MB of ids+masks > L2 together with table/grad traffic
@@ -878,9 +883,10 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--grad-allreduce", default="fp32", choices=["fp32", "bf16"],
                     help="wire dtype of the data-parallel gradient all-reduce (bf16 = optional compression, rounds the averaged gradient)")
-    ap.add_argument("--allreduce", default="nvls", choices=["nvls", "nccl"],
-                    help="nvls = the library's own multimem kernel through the NVSwitch on a symmetric-memory gradient arena "
-                         "(falls back to nccl when multicast is unavailable); nccl = one ncclAllReduce of the arena")
+    ap.add_argument("--allreduce", default="nvls", choices=["nvls", "multimem", "p2p", "nccl"],
+                    help="nvls = the library's own kernels on a symmetric-memory gradient arena: peer loads / stores on 2 GPUs, the "
+                         "multimem kernel through the NVSwitch above (falls back to nccl when multicast is unavailable); multimem / "
+                         "p2p force one of the two; nccl = one ncclAllReduce of the arena")
     ap.add_argument("--graphs", default="auto", choices=["auto", "off"],
                     help="auto: the timed loops replay CUDA graphs of the step (rbr_b200.graphs.GraphedTrainStep, one per rotating "
                          "batch; at N>1 the gradient exchange is captured with it), so host scheduling jitter cannot make them "

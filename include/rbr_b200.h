@@ -324,6 +324,13 @@ int rbr_clip_adam_step(float* params, const float* grads, float* exp_avg, float*
  * max_ctas <= 0 selects the default grid (32 CTAs: link-bound from 16 up, leaves the SMs to concurrent kernels).           */
 int rbr_multimem_allreduce_f32(void* multicast_ptr, int64_t n_floats, int rank, int world, float scale, int max_ctas,
                                void* stream);
+/* The same exchange with plain peer loads / stores instead of the switch reduction: `peer_ptrs` is a HOST array of `world`
+ * device addresses (rank order; every GPU's copy of the arena, peer-mapped — torch symmetric memory's buffer_ptrs), the range
+ * [offset_floats, offset_floats + n_floats) is reduced.  Each rank sums ITS 1/world slice over all copies in rank order, scales
+ * and writes the result into every copy: (world-1)/world * N link bytes per GPU and direction instead of ~(1 + 1/world) * N.
+ * Same barrier contract as above.  world in {2, 4, 8}; max_ctas <= 0: 64 CTAs.                                                  */
+int rbr_p2p_allreduce_f32(const void* peer_ptrs, int64_t offset_floats, int64_t n_floats, int rank, int world, float scale,
+                          int max_ctas, void* stream);
 
 #ifdef __cplusplus
 }

@@ -93,21 +93,45 @@ def enable_overlap(model: torch.nn.Module, group=None) -> None:
 
 
 class _NvlsState:
-    def __init__(self, hdl, mc, n, rank, world, device, overlap):
+    def __init__(self, hdl, mc, n, rank, world, device, overlap, kind="multimem"):
         self.hdl, self.mc, self.n, self.rank, self.world = hdl, mc, n, rank, world
+        # kind "p2p": plain peer loads / stores over the symmetric-memory peer mappings (rbr_p2p_allreduce_f32) — fewer link
+        # bytes than the switch reduction for small worlds; "multimem": the NVLS kernel
+        self.kind = kind
+        self.peers = None
+        if kind == "p2p":
+            import ctypes
+            ptrs = [int(x) for x in hdl.buffer_ptrs]
+            self.peers = (ctypes.c_uint64 * len(ptrs))(*ptrs)
         self.overlap = overlap
         self.side = torch.cuda.Stream(device=device, priority=-1) if overlap else None
         self.ev_ready = torch.cuda.Event() if overlap else None
         self.ev_done = torch.cuda.Event() if overlap else None
         self.early: Optional[tuple] = None          # (lo, hi) float range already being reduced on the side stream
 
+    def reduce(self, lo: int, cnt: int, scale: float, stream: int) -> None:
+        """All-reduce floats [lo, lo + cnt) of the arena on `stream` (between the caller's two cross-GPU barriers)."""
+        from ._lib import lib
+        if self.kind == "p2p":
+            import ctypes
+            lib.check(lib.rbr_p2p_allreduce_f32(ctypes.cast(self.peers, ctypes.c_void_p), lo, cnt, self.rank, self.world, scale, 0, stream),
+                      "rbr_p2p_allreduce_f32")
+        else:
+            lib.check(lib.rbr_multimem_allreduce_f32(self.mc + 4 * lo, cnt, self.rank, self.world, scale, 0, stream),
+                      "rbr_multimem_allreduce_f32")
 
-def enable_nvls_allreduce(model: torch.nn.Module, group=None, overlap: bool = True) -> bool:
+
+def enable_nvls_allreduce(model: torch.nn.Module, group=None, overlap: bool = True, kind: str = "auto") -> bool:
     """Put the model's flat gradient arena in symmetric memory (torch.distributed._symmetric_memory) and let
     allreduce_gradients() reduce it with the library's own NVLS kernel (rbr_multimem_allreduce_f32: multimem.ld_reduce /
     multimem.st through the NVSwitch, 1/world folded in) instead of ncclAllReduce.  Collective call (every rank, after
     init and before the first training step).  Returns False — and leaves the NCCL path in place — when the GPUs have
     no NVLS multicast support.
+
+    kind: "multimem" (the switch reduces), "p2p" (plain peer loads / stores: a third of the link bytes at world 2, 0.6 at 4),
+    "auto" = p2p for world 2, multimem above.  Measured on the 64.6 MB arena, barriers included (tools/allreduce_sweep.py):
+    world 2: p2p 113 us, multimem 180 us, ncclAllReduce 148 us; world 4: p2p 165 us, multimem 163 us (with a quarter of the
+    CTAs, which matters for the overlapped word-table slice), ncclAllReduce 185 us.
 
     overlap=True: the word-embedding gradient (≈ 90 % of the bytes) is reduced on a side stream from inside backward,
     as soon as the table gradients of all document sides are complete (ops.EncodeDocsFn runs them first), concurrently
@@ -139,7 +163,12 @@ def enable_nvls_allreduce(model: torch.nn.Module, group=None, overlap: bool = Tr
         return False
     ngram = getattr(model, "ngram", None)
     overlap = bool(overlap and ngram is not None and hasattr(ngram, "table_grad_hook"))
-    st = _NvlsState(hdl, mc, n, dist.get_rank(group), dist.get_world_size(group), dev, overlap)
+    world = dist.get_world_size(group)
+    if kind == "auto":
+        kind = os.environ.get("RBR_ALLREDUCE_KIND", "p2p" if world == 2 else "multimem")
+    if kind == "p2p" and world not in (2, 4, 8):
+        kind = "multimem"
+    st = _NvlsState(hdl, mc, n, dist.get_rank(group), world, dev, overlap, kind)
     model.__dict__["_rbr_arena_buffer"] = buf
     model.__dict__["_rbr_nvls"] = st
     if overlap:
@@ -155,8 +184,7 @@ def enable_nvls_allreduce(model: torch.nn.Module, group=None, overlap: bool = Tr
             with torch.cuda.stream(st.side):
                 st.side.wait_event(st.ev_ready)
                 hdl.barrier(channel=2)          # every rank's table gradient is complete
-                lib.check(lib.rbr_multimem_allreduce_f32(mc + 4 * lo, cnt, st.rank, st.world, 1.0 / st.world, 0,
-                                                         st.side.cuda_stream), "rbr_multimem_allreduce_f32")
+                st.reduce(lo, cnt, 1.0 / st.world, st.side.cuda_stream)
                 hdl.barrier(channel=3)
                 st.ev_done.record(st.side)
             # called once per row slice of the table gradient (consecutive slices): the reduced range grows
@@ -181,8 +209,7 @@ def _nvls_allreduce(model: torch.nn.Module, flat: torch.Tensor, average: bool) -
         ranges = [r for r in ((0, lo), (hi, st.n)) if r[1] > r[0]]
     st.hdl.barrier(channel=0)                   # every rank has finished writing its gradients (stream-ordered, device side)
     for lo, hi in ranges:
-        lib.check(lib.rbr_multimem_allreduce_f32(st.mc + 4 * lo, hi - lo, st.rank, st.world, scale, 0, main.cuda_stream),
-                  "rbr_multimem_allreduce_f32")
+        st.reduce(lo, hi - lo, scale, main.cuda_stream)
     st.hdl.barrier(channel=1)                   # every slice has been broadcast before anyone reads the result
     if st.early is not None:
         main.wait_event(st.ev_done)             # the overlapped word-table reduction

@@ -70,10 +70,11 @@ rank, local, world = parallel.init_from_env("nccl")
 torch.cuda.set_device(local)
 from rbr_b200.graphs import GraphedTrainStep
 results = {}
-for overlap in (False, True):
+for overlap, kind in ((False, "multimem"), (True, "multimem"), (False, "p2p"), (True, "p2p")):
     model = build("bf16")
     parallel.broadcast_parameters(model)
-    ok = parallel.enable_nvls_allreduce(model, overlap=overlap)
+    ok = parallel.enable_nvls_allreduce(model, overlap=overlap, kind=kind)
+    assert not ok or model.__dict__["_rbr_nvls"].kind == kind
     if not ok:
         print("rank", rank, "SKIP no NVLS multicast")
         dist.barrier(); dist.destroy_process_group(); sys.exit(0)
@@ -95,14 +96,14 @@ for overlap in (False, True):
         assert n == 1
         torch.cuda.synchronize()
         err = rel(model.last_arena.flat, expect)
-        assert err < 2e-6, (overlap, trial, err)
+        assert err < 2e-6, (kind, overlap, trial, err)
     # the same exchange captured in a CUDA graph with the step
     gs = GraphedTrainStep(model, torch.nn.MSELoss(), batch, ratings, post_backward=lambda: parallel.allreduce_gradients(model))
     for trial in range(3):
         gs.replay()
         torch.cuda.synchronize()
         err = rel(model.last_arena.flat, expect)
-        assert err < 2e-6, ("graph", overlap, trial, err)
+        assert err < 2e-6, ("graph", kind, overlap, trial, err)
     # gradient accumulation into the persistent arena is refused, not silently wiped
     model.zero_grad(set_to_none=False)
     try:
