@@ -289,3 +289,29 @@ def test_conv_fwd_workspace_holds_the_row_index_table():
         base = lib.rbr_conv_fwd_workspace_bytes(n)
         assert base % 256 == 0                                                       # the table starts 16-byte aligned behind the lists
         assert lib.rbr_conv_fwd_workspace_bytes2(n, L, K, pad) == base + (n + 1) * rs * 4
+
+
+def test_staged_inputs_wire_format_on_cpu():
+    """staging.StagedInputs host logic (no GPU): token ids travel as uint16 when the vocabulary fits and as int32 otherwise, masks
+    are not sent, everything else travels unchanged; `pack` refuses ids that would alias under the narrowing."""
+    import pytest
+    from rbr_b200 import synth
+    from rbr_b200.staging import StagedInputs
+    batch, ratings = synth.deepconn_batch(16, 40, 600, 50, 30, seed=3)
+    ref_bytes = sum(t.numel() * t.element_size() for t in batch) + ratings.numel() * 4
+    for vocab, dt, frac in ((600, torch.uint16, 0.30), (65536, torch.uint16, 0.30), (65537, torch.int32, 0.52), (None, torch.int32, 0.52)):
+        st = StagedInputs(batch, ratings, "cpu", vocab=vocab)
+        assert st.token_dtype == dt and st.batch[0].dtype == dt and st.batch[2] is None and st.batch[3] is None
+        assert st.h2d_bytes % 256 == 0 and st.h2d_bytes < frac * ref_bytes + 6 * 256
+        host = st.pack(batch, ratings, out=torch.empty(st.nbytes, dtype=torch.uint8))
+        st.dev.copy_(host)                                   # the one H2D copy
+        assert torch.equal(st.batch[0].to(torch.int64), batch[0]) and torch.equal(st.batch[1].to(torch.int64), batch[1])
+        assert torch.equal(st.batch[4], batch[4]) and torch.equal(st.batch[5], batch[5]) and torch.equal(st.ratings, ratings)
+    st = StagedInputs(batch, ratings, "cpu", vocab=600)
+    bad = [t.clone() for t in batch]
+    bad[0][0, 0] = 70000
+    with pytest.raises(ValueError, match="uint16"):
+        st.pack(bad, ratings, out=torch.empty(st.nbytes, dtype=torch.uint8))
+    # masks that are NOT ids != 0 can still be sent
+    st = StagedInputs(batch, ratings, "cpu", vocab=600, derive_masks=False)
+    assert st.batch[2] is not None and st.batch[2].dtype == torch.uint8
